@@ -734,6 +734,7 @@ void minimise(Problem& prob, double x[kNumParams], const oracle_solver_options& 
 
     double scale[kNumParams], diag[kNumParams], D[kNumParams], step[kNumParams], grad[kNumParams];
     double best_x[kNumParams];
+    const bool trace = std::getenv("PPCR_ORACLE_TRACE") != nullptr;
 
     // iteration zero
     double x_cost = prob.evaluate_full(x);
@@ -804,10 +805,13 @@ void minimise(Problem& prob, double x[kNumParams], const oracle_solver_options& 
         step_norm = std::sqrt(step_norm);
         double cand_cost = prob.evaluate_cost(cand);
 
+        if (trace && (step_norm <= kParamTol * (x_norm + kParamTol) || std::fabs(x_cost - cand_cost) <= opt.function_tolerance * x_cost))
+            std::fprintf(stderr, "  [oracle lm] it %d terminating: x_cost %.12g cand %.12g step %.3g\n", iteration, x_cost, cand_cost, step_norm);
         if (step_norm <= kParamTol * (x_norm + kParamTol)) { termination = 1; break; }
         if (std::fabs(x_cost - cand_cost) <= opt.function_tolerance * x_cost) { termination = 0; break; }
 
         double quality = ev.quality(cand_cost, model_change);
+        if (trace) std::fprintf(stderr, "  [oracle lm] it %d x_cost %.12g cand %.12g model %.6g quality %.6g radius %.4g step %.3g\n", iteration, x_cost, cand_cost, model_change, quality, radius, step_norm);
         if (quality > kMinRelDecrease) {  // HandleSuccessfulStep
             std::copy(cand, cand + kNumParams, x);
             x_norm = 0;

@@ -1,0 +1,1333 @@
+// ppcr_capi.cu -- host side of libppcr_cuda.so: device memory, the tick driver (host-stepped or a CUDA-graph
+// WHILE loop), and the extern "C" entry points declared in include/ppcr.h.
+//
+// Nothing in this file computes on the CPU: it sizes buffers, launches the kernels of ppcr_kernels.cuh and copies
+// results back.  If no CUDA device is usable every entry point fails (PPCR_ERR_NO_DEVICE); there is no fallback.
+#include "../../include/ppcr.h"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ppcr_kernels.cuh"
+
+using namespace ppcr;
+
+static_assert(sizeof(ppcr_iter_stats) == sizeof(IterStats), "stats layout");
+
+// ------------------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------------------
+
+static thread_local std::string g_last_error;
+
+static ppcr_status fail(ppcr_status code, const std::string& msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+struct CudaError {
+    cudaError_t err;
+    const char* what;
+    int line;
+};
+
+#define CK(call)                                                 \
+    do {                                                         \
+        cudaError_t e__ = (call);                                \
+        if (e__ != cudaSuccess) throw CudaError{e__, #call, __LINE__}; \
+    } while (0)
+
+static ppcr_status translate(const CudaError& e)
+{
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) at ppcr_capi.cu:%d: %s", static_cast<int>(e.err),
+             cudaGetErrorString(e.err), e.line, e.what);
+    cudaGetLastError();
+    if (e.err == cudaErrorNoDevice || e.err == cudaErrorInsufficientDriver || e.err == cudaErrorInvalidDevice)
+        return fail(PPCR_ERR_NO_DEVICE, buf);
+    return fail(PPCR_ERR_CUDA, buf);
+}
+
+struct StatusError {
+    ppcr_status code;
+    std::string msg;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// device buffers (grow-only, so batch slots can be reused without re-allocating)
+// ------------------------------------------------------------------------------------------------------------
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n)
+    {
+        if (n <= cap) return;
+        if (p) CK(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 64;
+        CK(cudaMalloc(&p, want * sizeof(T)));
+        cap = want;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+static int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+static int g_sm_count = 0;
+
+// ------------------------------------------------------------------------------------------------------------
+// one pair: its buffers and the host mirror of its PairDev
+// ------------------------------------------------------------------------------------------------------------
+
+struct Pair {
+    DevBuf<float4> src, tgt_raw, tgt_sorted, tmp_cloud;
+    DevBuf<int> cell_start, cell_of, rank, nbr_idx, nbr_cnt, scan_sums;
+    DevBuf<float> nbr_x, nbr_y, nbr_z, nbr_d2;
+    DevBuf<double> partials, history, mailbox;
+    DevBuf<PairState> state;
+    DevBuf<Config> cfg;
+    DevBuf<IterStats> stats;
+    DevBuf<unsigned> scratch_u;
+    DevBuf<unsigned long long> scratch_ull;
+    PairDev dev{};
+    Config hcfg{};
+    int64_t n_src = 0, n_tgt = 0;
+    bool want_d2 = false;
+    void release()
+    {
+        src.release(); tgt_raw.release(); tgt_sorted.release(); tmp_cloud.release();
+        cell_start.release(); cell_of.release(); rank.release(); nbr_idx.release(); nbr_cnt.release();
+        scan_sums.release(); nbr_x.release(); nbr_y.release(); nbr_z.release(); nbr_d2.release();
+        partials.release(); history.release(); mailbox.release(); state.release(); cfg.release(); stats.release();
+        scratch_u.release(); scratch_ull.release();
+    }
+};
+
+struct EventPair {
+    cudaEvent_t a, b;
+    int stage;
+};
+
+struct Engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    ppcr_params params{};
+    ppcr_options opts{};
+    std::vector<Pair> pairs;
+    DevBuf<PairDev> d_pairs;
+    DevBuf<int> d_active;
+    int* h_active = nullptr;  // pinned
+    int lists_R = 1;
+    size_t search_smem = 0;
+    // launch geometry (capacity based, so a captured graph stays valid while the slots are refilled)
+    int max_tiles = 1, max_eval_blocks = 1, max_tr_blocks = 1;
+    bool skip_search = false;
+    int max_ticks = 0;
+    // graph driver
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraphConditionalHandle cond = 0;
+    bool graph_ready = false;
+    bool graph_failed = false;
+    // stage timing
+    std::vector<EventPair> events;
+    ppcr_stage_times times{};
+    // sharded mode
+    int rank = 0, world = 1;
+    std::vector<void*> peer_ptrs;
+    // L2 flush buffer for ppcr_time_kernel
+    DevBuf<float4> flush;
+
+    ~Engine()
+    {
+        cudaSetDevice(device);
+        for (auto& e : events) {
+            cudaEventDestroy(e.a);
+            cudaEventDestroy(e.b);
+        }
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        if (graph) cudaGraphDestroy(graph);
+        for (size_t r = 0; r < peer_ptrs.size(); ++r)
+            if (peer_ptrs[r] && static_cast<int>(r) != rank) cudaIpcCloseMemHandle(peer_ptrs[r]);
+        for (auto& p : pairs) p.release();
+        d_pairs.release();
+        d_active.release();
+        flush.release();
+        if (h_active) cudaFreeHost(h_active);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+struct ppcr_handle {
+    Engine eng;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// device selection
+// ------------------------------------------------------------------------------------------------------------
+
+static void select_device(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        throw StatusError{PPCR_ERR_NO_DEVICE, "no CUDA device is visible; libppcr_cuda has no CPU fallback"};
+    }
+    if (device < 0 || device >= count) throw StatusError{PPCR_ERR_NO_DEVICE, "device ordinal out of range"};
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        throw StatusError{PPCR_ERR_NO_DEVICE, std::string("libppcr_cuda is built for sm_100a only; device is ") + prop.name};
+    g_sm_count = prop.multiProcessorCount;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// scans, grid build
+// ------------------------------------------------------------------------------------------------------------
+
+// in-place exclusive scan of data[0..n); the grand total is also written to data[n] when write_total
+static void exclusive_scan(int* data, int n, DevBuf<int>& sums, bool write_total, cudaStream_t st)
+{
+    const int n_blocks = ceil_div(n, kScanTile);
+    sums.reserve(static_cast<size_t>(n_blocks) + 1);
+    k_scan_local<<<n_blocks, kScanThreads, 0, st>>>(data, n, sums.p);
+    k_scan_sums<<<1, 1024, 0, st>>>(sums.p, n_blocks, write_total ? data + n : nullptr);
+    k_scan_add<<<n_blocks, kScanThreads, 0, st>>>(data, n, sums.p, 0);
+    CK(cudaGetLastError());
+}
+
+struct Bbox {
+    float lo[3], hi[3];
+};
+
+static Bbox cloud_bbox(const float4* pts, int n, Pair& P, cudaStream_t st)
+{
+    P.scratch_u.reserve(8);
+    unsigned init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    CK(cudaMemcpyAsync(P.scratch_u.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    k_bbox<<<std::min(ceil_div(n, 256), 4 * std::max(g_sm_count, 1)), 256, 0, st>>>(pts, n, P.scratch_u.p);
+    CK(cudaGetLastError());
+    unsigned out[6];
+    CK(cudaMemcpyAsync(out, P.scratch_u.p, sizeof(out), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    Bbox b;
+    for (int k = 0; k < 3; ++k) {
+        b.lo[k] = ord2f(out[k]);
+        b.hi[k] = ord2f(out[3 + k]);
+    }
+    return b;
+}
+
+static GridDev make_grid(const Bbox& b, double h, double radius, long long max_cells)
+{
+    GridDev g{};
+    double ext[3];
+    for (int k = 0; k < 3; ++k) ext[k] = std::max(0.0, static_cast<double>(b.hi[k]) - b.lo[k]);
+    for (;;) {
+        const float inv = static_cast<float>(1.0 / h);
+        long long cells = 1;
+        int dims[3];
+        for (int k = 0; k < 3; ++k) {
+            dims[k] = static_cast<int>(std::floor(static_cast<float>(b.hi[k] - b.lo[k]) * inv)) + 2;
+            cells *= dims[k];
+        }
+        if (cells <= max_cells) {
+            g.ox = b.lo[0];
+            g.oy = b.lo[1];
+            g.oz = b.lo[2];
+            g.inv_h = inv;
+            g.nx = dims[0];
+            g.ny = dims[1];
+            g.nz = dims[2];
+            g.n_cells = static_cast<int>(cells);
+            break;
+        }
+        h *= std::cbrt(static_cast<double>(cells) / static_cast<double>(max_cells)) * 1.02;
+    }
+    g.h_cover = static_cast<float>((1.0 / static_cast<double>(g.inv_h)) * (1.0 - 1e-6));
+    const double span = std::max({ext[0], ext[1], ext[2]}) + radius;
+    g.cover_slack = static_cast<float>(16.0 * FLT_EPSILON * span + 1e-30);
+    return g;
+}
+
+// counting sort of the target into grid cells; chooses the cell edge from the measured occupancy
+static void build_target_grid(Engine& E, Pair& P, float cell_size_opt, long long max_cells)
+{
+    cudaStream_t st = E.stream;
+    const int n = static_cast<int>(P.n_tgt);
+    const double radius = E.params.radius;
+    const int m = P.dev.m;
+    const Bbox bb = cloud_bbox(P.tgt_raw.p, n, P, st);
+    for (int k = 0; k < 3; ++k)
+        if (!std::isfinite(bb.lo[k]) || !std::isfinite(bb.hi[k]))
+            throw StatusError{PPCR_ERR_INVALID, "target cloud contains non-finite coordinates"};
+    double ext[3];
+    for (int k = 0; k < 3; ++k) ext[k] = std::max(1e-6, static_cast<double>(bb.hi[k]) - bb.lo[k]);
+    std::sort(ext, ext + 3);
+    const double target_occ = std::max(1.5, m / 3.0);
+    double h;
+    const bool fixed = cell_size_opt > 0.f;
+    if (fixed) {
+        h = cell_size_opt;
+    } else {
+        h = std::sqrt(ext[2] * ext[1] * target_occ / std::max(1, n));  // surface-like first guess
+    }
+    const double h_min = radius / 32.0, h_max = radius;
+    h = std::min(std::max(h, h_min), h_max);
+    P.cell_of.reserve(n);
+    P.rank.reserve(n);
+    P.scratch_ull.reserve(2);
+    GridDev g{};
+    for (int trial = 0; trial < 5; ++trial) {
+        g = make_grid(bb, h, radius, max_cells);
+        P.cell_start.reserve(static_cast<size_t>(g.n_cells) + 2);
+        CK(cudaMemsetAsync(P.cell_start.p, 0, (static_cast<size_t>(g.n_cells) + 2) * sizeof(int), st));
+        k_cell_count<<<ceil_div(n, 256), 256, 0, st>>>(P.tgt_raw.p, n, g, P.cell_start.p, P.cell_of.p, P.rank.p);
+        CK(cudaGetLastError());
+        if (fixed || trial == 4) break;
+        CK(cudaMemsetAsync(P.scratch_ull.p, 0, sizeof(unsigned long long), st));
+        k_count_occupied<<<std::min(ceil_div(g.n_cells, 256), 8 * std::max(g_sm_count, 1)), 256, 0, st>>>(P.cell_start.p, g.n_cells, P.scratch_ull.p);
+        unsigned long long occ = 0;
+        CK(cudaMemcpyAsync(&occ, P.scratch_ull.p, sizeof(occ), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const double avg = static_cast<double>(n) / static_cast<double>(std::max<unsigned long long>(occ, 1));
+        const double h_eff = 1.0 / static_cast<double>(g.inv_h);
+        if (avg > target_occ / 1.5 && avg < target_occ * 1.5) break;
+        double h_new = h_eff * std::pow(target_occ / avg, 0.45);
+        h_new = std::min(std::max(h_new, h_min), h_max);
+        if (std::fabs(h_new - h_eff) < 0.05 * h_eff) break;
+        h = h_new;
+    }
+    exclusive_scan(P.cell_start.p, g.n_cells, P.scan_sums, true, st);
+    P.tgt_sorted.reserve(n);
+    k_cell_scatter<<<ceil_div(n, 256), 256, 0, st>>>(P.tgt_raw.p, n, P.cell_start.p, P.cell_of.p, P.rank.p, P.tgt_sorted.p);
+    CK(cudaGetLastError());
+    P.dev.grid = g;
+    P.dev.tgt_sorted = P.tgt_sorted.p;
+    P.dev.cell_start = P.cell_start.p;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// voxel filter
+// ------------------------------------------------------------------------------------------------------------
+
+// Filters `in` (n points) into `out`; returns the filtered size, or -1 when PCL would refuse the leaf size.
+static int64_t voxel_filter_device(const float4* in, int64_t n, double leaf_d, DevBuf<float4>& out, Pair& scratch,
+                                   cudaStream_t st)
+{
+    if (n == 0) return 0;
+    const float leaf = static_cast<float>(leaf_d);
+    const float inv = 1.0f / leaf;
+    const Bbox bb = cloud_bbox(in, static_cast<int>(n), scratch, st);
+    int64_t d[3];
+    VoxelGeom vg{};
+    vg.inv_leaf = inv;
+    int div[3];
+    for (int k = 0; k < 3; ++k) {
+        d[k] = static_cast<int64_t>((bb.hi[k] - bb.lo[k]) * inv) + 1;
+        vg.minb[k] = static_cast<int>(std::floor(bb.lo[k] * inv));
+        div[k] = static_cast<int>(std::floor(bb.hi[k] * inv)) - vg.minb[k] + 1;
+    }
+    if (d[0] * d[1] * d[2] > static_cast<int64_t>(INT_MAX)) return -1;
+    vg.mul[0] = 1;
+    vg.mul[1] = div[0];
+    vg.mul[2] = div[0] * div[1];
+    DevBuf<unsigned> keys, vals, keys2, vals2;
+    DevBuf<int> head;
+    DevBuf<unsigned char> tmp;
+    const int ni = static_cast<int>(n);
+    keys.reserve(n); vals.reserve(n); keys2.reserve(n); vals2.reserve(n); head.reserve(n + 2);
+    k_voxel_keys<<<ceil_div(n, 256), 256, 0, st>>>(in, ni, vg, keys.p, vals.p);
+    CK(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys2.p, vals.p, vals2.p, ni, 0, 32, st));
+    tmp.reserve(tmp_bytes);
+    CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys2.p, vals.p, vals2.p, ni, 0, 32, st));  // stable
+    k_voxel_heads<<<ceil_div(n, 256), 256, 0, st>>>(keys2.p, ni, head.p);
+    CK(cudaGetLastError());
+    exclusive_scan(head.p, ni, scratch.scan_sums, true, st);
+    int n_out = 0;
+    CK(cudaMemcpyAsync(&n_out, head.p + ni, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    out.reserve(static_cast<size_t>(n_out) + 1);
+    k_voxel_mean<<<ceil_div(n, 256), 256, 0, st>>>(in, keys2.p, vals2.p, head.p, ni, out.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    keys.release(); vals.release(); keys2.release(); vals2.release(); head.release(); tmp.release();
+    return n_out;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pair / engine setup
+// ------------------------------------------------------------------------------------------------------------
+
+static void validate_params(const ppcr_params& p)
+{
+    if (p.max_neighbours < 1 || p.max_neighbours > 128)
+        throw StatusError{PPCR_ERR_UNSUPPORTED, "max_neighbours must be in [1,128] (0/negative = unlimited is not implemented)"};
+    if (!(p.radius > 0.0) || !std::isfinite(p.radius)) throw StatusError{PPCR_ERR_INVALID, "radius must be finite and > 0"};
+    if (!(p.dof > 0.0)) throw StatusError{PPCR_ERR_INVALID, "dof must be > 0 (+inf selects the Gaussian model)"};
+    if (p.n_iter < 0) throw StatusError{PPCR_ERR_INVALID, "n_iter must be >= 0"};
+}
+
+static void upload_cloud(DevBuf<float4>& dst, const float* src, int64_t n, bool on_device, cudaStream_t st)
+{
+    dst.reserve(static_cast<size_t>(std::max<int64_t>(n, 1)));
+    if (n > 0)
+        CK(cudaMemcpyAsync(dst.p, src, static_cast<size_t>(n) * sizeof(float4),
+                           on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+}
+
+// Everything the reference constructor does (registration.cc:15-49) plus the grid build that replaces the
+// per-iteration kd-tree construction (:66-67; the target never changes after the constructor).
+static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, const float* tgt, int64_t n_tgt,
+                       bool on_device, long long max_cells)
+{
+    if (n_src < 0 || n_tgt < 0 || (n_src > 0 && !src) || (n_tgt > 0 && !tgt)) throw StatusError{PPCR_ERR_INVALID, "null cloud"};
+    if (n_src > INT_MAX / 2 || n_tgt > INT_MAX / 2) throw StatusError{PPCR_ERR_UNSUPPORTED, "clouds above 2^30 points are not supported"};
+    cudaStream_t st = E.stream;
+    const ppcr_params& prm = E.params;
+    upload_cloud(P.src, src, n_src, on_device, st);
+    upload_cloud(P.tgt_raw, tgt, n_tgt, on_device, st);
+    P.n_src = n_src;
+    P.n_tgt = n_tgt;
+    if (prm.source_filter_size > 0 && n_src > 0) {
+        int64_t k = voxel_filter_device(P.src.p, n_src, prm.source_filter_size, P.tmp_cloud, P, st);
+        if (k >= 0) {
+            std::swap(P.src, P.tmp_cloud);
+            P.n_src = k;
+        }
+    }
+    if (prm.target_filter_size > 0 && n_tgt > 0) {
+        int64_t k = voxel_filter_device(P.tgt_raw.p, n_tgt, prm.target_filter_size, P.tmp_cloud, P, st);
+        if (k >= 0) {
+            std::swap(P.tgt_raw, P.tmp_cloud);
+            P.n_tgt = k;
+        }
+    }
+    PairDev& D = P.dev;
+    D.n_src = static_cast<int>(P.n_src);
+    D.n_tgt = static_cast<int>(P.n_tgt);
+    D.n_pad = (D.n_src + 31) / 32 * 32;
+    if (D.n_pad == 0) D.n_pad = 32;
+    D.m = static_cast<int>(std::min<int64_t>(prm.max_neighbours, std::max<int64_t>(P.n_tgt, 1)));
+    D.r2f = static_cast<float>(prm.radius * prm.radius);
+    D.rpad = std::nextafter(static_cast<float>(prm.radius * (1.0 + 1e-5)), INFINITY);
+    D.src = P.src.p;
+    if (D.n_src > 0) {
+        k_tag_index<<<ceil_div(D.n_src, 256), 256, 0, st>>>(P.src.p, D.n_src);
+        CK(cudaGetLastError());
+    }
+    if (P.n_tgt > 0) {
+        build_target_grid(E, P, E.opts.cell_size, max_cells);
+    } else {
+        // an empty target: a 1-cell grid with no points, every search returns nothing
+        P.cell_start.reserve(4);
+        CK(cudaMemsetAsync(P.cell_start.p, 0, 4 * sizeof(int), st));
+        P.tgt_sorted.reserve(1);
+        GridDev g{};
+        g.inv_h = 1.f; g.h_cover = 1.f; g.cover_slack = 0.f; g.nx = g.ny = g.nz = 1; g.n_cells = 1;
+        D.grid = g;
+        D.tgt_sorted = P.tgt_sorted.p;
+        D.cell_start = P.cell_start.p;
+    }
+    const size_t plane = static_cast<size_t>(D.m) * D.n_pad;
+    P.nbr_x.reserve(plane); P.nbr_y.reserve(plane); P.nbr_z.reserve(plane); P.nbr_idx.reserve(plane);
+    P.nbr_cnt.reserve(D.n_pad);
+    if (P.want_d2) P.nbr_d2.reserve(plane);
+    D.nbr_x = P.nbr_x.p; D.nbr_y = P.nbr_y.p; D.nbr_z = P.nbr_z.p; D.nbr_idx = P.nbr_idx.p;
+    D.nbr_d2 = P.want_d2 ? P.nbr_d2.p : nullptr;
+    D.nbr_cnt = P.nbr_cnt.p;
+    CK(cudaMemsetAsync(P.nbr_cnt.p, 0, static_cast<size_t>(D.n_pad) * sizeof(int), st));
+    D.n_eval_blocks = std::max(1, std::min(ceil_div(std::max(D.n_src, 1), kEvalThreads), 4 * std::max(g_sm_count, 1)));
+    P.partials.reserve(static_cast<size_t>(D.n_eval_blocks) * kNSum);
+    D.partials = P.partials.p;
+    CK(cudaMemsetAsync(P.partials.p, 0, static_cast<size_t>(D.n_eval_blocks) * kNSum * sizeof(double), st));
+    D.max_hist = std::max(1, prm.n_iter);
+    P.history.reserve(static_cast<size_t>(D.max_hist) * 16);
+    P.stats.reserve(D.max_hist);
+    P.state.reserve(1);
+    P.cfg.reserve(1);
+    D.history = P.history.p;
+    D.stats = P.stats.p;
+    D.state = P.state.p;
+    D.cfg = P.cfg.p;
+    Config& c = P.hcfg;
+    for (int k = 0; k < 4; ++k) c.x0[k] = prm.initial_rotation[k];
+    for (int k = 0; k < 3; ++k) c.x0[4 + k] = prm.initial_translation[k];
+    c.function_tolerance = E.opts.function_tolerance > 0 ? E.opts.function_tolerance : 10e-6;
+    c.cost_drop_thresh = prm.cost_drop_thresh;
+    c.n_cost_drop_it = prm.n_cost_drop_it;
+    c.dof = prm.dof;
+    c.n_iter = prm.n_iter;
+    c.max_lm_iterations = INT_MAX;
+    c.is_normal = !(prm.dof < DBL_MAX);
+    c.fast_weights = E.opts.fast_weights;
+    D.wcfg = make_weight_cfg(prm.dof);
+    PairState hs;
+    memset(&hs, 0, sizeof(hs));
+    state_init(&hs, &c);
+    CK(cudaMemcpyAsync(P.cfg.p, &c, sizeof(c), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(P.state.p, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
+    D.mailbox = nullptr;
+    D.rank = 0;
+    D.world = 1;
+    D.spin_limit = 4000000000ll;  // ~2 s of SM clocks
+    CK(cudaStreamSynchronize(st));  // host temporaries (hs, c) must outlive the copies
+}
+
+static void engine_init(Engine& E, const ppcr_params& params, const ppcr_options* options)
+{
+    E.params = params;
+    if (options) E.opts = *options; else memset(&E.opts, 0, sizeof(E.opts));
+    validate_params(params);
+    E.device = E.opts.device;
+    select_device(E.device);
+    if (E.opts.stream) {
+        E.stream = static_cast<cudaStream_t>(E.opts.stream);
+        E.own_stream = false;
+    } else {
+        CK(cudaStreamCreateWithFlags(&E.stream, cudaStreamNonBlocking));
+        E.own_stream = true;
+    }
+    E.d_active.reserve(4);
+    CK(cudaMallocHost(&E.h_active, 4 * sizeof(int)));
+    if (E.opts.ticks_per_sync <= 0) E.opts.ticks_per_sync = 4;
+    const char* env = getenv("PPCR_DRIVER");
+    if (env && E.opts.driver == 0) E.opts.driver = atoi(env);
+}
+
+template <int R>
+static void set_search_attr(size_t smem)
+{
+    CK(cudaFuncSetAttribute(k_search<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+}
+
+// publishes the PairDev array and derives the launch geometry
+static void engine_commit(Engine& E)
+{
+    const int np = static_cast<int>(E.pairs.size());
+    std::vector<PairDev> host(np);
+    int max_m = 1;
+    long long max_src = 1;
+    int max_eval = 1;
+    for (int p = 0; p < np; ++p) {
+        host[p] = E.pairs[p].dev;
+        max_m = std::max(max_m, host[p].m);
+        max_src = std::max<long long>(max_src, host[p].n_src);
+        max_eval = std::max(max_eval, host[p].n_eval_blocks);
+    }
+    E.d_pairs.reserve(np);
+    CK(cudaMemcpyAsync(E.d_pairs.p, host.data(), sizeof(PairDev) * np, cudaMemcpyHostToDevice, E.stream));
+    CK(cudaStreamSynchronize(E.stream));
+    const int cap_m = E.params.max_neighbours;
+    E.lists_R = cap_m <= 32 ? 1 : (cap_m <= 64 ? 2 : 4);
+    E.search_smem = static_cast<size_t>(cap_m) * kTileQ * 20;
+    if (E.lists_R == 1) set_search_attr<1>(E.search_smem);
+    else if (E.lists_R == 2) set_search_attr<2>(E.search_smem);
+    else set_search_attr<4>(E.search_smem);
+    const int tiles = ceil_div(max_src, kTileQ);
+    const int trb = std::max(1, std::min(ceil_div(max_src, 256), 8 * std::max(g_sm_count, 1)));
+    if (tiles > E.max_tiles || max_eval > E.max_eval_blocks || trb > E.max_tr_blocks) {
+        E.max_tiles = std::max(E.max_tiles, tiles);
+        E.max_eval_blocks = std::max(E.max_eval_blocks, max_eval);
+        E.max_tr_blocks = std::max(E.max_tr_blocks, trb);
+        if (E.graph_exec) {  // geometry changed: the captured graph is stale
+            cudaGraphExecDestroy(E.graph_exec);
+            cudaGraphDestroy(E.graph);
+            E.graph_exec = nullptr;
+            E.graph = nullptr;
+            E.graph_ready = false;
+        }
+    }
+    // generous device-side cap: n_iter outer iterations, each at most ~64 LM evaluations in practice
+    const long long cap = (static_cast<long long>(E.params.n_iter) + 2) * 256 + 64;
+    E.max_ticks = static_cast<int>(std::min<long long>(cap, INT_MAX / 2));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// tick driver
+// ------------------------------------------------------------------------------------------------------------
+
+enum Stage { ST_SEARCH = 0, ST_EVAL = 1, ST_CTRL = 2, ST_TRANSFORM = 3 };
+
+static void stage_begin(Engine& E, bool rec, int stage)
+{
+    if (!rec) return;
+    EventPair ep;
+    CK(cudaEventCreate(&ep.a));
+    CK(cudaEventCreate(&ep.b));
+    ep.stage = stage;
+    CK(cudaEventRecord(ep.a, E.stream));
+    E.events.push_back(ep);
+}
+static void stage_end(Engine& E, bool rec)
+{
+    if (!rec) return;
+    CK(cudaEventRecord(E.events.back().b, E.stream));
+}
+
+static void launch_search(Engine& E)
+{
+    const int np = static_cast<int>(E.pairs.size());
+    dim3 grid(E.max_tiles, np);
+    if (E.lists_R == 1) k_search<1><<<grid, kSearchWarps * 32, E.search_smem, E.stream>>>(E.d_pairs.p);
+    else if (E.lists_R == 2) k_search<2><<<grid, kSearchWarps * 32, E.search_smem, E.stream>>>(E.d_pairs.p);
+    else k_search<4><<<grid, kSearchWarps * 32, E.search_smem, E.stream>>>(E.d_pairs.p);
+}
+
+static void launch_eval(Engine& E)
+{
+    const int np = static_cast<int>(E.pairs.size());
+    dim3 grid(E.max_eval_blocks, np);
+    if (E.opts.fast_weights) k_eval<true><<<grid, kEvalThreads, 0, E.stream>>>(E.d_pairs.p);
+    else k_eval<false><<<grid, kEvalThreads, 0, E.stream>>>(E.d_pairs.p);
+}
+
+static void launch_tick(Engine& E, bool use_cond, bool rec)
+{
+    const int np = static_cast<int>(E.pairs.size());
+    if (!E.skip_search) {
+        stage_begin(E, rec, ST_SEARCH);
+        launch_search(E);
+        stage_end(E, rec);
+    }
+    stage_begin(E, rec, ST_EVAL);
+    launch_eval(E);
+    stage_end(E, rec);
+    stage_begin(E, rec, ST_CTRL);
+    k_controller<<<np, kCtrlThreads, 0, E.stream>>>(E.d_pairs.p, E.max_ticks);
+    stage_end(E, rec);
+    stage_begin(E, rec, ST_TRANSFORM);
+    k_transform<<<dim3(E.max_tr_blocks, np), 256, 0, E.stream>>>(E.d_pairs.p, np, E.d_active.p, E.cond, use_cond ? 1 : 0);
+    stage_end(E, rec);
+    CK(cudaGetLastError());
+    E.times.ticks += 1;
+    E.times.total_launches += E.skip_search ? 3 : 4;
+}
+
+static void collect_stage_times(Engine& E)
+{
+    for (auto& ep : E.events) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) {
+            switch (ep.stage) {
+                case ST_SEARCH: E.times.search_ms += ms; E.times.search_launches++; break;
+                case ST_EVAL: E.times.eval_ms += ms; E.times.eval_launches++; break;
+                case ST_CTRL: E.times.controller_ms += ms; E.times.controller_launches++; break;
+                default: E.times.transform_ms += ms; E.times.transform_launches++; break;
+            }
+        }
+        cudaEventDestroy(ep.a);
+        cudaEventDestroy(ep.b);
+    }
+    E.events.clear();
+}
+
+// body graph = one tick, wrapped in a WHILE node whose condition k_transform sets on the device
+static bool build_graph(Engine& E)
+{
+    if (E.graph_ready) return true;
+    if (E.graph_failed) return false;
+    cudaError_t e;
+    e = cudaGraphCreate(&E.graph, 0);
+    if (e != cudaSuccess) goto bad;
+    e = cudaGraphConditionalHandleCreate(&E.cond, E.graph, 1, cudaGraphCondAssignDefault);
+    if (e != cudaSuccess) goto bad;
+    {
+        cudaGraphNodeParams np{};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = E.cond;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        e = cudaGraphAddNode(&node, E.graph, nullptr, 0, &np);
+        if (e != cudaSuccess) goto bad;
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        e = cudaStreamBeginCaptureToGraph(E.stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) goto bad;
+        try {
+            launch_tick(E, true, false);
+        } catch (...) {
+            cudaGraph_t dummy;
+            cudaStreamEndCapture(E.stream, &dummy);
+            goto bad;
+        }
+        E.times.ticks -= 1;
+        E.times.total_launches -= E.skip_search ? 3 : 4;
+        e = cudaStreamEndCapture(E.stream, nullptr);
+        if (e != cudaSuccess) goto bad;
+    }
+    e = cudaGraphInstantiate(&E.graph_exec, E.graph, 0);
+    if (e != cudaSuccess) goto bad;
+    E.graph_ready = true;
+    return true;
+bad:
+    cudaGetLastError();
+    if (E.graph_exec) cudaGraphExecDestroy(E.graph_exec);
+    if (E.graph) cudaGraphDestroy(E.graph);
+    E.graph_exec = nullptr;
+    E.graph = nullptr;
+    E.graph_failed = true;
+    if (E.opts.driver == 2) throw StatusError{PPCR_ERR_CUDA, std::string("CUDA graph WHILE driver unavailable: ") + cudaGetErrorString(e)};
+    return false;
+}
+
+// Runs ticks until every pair of the engine is done.
+static void run_to_completion(Engine& E)
+{
+    const int np = static_cast<int>(E.pairs.size());
+    k_align_begin<<<ceil_div(np, 64), 64, 0, E.stream>>>(E.d_pairs.p, np);
+    CK(cudaGetLastError());
+    const bool rec = E.opts.record_stage_times != 0;
+    bool use_graph = (E.opts.driver == 2) || (E.opts.driver == 0 && !rec && E.world == 1);
+    if (use_graph) use_graph = build_graph(E);
+    if (use_graph) {
+        CK(cudaGraphLaunch(E.graph_exec, E.stream));
+        CK(cudaStreamSynchronize(E.stream));
+    } else {
+        long long guard = 0;
+        for (;;) {
+            for (int t = 0; t < E.opts.ticks_per_sync; ++t) launch_tick(E, false, rec);
+            CK(cudaMemcpyAsync(E.h_active, E.d_active.p, sizeof(int), cudaMemcpyDeviceToHost, E.stream));
+            CK(cudaStreamSynchronize(E.stream));
+            if (!E.h_active[0]) break;
+            guard += E.opts.ticks_per_sync;
+            if (guard > static_cast<long long>(E.max_ticks) + 64) throw StatusError{PPCR_ERR_CUDA, "tick guard exceeded"};
+        }
+        if (rec) collect_stage_times(E);
+    }
+}
+
+static PairState download_state(Engine& E, int p)
+{
+    PairState s;
+    CK(cudaMemcpyAsync(&s, E.pairs[p].state.p, sizeof(s), cudaMemcpyDeviceToHost, E.stream));
+    CK(cudaStreamSynchronize(E.stream));
+    return s;
+}
+
+static void check_state_error(const PairState& s)
+{
+    if (s.error >= 100) throw StatusError{PPCR_ERR_TIMEOUT, "a peer rank did not arrive at the moment exchange"};
+    if (s.error != 0) throw StatusError{PPCR_ERR_CUDA, "device tick cap reached before convergence"};
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// helpers shared by the stage-level entry points
+// ------------------------------------------------------------------------------------------------------------
+
+static void set_phase(Engine& E, int p, int phase)
+{
+    PairState s = download_state(E, p);
+    s.phase = phase;
+    CK(cudaMemcpyAsync(E.pairs[p].state.p, &s, sizeof(s), cudaMemcpyHostToDevice, E.stream));
+    CK(cudaStreamSynchronize(E.stream));
+}
+
+// slot-major device planes -> row-major [n_src][max_nn] host arrays
+static void download_association(Engine& E, int p, int32_t* idx, float* d2, int32_t* count, int64_t n_src, int max_nn)
+{
+    Pair& P = E.pairs[p];
+    const PairDev& D = P.dev;
+    if (n_src != D.n_src) throw StatusError{PPCR_ERR_INVALID, "n_src does not match the handle's (filtered) source size"};
+    std::vector<int> h_idx(static_cast<size_t>(D.m) * D.n_pad), h_cnt(D.n_pad);
+    std::vector<float> h_d2;
+    CK(cudaMemcpyAsync(h_idx.data(), D.nbr_idx, h_idx.size() * sizeof(int), cudaMemcpyDeviceToHost, E.stream));
+    CK(cudaMemcpyAsync(h_cnt.data(), D.nbr_cnt, h_cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, E.stream));
+    if (d2) {
+        if (!D.nbr_d2) throw StatusError{PPCR_ERR_INVALID, "distances were not recorded"};
+        h_d2.resize(h_idx.size());
+        CK(cudaMemcpyAsync(h_d2.data(), D.nbr_d2, h_d2.size() * sizeof(float), cudaMemcpyDeviceToHost, E.stream));
+    }
+    CK(cudaStreamSynchronize(E.stream));
+    for (int64_t i = 0; i < n_src; ++i) {
+        const int c = h_cnt[i];
+        count[i] = c;
+        for (int k = 0; k < max_nn; ++k) {
+            const bool have = k < c && k < D.m;
+            idx[i * max_nn + k] = have ? h_idx[static_cast<size_t>(k) * D.n_pad + i] : -1;
+            if (d2) d2[i * max_nn + k] = have ? h_d2[static_cast<size_t>(k) * D.n_pad + i] : 0.f;
+        }
+    }
+}
+
+// explicit association (row-major idx/count on the host) -> slot-major planes on the device
+static void upload_association(Engine& E, int p, const float* tgt_xyzw, int64_t n_tgt, const int32_t* idx,
+                               const int32_t* count, int max_nn)
+{
+    Pair& P = E.pairs[p];
+    const PairDev& D = P.dev;
+    const size_t plane = static_cast<size_t>(D.m) * D.n_pad;
+    std::vector<float> hx(plane, 0.f), hy(plane, 0.f), hz(plane, 0.f);
+    std::vector<int> hi(plane, -1), hc(D.n_pad, 0);
+    int64_t K = 0;
+    for (int64_t i = 0; i < D.n_src; ++i) {
+        const int c = count[i];
+        if (c < 0 || c > max_nn || c > D.m) throw StatusError{PPCR_ERR_INVALID, "association count out of range"};
+        hc[i] = c;
+        K += c;
+        for (int k = 0; k < c; ++k) {
+            const int j = idx[i * max_nn + k];
+            if (j < 0 || j >= n_tgt) throw StatusError{PPCR_ERR_INVALID, "association index out of range"};
+            const size_t o = static_cast<size_t>(k) * D.n_pad + i;
+            hx[o] = tgt_xyzw[4 * static_cast<size_t>(j)];
+            hy[o] = tgt_xyzw[4 * static_cast<size_t>(j) + 1];
+            hz[o] = tgt_xyzw[4 * static_cast<size_t>(j) + 2];
+            hi[o] = j;
+        }
+    }
+    CK(cudaMemcpyAsync(D.nbr_x, hx.data(), plane * sizeof(float), cudaMemcpyHostToDevice, E.stream));
+    CK(cudaMemcpyAsync(D.nbr_y, hy.data(), plane * sizeof(float), cudaMemcpyHostToDevice, E.stream));
+    CK(cudaMemcpyAsync(D.nbr_z, hz.data(), plane * sizeof(float), cudaMemcpyHostToDevice, E.stream));
+    CK(cudaMemcpyAsync(D.nbr_idx, hi.data(), plane * sizeof(int), cudaMemcpyHostToDevice, E.stream));
+    CK(cudaMemcpyAsync(D.nbr_cnt, hc.data(), hc.size() * sizeof(int), cudaMemcpyHostToDevice, E.stream));
+    PairState s = download_state(E, p);
+    s.K = K;
+    CK(cudaMemcpyAsync(P.state.p, &s, sizeof(s), cudaMemcpyHostToDevice, E.stream));
+    CK(cudaStreamSynchronize(E.stream));
+}
+
+// the 24 moments, reduced exactly like k_controller does (warp-strided partial sums, then warps in order)
+static void reduce_partials_like_controller(Engine& E, int p, double* S)
+{
+    const PairDev& D = E.pairs[p].dev;
+    std::vector<double> part(static_cast<size_t>(D.n_eval_blocks) * kNSum);
+    CK(cudaMemcpyAsync(part.data(), D.partials, part.size() * sizeof(double), cudaMemcpyDeviceToHost, E.stream));
+    CK(cudaStreamSynchronize(E.stream));
+    const int W = kCtrlThreads / 32;
+    for (int k = 0; k < kNSum; ++k) {
+        double total = 0.0;
+        for (int w = 0; w < W; ++w) {
+            double v = 0.0;
+            for (int b = w; b < D.n_eval_blocks; b += W) v += part[static_cast<size_t>(b) * kNSum + k];
+            total += v;
+        }
+        S[k] = total;
+    }
+}
+
+template <typename F>
+static ppcr_status guarded(F&& f)
+{
+    try {
+        f();
+        return PPCR_OK;
+    } catch (const CudaError& e) {
+        return translate(e);
+    } catch (const StatusError& e) {
+        return fail(e.code, e.msg);
+    } catch (const std::bad_alloc&) {
+        return fail(PPCR_ERR_CUDA, "host allocation failed");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// extern "C"
+// ------------------------------------------------------------------------------------------------------------
+
+extern "C" {
+
+const char* ppcr_last_error(void) { return g_last_error.c_str(); }
+const char* ppcr_version(void) { return "ppcr-b200 0.1 (sm_100a)"; }
+
+void ppcr_default_params(ppcr_params* p)
+{
+    memset(p, 0, sizeof(*p));
+    p->max_neighbours = 20;
+    p->dof = 5;
+    p->radius = 1;
+    p->n_iter = 1000;
+    p->cost_drop_thresh = 0.01;
+    p->n_cost_drop_it = 5;
+    p->initial_rotation[0] = 1;
+}
+
+void ppcr_default_options(ppcr_options* o) { memset(o, 0, sizeof(*o)); }
+
+ppcr_status ppcr_create_ex(const float* src, int64_t n_src, const float* tgt, int64_t n_tgt, const ppcr_params* params,
+                           const ppcr_options* options, ppcr_handle** out)
+{
+    if (!params || !out) return fail(PPCR_ERR_INVALID, "null argument");
+    *out = nullptr;
+    ppcr_handle* h = nullptr;
+    ppcr_status s = guarded([&] {
+        h = new ppcr_handle();
+        Engine& E = h->eng;
+        engine_init(E, *params, options);
+        E.pairs.resize(1);
+        pair_setup(E, E.pairs[0], src, n_src, tgt, n_tgt, E.opts.input_on_device != 0, 1ll << 26);
+        engine_commit(E);
+    });
+    if (s != PPCR_OK) {
+        delete h;
+        return s;
+    }
+    *out = h;
+    return PPCR_OK;
+}
+
+ppcr_status ppcr_create(const float* src, int64_t n_src, const float* tgt, int64_t n_tgt, const ppcr_params* params,
+                        ppcr_handle** out)
+{
+    return ppcr_create_ex(src, n_src, tgt, n_tgt, params, nullptr, out);
+}
+
+void ppcr_destroy(ppcr_handle* h) { delete h; }
+
+ppcr_status ppcr_align(ppcr_handle* h)
+{
+    if (!h) return fail(PPCR_ERR_INVALID, "null handle");
+    return guarded([&] {
+        Engine& E = h->eng;
+        CK(cudaSetDevice(E.device));
+        run_to_completion(E);
+        check_state_error(download_state(E, 0));
+    });
+}
+
+ppcr_status ppcr_has_converged(ppcr_handle* h, int32_t* out)
+{
+    if (!h || !out) return fail(PPCR_ERR_INVALID, "null argument");
+    return guarded([&] {
+        Engine& E = h->eng;
+        CK(cudaSetDevice(E.device));
+        PairState s = download_state(E, 0);
+        *out = has_converged(&s, &E.pairs[0].hcfg) ? 1 : 0;  // mutates the counter, like the reference
+        CK(cudaMemcpyAsync(E.pairs[0].state.p, &s, sizeof(s), cudaMemcpyHostToDevice, E.stream));
+        CK(cudaStreamSynchronize(E.stream));
+    });
+}
+
+ppcr_status ppcr_history(ppcr_handle* h, double* T, int32_t* n_inout)
+{
+    if (!h || !n_inout) return fail(PPCR_ERR_INVALID, "null argument");
+    return guarded([&] {
+        Engine& E = h->eng;
+        CK(cudaSetDevice(E.device));
+        PairState s = download_state(E, 0);
+        const int n = std::min(s.current_iteration, E.pairs[0].dev.max_hist);
+        const int take = std::min(n, *n_inout);
+        if (T && take > 0) {
+            CK(cudaMemcpyAsync(T, E.pairs[0].history.p, static_cast<size_t>(take) * 16 * sizeof(double), cudaMemcpyDeviceToHost, E.stream));
+            CK(cudaStreamSynchronize(E.stream));
+        }
+        *n_inout = n;
+    });
+}
+
+ppcr_status ppcr_iteration_stats(ppcr_handle* h, ppcr_iter_stats* out, int32_t* n_inout)
+{
+    if (!h || !n_inout) return fail(PPCR_ERR_INVALID, "null argument");
+    return guarded([&] {
+        Engine& E = h->eng;
+        CK(cudaSetDevice(E.device));
+        PairState s = download_state(E, 0);
+        const int n = std::min(s.current_iteration, E.pairs[0].dev.max_hist);
+        const int take = std::min(n, *n_inout);
+        if (out && take > 0) {
+            CK(cudaMemcpyAsync(out, E.pairs[0].stats.p, static_cast<size_t>(take) * sizeof(IterStats), cudaMemcpyDeviceToHost, E.stream));
+            CK(cudaStreamSynchronize(E.stream));
+        }
+        *n_inout = n;
+    });
+}
+
+static void download_cloud(Engine& E, const float4* dev, int64_t n, float* out, int64_t* n_inout, bool clear_w)
+{
+    if (!n_inout) throw StatusError{PPCR_ERR_INVALID, "null argument"};
+    if (*n_inout < n || !out) {
+        *n_inout = n;
+        if (out) throw StatusError{PPCR_ERR_SMALL_BUFFER, "output buffer too small"};
+        return;
+    }
+    if (n > 0) {
+        CK(cudaMemcpyAsync(out, dev, static_cast<size_t>(n) * sizeof(float4), cudaMemcpyDeviceToHost, E.stream));
+        CK(cudaStreamSynchronize(E.stream));
+        if (clear_w)
+            for (int64_t i = 0; i < n; ++i) out[4 * i + 3] = 1.0f;
+    }
+    *n_inout = n;
+}
+
+ppcr_status ppcr_filtered_source(ppcr_handle* h, float* out, int64_t* n_inout)
+{
+    if (!h) return fail(PPCR_ERR_INVALID, "null handle");
+    return guarded([&] {
+        Engine& E = h->eng;
+        CK(cudaSetDevice(E.device));
+        download_cloud(E, E.pairs[0].src.p, E.pairs[0].n_src, out, n_inout, true);
+    });
+}
+
+ppcr_status ppcr_filtered_target(ppcr_handle* h, float* out, int64_t* n_inout)
+{
+    if (!h) return fail(PPCR_ERR_INVALID, "null handle");
+    return guarded([&] {
+        Engine& E = h->eng;
+        CK(cudaSetDevice(E.device));
+        download_cloud(E, E.pairs[0].tgt_raw.p, E.pairs[0].n_tgt, out, n_inout, false);
+    });
+}
+
+ppcr_status ppcr_association(ppcr_handle* h, int32_t* idx, int32_t* count, int64_t n_src, int32_t max_neighbours)
+{
+    if (!h || !idx || !count) return fail(PPCR_ERR_INVALID, "null argument");
+    return guarded([&] {
+        Engine& E = h->eng;
+        CK(cudaSetDevice(E.device));
+        download_association(E, 0, idx, nullptr, count, n_src, max_neighbours);
+    });
+}
+
+ppcr_status ppcr_get_stage_times(ppcr_handle* h, ppcr_stage_times* out)
+{
+    if (!h || !out) return fail(PPCR_ERR_INVALID, "null argument");
+    *out = h->eng.times;
+    return PPCR_OK;
+}
+
+ppcr_status ppcr_time_kernel(ppcr_handle* h, int32_t which, int32_t reps, int32_t flush_l2, float* avg_ms,
+                             double* algorithmic_bytes)
+{
+    if (!h || !avg_ms || reps <= 0) return fail(PPCR_ERR_INVALID, "bad argument");
+    return guarded([&] {
+        Engine& E = h->eng;
+        CK(cudaSetDevice(E.device));
+        Pair& P = E.pairs[0];
+        const PairDev& D = P.dev;
+        PairState saved = download_state(E, 0);
+        PairState tmp = saved;
+        tmp.phase = (which == 0) ? PH_SEARCH : PH_LM;
+        tmp.apply_dT = (which == 2) ? 1 : 0;
+        if (which == 2)
+            for (int k = 0; k < 16; ++k) tmp.dT[k] = (k % 5 == 0) ? 1.0 : 0.0;  // identity: the cloud is unchanged
+        CK(cudaMemcpyAsync(P.state.p, &tmp, sizeof(tmp), cudaMemcpyHostToDevice, E.stream));
+        const size_t flush_n = (256ull << 20) / sizeof(float4);
+        if (flush_l2) E.flush.reserve(flush_n);
+        std::vector<cudaEvent_t> ev(2 * static_cast<size_t>(reps));
+        for (auto& e : ev) CK(cudaEventCreate(&e));
+        for (int r = 0; r < reps; ++r) {
+            if (flush_l2) k_fill<<<4 * std::max(g_sm_count, 1), 256, 0, E.stream>>>(E.flush.p, flush_n, static_cast<float>(r));
+            CK(cudaEventRecord(ev[2 * r], E.stream));
+            switch (which) {
+                case 0: launch_search(E); break;
+                case 1: launch_eval(E); break;
+                case 2: k_transform<<<dim3(E.max_tr_blocks, 1), 256, 0, E.stream>>>(E.d_pairs.p, 1, E.d_active.p, E.cond, 0); break;
+                default: build_target_grid(E, P, 1.0f / D.grid.inv_h, 1ll << 26); break;
+            }
+            CK(cudaEventRecord(ev[2 * r + 1], E.stream));
+        }
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(E.stream));
+        double total = 0;
+        for (int r = 0; r < reps; ++r) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, ev[2 * r], ev[2 * r + 1]));
+            total += ms;
+        }
+        for (auto& e : ev) cudaEventDestroy(e);
+        *avg_ms = static_cast<float>(total / reps);
+        PairState after = download_state(E, 0);
+        const double K = (which == 0) ? static_cast<double>(after.K - tmp.K) / reps : static_cast<double>(saved.K);
+        if (algorithmic_bytes) {
+            const double ns = D.n_src, nt = D.n_tgt;
+            switch (which) {
+                case 0: *algorithmic_bytes = 16.0 * ns + 16.0 * nt + 4.0 * ns + 16.0 * K; break;  // query, target, count, 3 planes + idx
+                case 1: *algorithmic_bytes = 16.0 * ns + 4.0 * ns + 12.0 * K; break;              // source, count, 3 planes
+                case 2: *algorithmic_bytes = 32.0 * ns; break;
+                default: *algorithmic_bytes = 36.0 * nt + 8.0 * D.grid.n_cells; break;
+            }
+        }
+        CK(cudaMemcpyAsync(P.state.p, &saved, sizeof(saved), cudaMemcpyHostToDevice, E.stream));
+        CK(cudaStreamSynchronize(E.stream));
+    });
+}
+
+// ---- stage-level entry points ------------------------------------------------------------------------------
+
+ppcr_status ppcr_voxel_filter(const float* xyzw, int64_t n, double leaf, float* out_xyzw, int64_t* n_out)
+{
+    if ((n > 0 && (!xyzw || !out_xyzw)) || !n_out || n < 0 || !(leaf > 0)) return fail(PPCR_ERR_INVALID, "bad argument");
+    return guarded([&] {
+        ppcr_params prm;
+        ppcr_default_params(&prm);
+        Engine E;
+        engine_init(E, prm, nullptr);
+        Pair P;
+        DevBuf<float4> in, out;
+        upload_cloud(in, xyzw, n, false, E.stream);
+        int64_t k = voxel_filter_device(in.p, n, leaf, out, P, E.stream);
+        if (k < 0) {
+            memcpy(out_xyzw, xyzw, static_cast<size_t>(n) * 16);
+            *n_out = n;
+        } else {
+            if (k > 0) CK(cudaMemcpy(out_xyzw, out.p, static_cast<size_t>(k) * sizeof(float4), cudaMemcpyDeviceToHost));
+            *n_out = k;
+        }
+        in.release();
+        out.release();
+        P.release();
+    });
+}
+
+ppcr_status ppcr_radius_search(const float* src, int64_t n_src, const float* tgt, int64_t n_tgt, double radius,
+                               int32_t max_nn, float cell_size, int32_t* out_idx, float* out_d2, int32_t* out_count)
+{
+    if (!out_idx || !out_count) return fail(PPCR_ERR_INVALID, "null output");
+    return guarded([&] {
+        ppcr_params prm;
+        ppcr_default_params(&prm);
+        prm.radius = radius;
+        prm.max_neighbours = max_nn;
+        ppcr_options opt;
+        ppcr_default_options(&opt);
+        opt.cell_size = cell_size;
+        Engine E;
+        engine_init(E, prm, &opt);
+        E.pairs.resize(1);
+        E.pairs[0].want_d2 = true;
+        pair_setup(E, E.pairs[0], src, n_src, tgt, n_tgt, false, 1ll << 26);
+        engine_commit(E);
+        set_phase(E, 0, PH_SEARCH);
+        if (n_src > 0) launch_search(E);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(E.stream));
+        download_association(E, 0, out_idx, out_d2, out_count, n_src, max_nn);
+    });
+}
+
+static void pose7_to_state(const double* pose, Pose* out) { pose_from_x(pose, out); }
+
+ppcr_status ppcr_weights_normal_eq(const float* src, int64_t n_src, const float* tgt, int64_t n_tgt, const int32_t* idx,
+                                   const int32_t* count, int32_t max_nn, double dof, int32_t dimension,
+                                   const double* pose_w, const double* pose_e, int32_t fast_weights,
+                                   double* weights, double* normal_eq)
+{
+    if (!idx || !count || !pose_w || !pose_e || !normal_eq) return fail(PPCR_ERR_INVALID, "null argument");
+    return guarded([&] {
+        ppcr_params prm;
+        ppcr_default_params(&prm);
+        prm.max_neighbours = max_nn;
+        prm.dof = dof;
+        prm.radius = 1.0;
+        ppcr_options opt;
+        ppcr_default_options(&opt);
+        opt.fast_weights = fast_weights;
+        opt.cell_size = 1.0f;
+        Engine E;
+        engine_init(E, prm, &opt);
+        E.pairs.resize(1);
+        pair_setup(E, E.pairs[0], src, n_src, tgt, n_tgt, false, 1ll << 22);
+        E.pairs[0].dev.wcfg = make_weight_cfg(dof, dimension > 0 ? dimension : 3);
+        engine_commit(E);
+        upload_association(E, 0, tgt, n_tgt, idx, count, max_nn);
+        PairState s = download_state(E, 0);
+        s.phase = PH_LM;
+        pose7_to_state(pose_e, &s.pose_e);
+        pose7_to_state(pose_w, &s.pose_w);
+        CK(cudaMemcpyAsync(E.pairs[0].state.p, &s, sizeof(s), cudaMemcpyHostToDevice, E.stream));
+        launch_eval(E);
+        CK(cudaGetLastError());
+        double S[kNSum];
+        reduce_partials_like_controller(E, 0, S);
+        double H[kNP * kNP], g[kNP], cost;
+        expand_moments(S, pose_e, H, g, &cost);  // the controller's expansion, same source
+        int o = 0;
+        for (int r = 0; r < kNP; ++r)
+            for (int c = r; c < kNP; ++c) normal_eq[o++] = H[r * kNP + c];
+        for (int r = 0; r < kNP; ++r) normal_eq[o++] = g[r];
+        normal_eq[o] = cost;
+        if (weights) {
+            const PairDev& D = E.pairs[0].dev;
+            DevBuf<double> dw;
+            const size_t plane = static_cast<size_t>(D.m) * D.n_pad;
+            dw.reserve(plane);
+            CK(cudaMemsetAsync(dw.p, 0, plane * sizeof(double), E.stream));
+            if (fast_weights) k_dump_weights<true><<<ceil_div(std::max(D.n_src, 1), 128), 128, 0, E.stream>>>(E.d_pairs.p, dw.p);
+            else k_dump_weights<false><<<ceil_div(std::max(D.n_src, 1), 128), 128, 0, E.stream>>>(E.d_pairs.p, dw.p);
+            CK(cudaGetLastError());
+            std::vector<double> hw(plane);
+            CK(cudaMemcpyAsync(hw.data(), dw.p, plane * sizeof(double), cudaMemcpyDeviceToHost, E.stream));
+            CK(cudaStreamSynchronize(E.stream));
+            for (int64_t i = 0; i < n_src; ++i)
+                for (int k = 0; k < max_nn; ++k)
+                    weights[i * max_nn + k] = (k < count[i]) ? hw[static_cast<size_t>(k) * D.n_pad + i] : 0.0;
+            dw.release();
+        }
+    });
+}
+
+ppcr_status ppcr_iteration_solve(const float* src, int64_t n_src, const float* tgt, int64_t n_tgt, const int32_t* idx,
+                                 const int32_t* count, int32_t max_nn, const ppcr_params* params,
+                                 double function_tolerance, double* out_pose, double* out_T, ppcr_iter_stats* stats)
+{
+    if (!idx || !count || !params) return fail(PPCR_ERR_INVALID, "null argument");
+    return guarded([&] {
+        ppcr_params prm = *params;
+        prm.max_neighbours = max_nn;
+        prm.n_iter = 1;  // exactly one ceres::Solve
+        prm.source_filter_size = 0;
+        prm.target_filter_size = 0;
+        ppcr_options opt;
+        ppcr_default_options(&opt);
+        opt.function_tolerance = function_tolerance;
+        opt.cell_size = static_cast<float>(prm.radius);
+        opt.driver = 1;
+        Engine E;
+        engine_init(E, prm, &opt);
+        E.pairs.resize(1);
+        pair_setup(E, E.pairs[0], src, n_src, tgt, n_tgt, false, 1ll << 22);
+        engine_commit(E);
+        E.skip_search = true;
+        // align_begin would reset K, so arm the state by hand: first loop test passed, association given
+        PairState s = download_state(E, 0);
+        lm_reset(&s, &E.pairs[0].hcfg);
+        s.phase = PH_SEARCH;
+        s.num_unuseful = 1;
+        CK(cudaMemcpyAsync(E.pairs[0].state.p, &s, sizeof(s), cudaMemcpyHostToDevice, E.stream));
+        CK(cudaStreamSynchronize(E.stream));
+        upload_association(E, 0, tgt, n_tgt, idx, count, max_nn);
+        long long guard = 0;
+        for (;;) {
+            for (int t = 0; t < E.opts.ticks_per_sync; ++t) launch_tick(E, false, false);
+            CK(cudaMemcpyAsync(E.h_active, E.d_active.p, sizeof(int), cudaMemcpyDeviceToHost, E.stream));
+            CK(cudaStreamSynchronize(E.stream));
+            if (!E.h_active[0]) break;
+            if (++guard > 100000) throw StatusError{PPCR_ERR_CUDA, "inner solve did not terminate"};
+        }
+        PairState f = download_state(E, 0);
+        check_state_error(f);
+        if (out_pose) memcpy(out_pose, f.x, sizeof(double) * kNP);
+        if (out_T) memcpy(out_T, f.dT, sizeof(double) * 16);
+        if (stats) CK(cudaMemcpy(stats, E.pairs[0].stats.p, sizeof(IterStats), cudaMemcpyDeviceToHost));
+    });
+}
+
+ppcr_status ppcr_transform(float* xyzw, int64_t n, const double* T)
+{
+    if ((n > 0 && !xyzw) || !T || n < 0) return fail(PPCR_ERR_INVALID, "bad argument");
+    return guarded([&] {
+        select_device(0);
+        if (n == 0) return;
+        DevBuf<float4> d;
+        DevBuf<double> dT;
+        d.reserve(n);
+        dT.reserve(16);
+        CK(cudaMemcpy(d.p, xyzw, static_cast<size_t>(n) * 16, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dT.p, T, 16 * sizeof(double), cudaMemcpyHostToDevice));
+        k_transform_plain<<<std::min(ceil_div(n, 256), 8 * std::max(g_sm_count, 1)), 256>>>(d.p, static_cast<int>(n), dT.p);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(xyzw, d.p, static_cast<size_t>(n) * 16, cudaMemcpyDeviceToHost));
+        d.release();
+        dT.release();
+    });
+}
+
+// ---- batch ---------------------------------------------------------------------------------------------------
+
+ppcr_status ppcr_align_batch(const ppcr_pair* pairs, int32_t n_pairs, const ppcr_params* params,
+                             const ppcr_options* options, int32_t slots, double* out_T, int32_t* out_n_outer,
+                             int64_t* out_corr)
+{
+    if (!pairs || n_pairs < 0 || !params || !out_T) return fail(PPCR_ERR_INVALID, "bad argument");
+    return guarded([&] {
+        if (n_pairs == 0) return;
+        Engine E;
+        engine_init(E, *params, options);
+        if (slots <= 0) slots = 16;
+        slots = std::min(slots, n_pairs);
+        E.pairs.resize(slots);
+        const bool on_dev = E.opts.input_on_device != 0;
+        for (int base = 0; base < n_pairs; base += slots) {
+            const int wave = std::min(slots, n_pairs - base);
+            for (int s = 0; s < slots; ++s) {
+                const ppcr_pair& pr = pairs[base + std::min(s, wave - 1)];  // pad a short last wave with a repeat
+                pair_setup(E, E.pairs[s], pr.src_xyzw, pr.n_src, pr.tgt_xyzw, pr.n_tgt, on_dev, 1ll << 24);
+            }
+            engine_commit(E);
+            run_to_completion(E);
+            for (int s = 0; s < wave; ++s) {
+                PairState f = download_state(E, s);
+                check_state_error(f);
+                memcpy(out_T + static_cast<size_t>(base + s) * 16, f.T_total, sizeof(double) * 16);
+                if (out_n_outer) out_n_outer[base + s] = f.current_iteration;
+                if (out_corr) out_corr[base + s] = f.K_total;
+            }
+        }
+    });
+}
+
+// ---- sharded pair -------------------------------------------------------------------------------------------
+
+ppcr_status ppcr_shard_export(ppcr_handle* h, int32_t rank, int32_t world, uint8_t* token_out)
+{
+    if (!h || !token_out || world < 1 || world > 8 || rank < 0 || rank >= world) return fail(PPCR_ERR_INVALID, "bad argument");
+    return guarded([&] {
+        static_assert(sizeof(cudaIpcMemHandle_t) <= PPCR_SHARD_TOKEN_BYTES, "token size");
+        Engine& E = h->eng;
+        CK(cudaSetDevice(E.device));
+        Pair& P = E.pairs[0];
+        E.rank = rank;
+        E.world = world;
+        // a dedicated allocation: IPC handles cover whole cudaMalloc blocks
+        P.mailbox.reserve(2ull * 8 * kMailDoubles);
+        CK(cudaMemset(P.mailbox.p, 0, P.mailbox.cap * sizeof(double)));
+        cudaIpcMemHandle_t mh;
+        CK(cudaIpcGetMemHandle(&mh, P.mailbox.p));
+        memset(token_out, 0, PPCR_SHARD_TOKEN_BYTES);
+        memcpy(token_out, &mh, sizeof(mh));
+    });
+}
+
+ppcr_status ppcr_shard_connect(ppcr_handle* h, const uint8_t* tokens)
+{
+    if (!h || !tokens) return fail(PPCR_ERR_INVALID, "bad argument");
+    return guarded([&] {
+        Engine& E = h->eng;
+        CK(cudaSetDevice(E.device));
+        Pair& P = E.pairs[0];
+        if (!P.mailbox.p) throw StatusError{PPCR_ERR_INVALID, "call ppcr_shard_export first"};
+        E.peer_ptrs.assign(E.world, nullptr);
+        for (int r = 0; r < E.world; ++r) {
+            if (r == E.rank) {
+                E.peer_ptrs[r] = P.mailbox.p;
+            } else {
+                cudaIpcMemHandle_t mh;
+                memcpy(&mh, tokens + static_cast<size_t>(r) * PPCR_SHARD_TOKEN_BYTES, sizeof(mh));
+                void* ptr = nullptr;
+                CK(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+                E.peer_ptrs[r] = ptr;
+            }
+        }
+        P.dev.mailbox = P.mailbox.p;
+        for (int r = 0; r < 8; ++r) P.dev.peer_mailbox[r] = r < E.world ? static_cast<double*>(E.peer_ptrs[r]) : nullptr;
+        P.dev.rank = E.rank;
+        P.dev.world = E.world;
+        engine_commit(E);
+    });
+}
+
+}  // extern "C"

@@ -1,7 +1,7 @@
 """Synthetic clouds for the BASELINE.json configs and the reference's own test fixture.
 
 All generators are numpy.random.Generator(PCG64(seed)) driven and return float32 [N,4] clouds
-(x, y, z, 1) -- the 16-byte pcl::PointXYZ record -- so the same bits feed the oracle and the GPU.
+(x, y, z, 1) -- the 16-byte pcl::PointXYZ record -- so the same bits feed the CPU checker and the GPU.
 """
 from __future__ import annotations
 

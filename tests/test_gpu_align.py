@@ -1,0 +1,110 @@
+"""align(): the whole outer loop on the GPU vs the oracle (src/prob_point_cloud_registration.cc:63-158)."""
+import numpy as np
+import pytest
+
+from helpers import pose_delta
+from probabilistic_point_clouds_registration_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_RAD = 1e-4   # north_star: final pose within 1e-4 rad and 1e-4 m of the reference's CPU result
+POSE_TOL_M = 1e-4
+
+
+def _run_both(capi, oracle, src, tgt, driver=0, inner_kind=1, **kw):
+    gp = capi.make_params(**kw)
+    op = oracle.make_params(**kw)
+    with capi.Registration(src, tgt, gp, capi.make_options(driver=driver)) as reg:
+        reg.align()
+        hist = reg.transformation_history()
+        stats = reg.iteration_stats()
+        moved = reg.filtered_source()
+        done = reg.has_converged()
+    ref = oracle.align(src, tgt, op, oracle.make_options(inner_kind=inner_kind), use_grid=True)
+    return hist, stats, moved, done, ref
+
+
+def _assert_parity(hist, stats, moved, ref):
+    assert len(hist) == ref.n_outer, (len(hist), ref.n_outer)
+    for k in range(len(hist)):
+        assert stats[k]["n_correspondences"] == ref.stats[k]["n_correspondences"], k
+        assert stats[k]["lm_iterations"] == ref.stats[k]["lm_iterations"], k
+        assert stats[k]["num_successful_steps"] == ref.stats[k]["num_successful_steps"], k
+        np.testing.assert_allclose(stats[k]["initial_cost"], ref.stats[k]["initial_cost"], rtol=1e-7)
+        np.testing.assert_allclose(stats[k]["final_cost"], ref.stats[k]["final_cost"], rtol=1e-7)
+    rot, tr = pose_delta(hist[-1], ref.transformation)
+    assert rot < POSE_TOL_RAD and tr < POSE_TOL_M, (rot, tr)
+    # the moved float32 cloud: identical up to the last-bit effects of fp64 summation order
+    assert np.max(np.abs(moved[:, :3] - ref.filtered_source[:, :3])) < 1e-5
+
+
+@pytest.mark.parametrize("driver", [1, 2])
+@pytest.mark.parametrize("radius", [1.0, 3.0])
+def test_config1_plane_sphere(capi, oracle, driver, radius):
+    """BASELINE config 1: 10k-point plane+sphere, 10 deg / 0.1 m, t-distribution, struct and CLI radius."""
+    src, tgt, _ = synth.config1_plane_sphere()
+    hist, stats, moved, done, ref = _run_both(capi, oracle, src, tgt, driver=driver, max_neighbours=20, dof=5.0,
+                                              radius=radius)
+    assert done
+    _assert_parity(hist, stats, moved, ref)
+
+
+def test_gaussian_with_voxel_filters(capi, oracle):
+    """BASELINE config 2, reduced: LiDAR-like pair, 20% outliers, -u, voxel filter on both clouds."""
+    src, tgt, _ = synth.lidar_pair(2, 32, 700, outlier_frac=0.2)
+    hist, stats, moved, done, ref = _run_both(capi, oracle, src, tgt, max_neighbours=20, dof=np.inf, radius=3.0,
+                                              source_filter_size=0.25, target_filter_size=0.25)
+    assert len(moved) == ref.n_filtered_src < len(src)
+    _assert_parity(hist, stats, moved, ref)
+
+
+def test_faithful_oracle_small(capi, oracle):
+    """Against the dual-number + dense-QR oracle (the closest restatement of Ceres AutoDiff + DENSE_QR)."""
+    src, tgt, _ = synth.config1_plane_sphere(seed=11, n_plane=700, n_sphere=500)
+    hist, stats, moved, done, ref = _run_both(capi, oracle, src, tgt, inner_kind=0, max_neighbours=20, dof=5.0,
+                                              radius=1.0)
+    _assert_parity(hist, stats, moved, ref)
+
+
+def test_has_converged_semantics(capi):
+    """hasConverged() mutates (registration.cc:138-158): n_iter==0 is converged at once; with the counter at
+    zero it takes n_cost_drop_it + 2 calls of an idle handle to report convergence."""
+    src, tgt, _ = synth.config1_plane_sphere(n_plane=300, n_sphere=300)
+    with capi.Registration(src, tgt, capi.make_params(n_iter=0)) as reg:
+        assert reg.has_converged()
+        reg.align()
+        assert len(reg.transformation_history()) == 0
+        with pytest.raises(IndexError):
+            reg.transformation()
+    with capi.Registration(src, tgt, capi.make_params(n_iter=50, n_cost_drop_it=2)) as reg:
+        assert [reg.has_converged() for _ in range(4)] == [False, False, False, True]
+
+
+def test_n_iter_cap_and_history(capi, oracle):
+    src, tgt, _ = synth.config1_plane_sphere(n_plane=600, n_sphere=400)
+    hist, stats, moved, done, ref = _run_both(capi, oracle, src, tgt, max_neighbours=8, dof=5.0, radius=0.7, n_iter=3)
+    assert len(hist) == 3 and done
+    _assert_parity(hist, stats, moved, ref)
+
+
+def test_zero_cost_runs_all_iterations(capi, oracle):
+    """A perfectly aligned noiseless pair has initial cost 0 -> NaN cost drop -> the counter resets and the loop
+    only stops at n_iter."""
+    tgt = synth.reference_test_cloud()
+    hist, stats, moved, done, ref = _run_both(capi, oracle, tgt, tgt, max_neighbours=1, dof=5.0, radius=0.2, n_iter=12)
+    assert len(hist) == ref.n_outer == 12
+    np.testing.assert_allclose(hist[-1], np.eye(4), atol=1e-12)
+
+
+def test_batch_matches_single(capi):
+    pairs = [synth.lidar_pair(100 + i, 16, 400, random_motion=(2.0, 0.5))[:2] for i in range(5)]
+    params = capi.make_params(max_neighbours=12, radius=2.0, n_iter=30)
+    T, n_outer, corr = capi.align_batch(pairs, params, slots=3)
+    for i, (s, t) in enumerate(pairs):
+        with capi.Registration(s, t, params) as reg:
+            reg.align()
+            h = reg.transformation_history()
+            st = reg.iteration_stats()
+        assert n_outer[i] == len(h)
+        assert corr[i] == sum(x["n_correspondences"] for x in st)
+        np.testing.assert_allclose(T[i], h[-1], rtol=0, atol=1e-12)

@@ -1,0 +1,60 @@
+"""Inner solve (one ceres::Solve of the reference) on the GPU: the reference's exact-association fixture
+(test/PointCloudRegistrationTest.cc:30-116) and oracle parity."""
+import numpy as np
+import pytest
+
+from helpers import csr_from_rows, pose_delta
+from probabilistic_point_clouds_registration_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dof", [np.inf, 5.0])
+def test_reference_exact_association_fixture(capi, oracle, dof):
+    src = synth.reference_test_cloud()
+    T_true = synth.reference_test_transform()
+    tgt = synth.apply_T_like_pcl(src, T_true)                       # pcl::transformPointCloud, T_REG:37
+    n = len(src)
+    idx = np.arange(n, dtype=np.int32).reshape(n, 1)                # identity association, T_REG:41-45
+    cnt = np.ones(n, dtype=np.int32)
+    params = capi.make_params(max_neighbours=3, dof=dof)            # T_REG:46-48
+    pose, T, st = capi.iteration_solve(src, tgt, np.pad(idx, ((0, 0), (0, 2)), constant_values=-1), cnt, params,
+                                       function_tolerance=10e-5)    # T_REG:55
+    aligned = capi.transform(src, T)                                # T_REG:60-62
+    err = np.sqrt(((tgt[:, :3].astype(np.float64) - aligned[:, :3].astype(np.float64)) ** 2).sum(1)).mean()
+    assert err < 1e-6                                               # EXPECT_NEAR(mean_error, 0, 1e-6), T_REG:71
+    # and step-for-step agreement with the oracle's restated Ceres run
+    row_ptr, col = csr_from_rows(idx, cnt)
+    ref = oracle.iteration_solve(src, tgt, row_ptr, col, oracle.make_params(max_neighbours=3, dof=dof),
+                                 oracle.make_options(function_tolerance=10e-5, inner_kind=0))
+    assert st["lm_iterations"] == ref.num_iterations
+    assert st["num_successful_steps"] == ref.num_successful_steps
+    rot, tr = pose_delta(T, ref.T)
+    assert rot < 1e-9 and tr < 1e-9
+    np.testing.assert_allclose(st["initial_cost"], ref.initial_cost, rtol=1e-12)
+
+
+@pytest.mark.parametrize("dof,radius", [(5.0, 1.0), (np.inf, 0.6)])
+def test_inner_solve_matches_oracle_on_radius_association(capi, oracle, dof, radius):
+    src, tgt, _ = synth.config1_plane_sphere(seed=8, n_plane=1200, n_sphere=800)
+    idx, _, cnt, _ = oracle.radius_search(src, tgt, radius, 20)
+    params = capi.make_params(max_neighbours=20, dof=dof, radius=radius)
+    pose, T, st = capi.iteration_solve(src, tgt, idx, cnt, params, function_tolerance=1e-5)
+    row_ptr, col = csr_from_rows(idx, cnt)
+    ref = oracle.iteration_solve(src, tgt, row_ptr, col, oracle.make_params(max_neighbours=20, dof=dof, radius=radius),
+                                 oracle.make_options(function_tolerance=1e-5, inner_kind=0))
+    assert st["lm_iterations"] == ref.num_iterations
+    assert st["n_correspondences"] == int(cnt.sum())
+    rot, tr = pose_delta(T, ref.T)
+    assert rot < 1e-8 and tr < 1e-8
+    np.testing.assert_allclose([st["initial_cost"], st["final_cost"]], [ref.initial_cost, ref.final_cost], rtol=1e-9)
+
+
+def test_no_correspondences(capi):
+    src = np.ones((4, 4), dtype=np.float32)
+    tgt = np.ones((4, 4), dtype=np.float32)
+    idx = np.full((4, 3), -1, dtype=np.int32)
+    cnt = np.zeros(4, dtype=np.int32)
+    pose, T, st = capi.iteration_solve(src, tgt, idx, cnt, capi.make_params(max_neighbours=3))
+    np.testing.assert_array_equal(T, np.eye(4))   # a Ceres problem without residuals leaves the pose alone
+    assert st["initial_cost"] == 0 and st["final_cost"] == 0
