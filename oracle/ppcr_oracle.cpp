@@ -930,7 +930,10 @@ int64_t voxel_grid(const float* in, int64_t n, double leaf_d, float* out)
         int32_t maxb = static_cast<int32_t>(std::floor(hi[a] * inv));
         (void)maxb;
     }
-    if (d[0] * d[1] * d[2] > static_cast<int64_t>(std::numeric_limits<int32_t>::max())) {
+    // PCL multiplies the three int64 extents; the product is formed in double here so that absurd extents (where
+    // PCL's own multiplication would wrap) still take the "too small" branch.  Exact wherever the test is close.
+    if (static_cast<double>(d[0]) * static_cast<double>(d[1]) * static_cast<double>(d[2]) >
+        static_cast<double>(std::numeric_limits<int32_t>::max())) {
         std::memcpy(out, in, static_cast<size_t>(n) * 16);  // "Leaf size is too small": output = input
         return -1;
     }

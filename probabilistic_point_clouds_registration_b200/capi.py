@@ -294,8 +294,9 @@ def voxel_filter(cloud, leaf):
 
 def radius_search(src, tgt, radius, max_nn, cell_size=0.0):
     src, tgt = _cloud(src), _cloud(tgt)
-    idx = np.full((len(src), max_nn), -1, dtype=np.int32)
-    d2 = np.zeros((len(src), max_nn), dtype=np.float32)
+    cols = max(int(max_nn), 1)  # invalid max_nn values are rejected by the library, not by numpy
+    idx = np.full((len(src), cols), -1, dtype=np.int32)
+    d2 = np.zeros((len(src), cols), dtype=np.float32)
     cnt = np.zeros(len(src), dtype=np.int32)
     _check(lib().ppcr_radius_search(src.ctypes.data, len(src), tgt.ctypes.data, len(tgt), float(radius), int(max_nn),
                                     float(cell_size), idx.ctypes.data, d2.ctypes.data, cnt.ctypes.data))

@@ -94,6 +94,12 @@ static int ceil_div(long long a, long long b) { return static_cast<int>((a + b -
 
 static int g_sm_count = 0;
 
+// kernel-launch bookkeeping for ppcr_get_stage_times: every launch site outside the tick adds to the engine the
+// calling thread is currently working for
+static thread_local int32_t g_launch_sink_dummy = 0;
+static thread_local int32_t* g_launch_sink = &g_launch_sink_dummy;
+static inline void note_launches(int n) { *g_launch_sink += n; }
+
 // ------------------------------------------------------------------------------------------------------------
 // one pair: its buffers and the host mirror of its PairDev
 // ------------------------------------------------------------------------------------------------------------
@@ -160,6 +166,7 @@ struct Engine {
 
     ~Engine()
     {
+        if (g_launch_sink == &times.total_launches) g_launch_sink = &g_launch_sink_dummy;
         cudaSetDevice(device);
         for (auto& e : events) {
             cudaEventDestroy(e.a);
@@ -216,6 +223,7 @@ static void exclusive_scan(int* data, int n, DevBuf<int>& sums, bool write_total
     k_scan_sums<<<1, 1024, 0, st>>>(sums.p, n_blocks, write_total ? data + n : nullptr);
     k_scan_add<<<n_blocks, kScanThreads, 0, st>>>(data, n, sums.p, 0);
     CK(cudaGetLastError());
+    note_launches(3);
 }
 
 struct Bbox {
@@ -229,6 +237,7 @@ static Bbox cloud_bbox(const float4* pts, int n, Pair& P, cudaStream_t st)
     CK(cudaMemcpyAsync(P.scratch_u.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
     k_bbox<<<std::min(ceil_div(n, 256), 4 * std::max(g_sm_count, 1)), 256, 0, st>>>(pts, n, P.scratch_u.p);
     CK(cudaGetLastError());
+    note_launches(1);
     unsigned out[6];
     CK(cudaMemcpyAsync(out, P.scratch_u.p, sizeof(out), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -306,9 +315,11 @@ static void build_target_grid(Engine& E, Pair& P, float cell_size_opt, long long
         CK(cudaMemsetAsync(P.cell_start.p, 0, (static_cast<size_t>(g.n_cells) + 2) * sizeof(int), st));
         k_cell_count<<<ceil_div(n, 256), 256, 0, st>>>(P.tgt_raw.p, n, g, P.cell_start.p, P.cell_of.p, P.rank.p);
         CK(cudaGetLastError());
+        note_launches(1);
         if (fixed || trial == 4) break;
         CK(cudaMemsetAsync(P.scratch_ull.p, 0, sizeof(unsigned long long), st));
         k_count_occupied<<<std::min(ceil_div(g.n_cells, 256), 8 * std::max(g_sm_count, 1)), 256, 0, st>>>(P.cell_start.p, g.n_cells, P.scratch_ull.p);
+        note_launches(1);
         unsigned long long occ = 0;
         CK(cudaMemcpyAsync(&occ, P.scratch_ull.p, sizeof(occ), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -324,6 +335,7 @@ static void build_target_grid(Engine& E, Pair& P, float cell_size_opt, long long
     P.tgt_sorted.reserve(n);
     k_cell_scatter<<<ceil_div(n, 256), 256, 0, st>>>(P.tgt_raw.p, n, P.cell_start.p, P.cell_of.p, P.rank.p, P.tgt_sorted.p);
     CK(cudaGetLastError());
+    note_launches(1);
     P.dev.grid = g;
     P.dev.tgt_sorted = P.tgt_sorted.p;
     P.dev.cell_start = P.cell_start.p;
@@ -350,7 +362,8 @@ static int64_t voxel_filter_device(const float4* in, int64_t n, double leaf_d, D
         vg.minb[k] = static_cast<int>(std::floor(bb.lo[k] * inv));
         div[k] = static_cast<int>(std::floor(bb.hi[k] * inv)) - vg.minb[k] + 1;
     }
-    if (d[0] * d[1] * d[2] > static_cast<int64_t>(INT_MAX)) return -1;
+    // formed in double: exact near the threshold, and immune to int64 wrap-around for absurd extents
+    if (static_cast<double>(d[0]) * static_cast<double>(d[1]) * static_cast<double>(d[2]) > static_cast<double>(INT_MAX)) return -1;
     vg.mul[0] = 1;
     vg.mul[1] = div[0];
     vg.mul[2] = div[0] * div[1];
@@ -374,6 +387,7 @@ static int64_t voxel_filter_device(const float4* in, int64_t n, double leaf_d, D
     out.reserve(static_cast<size_t>(n_out) + 1);
     k_voxel_mean<<<ceil_div(n, 256), 256, 0, st>>>(in, keys2.p, vals2.p, head.p, ni, out.p);
     CK(cudaGetLastError());
+    note_launches(3 + 6);  // keys, heads, mean + the radix sort's passes (histogram, scan, 4 x onesweep)
     CK(cudaStreamSynchronize(st));
     keys.release(); vals.release(); keys2.release(); vals2.release(); head.release(); tmp.release();
     return n_out;
@@ -439,6 +453,7 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     if (D.n_src > 0) {
         k_tag_index<<<ceil_div(D.n_src, 256), 256, 0, st>>>(P.src.p, D.n_src);
         CK(cudaGetLastError());
+        note_launches(1);
     }
     if (P.n_tgt > 0) {
         build_target_grid(E, P, E.opts.cell_size, max_cells);
@@ -501,6 +516,7 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
 static void engine_init(Engine& E, const ppcr_params& params, const ppcr_options* options)
 {
     E.params = params;
+    g_launch_sink = &E.times.total_launches;
     if (options) E.opts = *options; else memset(&E.opts, 0, sizeof(E.opts));
     validate_params(params);
     E.device = E.opts.device;
@@ -701,6 +717,7 @@ static void run_to_completion(Engine& E)
     const int np = static_cast<int>(E.pairs.size());
     k_align_begin<<<ceil_div(np, 64), 64, 0, E.stream>>>(E.d_pairs.p, np);
     CK(cudaGetLastError());
+    E.times.total_launches += 1;
     const bool rec = E.opts.record_stage_times != 0;
     bool use_graph = (E.opts.driver == 2) || (E.opts.driver == 0 && !rec && E.world == 1);
     if (use_graph) use_graph = build_graph(E);
@@ -1005,8 +1022,16 @@ ppcr_status ppcr_association(ppcr_handle* h, int32_t* idx, int32_t* count, int64
 ppcr_status ppcr_get_stage_times(ppcr_handle* h, ppcr_stage_times* out)
 {
     if (!h || !out) return fail(PPCR_ERR_INVALID, "null argument");
-    *out = h->eng.times;
-    return PPCR_OK;
+    return guarded([&] {
+        Engine& E = h->eng;
+        CK(cudaSetDevice(E.device));
+        *out = E.times;
+        if (E.graph_ready) {  // the WHILE graph loops on the device: one body execution (4 kernels) per tick
+            const PairState s = download_state(E, 0);
+            out->ticks = s.ticks;
+            out->total_launches = E.times.total_launches + (E.skip_search ? 3 : 4) * s.ticks;
+        }
+    });
 }
 
 ppcr_status ppcr_time_kernel(ppcr_handle* h, int32_t which, int32_t reps, int32_t flush_l2, float* avg_ms,
