@@ -266,10 +266,13 @@ def run_ours(args):
         d2h_bytes = 0
         t0 = time.perf_counter()
         for k in range(args.steps):
+            tk = time.perf_counter()
             r, hist, stats = register_host()
             e2e_corr += sum(s["n_correspondences"] for s in stats)
             d2h_bytes = hist.nbytes + 40 * len(stats)
             r.close()
+            if os.environ.get("PPCR_BENCH_DEBUG"):
+                print(f"[rank {rank}] e2e step {k}: {1e3 * (time.perf_counter() - tk):.2f} ms", file=sys.stderr)
         barrier()
         e2e_s = time.perf_counter() - t0
         clocks = sampler.stop()

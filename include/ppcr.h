@@ -58,7 +58,7 @@ typedef struct ppcr_options {
     int32_t driver;            /* 0 auto, 1 host-stepped ticks, 2 CUDA-graph WHILE loop (no host round trip) */
     int32_t ticks_per_sync;    /* host-stepped driver: ticks enqueued between flag read-backs (default 4) */
     double function_tolerance; /* inner LM tolerance; 0 = the reference's 10e-6 (src/..registration.cc:97) */
-    float cell_size;           /* grid cell edge in metres; 0 = choose from the target density */
+    int32_t leaf_capacity;     /* octree nodes holding more target points than this are split; 0 = default (32) */
     int32_t fast_weights;      /* 0: fp64 log1p/exp for the weights (default); 1: fp32 transcendentals */
     void* stream;              /* cudaStream_t to run on; NULL = the handle creates its own */
     int32_t record_stage_times;/* 1: bracket kernels with CUDA events (host-stepped driver only) */
@@ -135,9 +135,9 @@ ppcr_status ppcr_voxel_filter(const float* xyzw, int64_t n, double leaf, float* 
 
 /* The radius search loop at :72-81 (pcl::KdTreeFLANN::radiusSearch semantics).
  * out_idx/out_d2: [n_src][max_nn], rows sorted ascending by (d2, index); out_count[n_src].
- * cell_size 0 = automatic. */
+ * leaf_capacity 0 = default; the result does not depend on it. */
 ppcr_status ppcr_radius_search(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, int64_t n_tgt,
-                               double radius, int32_t max_nn, float cell_size, int32_t* out_idx, float* out_d2,
+                               double radius, int32_t max_nn, int32_t leaf_capacity, int32_t* out_idx, float* out_d2,
                                int32_t* out_count);
 
 /* WeightUpdaterCallback + one Jacobian/cost evaluation (weight_updater_callback.hpp:36-63,

@@ -57,7 +57,7 @@ class Options(C.Structure):
         ("driver", C.c_int32),
         ("ticks_per_sync", C.c_int32),
         ("function_tolerance", C.c_double),
-        ("cell_size", C.c_float),
+        ("leaf_capacity", C.c_int32),
         ("fast_weights", C.c_int32),
         ("stream", C.c_void_p),
         ("record_stage_times", C.c_int32),
@@ -120,7 +120,7 @@ def lib():
         L.ppcr_get_stage_times.argtypes = [vp, C.POINTER(StageTimes)]
         L.ppcr_time_kernel.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(f64)]
         L.ppcr_voxel_filter.argtypes = [vp, i64, f64, vp, C.POINTER(i64)]
-        L.ppcr_radius_search.argtypes = [vp, i64, vp, i64, f64, i32, C.c_float, vp, vp, vp]
+        L.ppcr_radius_search.argtypes = [vp, i64, vp, i64, f64, i32, i32, vp, vp, vp]
         L.ppcr_weights_normal_eq.argtypes = [vp, i64, vp, i64, vp, vp, i32, f64, i32, vp, vp, i32, vp, vp]
         L.ppcr_iteration_solve.argtypes = [vp, i64, vp, i64, vp, vp, i32, C.POINTER(Params), f64, vp, vp, vp]
         L.ppcr_transform.argtypes = [vp, i64, vp]
@@ -165,7 +165,7 @@ def make_params(max_neighbours=20, dof=5.0, radius=1.0, n_iter=1000, cost_drop_t
     return p
 
 
-def make_options(device=0, input_on_device=False, driver=0, ticks_per_sync=0, function_tolerance=0.0, cell_size=0.0,
+def make_options(device=0, input_on_device=False, driver=0, ticks_per_sync=0, function_tolerance=0.0, leaf_capacity=0,
                  fast_weights=False, stream=None, record_stage_times=False) -> Options:
     o = Options()
     lib().ppcr_default_options(C.byref(o))
@@ -174,7 +174,7 @@ def make_options(device=0, input_on_device=False, driver=0, ticks_per_sync=0, fu
     o.driver = int(driver)
     o.ticks_per_sync = int(ticks_per_sync)
     o.function_tolerance = float(function_tolerance)
-    o.cell_size = float(cell_size)
+    o.leaf_capacity = int(leaf_capacity)
     o.fast_weights = int(bool(fast_weights))
     o.stream = C.c_void_p(stream) if stream else None
     o.record_stage_times = int(bool(record_stage_times))
@@ -292,14 +292,14 @@ def voxel_filter(cloud, leaf):
     return out[:n.value].copy()
 
 
-def radius_search(src, tgt, radius, max_nn, cell_size=0.0):
+def radius_search(src, tgt, radius, max_nn, leaf_capacity=0):
     src, tgt = _cloud(src), _cloud(tgt)
     cols = max(int(max_nn), 1)  # invalid max_nn values are rejected by the library, not by numpy
     idx = np.full((len(src), cols), -1, dtype=np.int32)
     d2 = np.zeros((len(src), cols), dtype=np.float32)
     cnt = np.zeros(len(src), dtype=np.int32)
     _check(lib().ppcr_radius_search(src.ctypes.data, len(src), tgt.ctypes.data, len(tgt), float(radius), int(max_nn),
-                                    float(cell_size), idx.ctypes.data, d2.ctypes.data, cnt.ctypes.data))
+                                    int(leaf_capacity), idx.ctypes.data, d2.ctypes.data, cnt.ctypes.data))
     return idx, d2, cnt
 
 

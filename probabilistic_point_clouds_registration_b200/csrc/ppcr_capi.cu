@@ -93,6 +93,7 @@ struct DevBuf {
 static int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 static int g_sm_count = 0;
+constexpr int kDefaultLeafCap = 32;
 
 // kernel-launch bookkeeping for ppcr_get_stage_times: every launch site outside the tick adds to the engine the
 // calling thread is currently working for
@@ -106,7 +107,12 @@ static inline void note_launches(int n) { *g_launch_sink += n; }
 
 struct Pair {
     DevBuf<float4> src, tgt_raw, tgt_sorted, tmp_cloud;
-    DevBuf<int> cell_start, cell_of, rank, nbr_idx, nbr_cnt, scan_sums;
+    DevBuf<int> nbr_idx, nbr_cnt, scan_sums;
+    DevBuf<TreeNode> nodes;
+    DevBuf<TreeCounters> tree_counters;
+    DevBuf<unsigned long long> sort_keys[2];
+    DevBuf<unsigned> sort_vals[2];
+    DevBuf<unsigned char> sort_tmp;
     DevBuf<float> nbr_x, nbr_y, nbr_z, nbr_d2;
     DevBuf<double> partials, history, mailbox;
     DevBuf<PairState> state;
@@ -121,7 +127,8 @@ struct Pair {
     void release()
     {
         src.release(); tgt_raw.release(); tgt_sorted.release(); tmp_cloud.release();
-        cell_start.release(); cell_of.release(); rank.release(); nbr_idx.release(); nbr_cnt.release();
+        nodes.release(); tree_counters.release(); sort_keys[0].release(); sort_keys[1].release();
+        sort_vals[0].release(); sort_vals[1].release(); sort_tmp.release(); nbr_idx.release(); nbr_cnt.release();
         scan_sums.release(); nbr_x.release(); nbr_y.release(); nbr_z.release(); nbr_d2.release();
         partials.release(); history.release(); mailbox.release(); state.release(); cfg.release(); stats.release();
         scratch_u.release(); scratch_ull.release();
@@ -143,8 +150,7 @@ struct Engine {
     DevBuf<PairDev> d_pairs;
     DevBuf<int> d_active;
     int* h_active = nullptr;  // pinned
-    int lists_R = 1;
-    size_t search_smem = 0;
+    int list_cap = 0;  // register capacity of the search kernel's top-m list; 0 = local-memory list (m > 32)
     // launch geometry (capacity based, so a captured graph stays valid while the slots are refilled)
     int max_tiles = 1, max_eval_blocks = 1, max_tr_blocks = 1;
     bool skip_search = false;
@@ -249,96 +255,90 @@ static Bbox cloud_bbox(const float4* pts, int n, Pair& P, cudaStream_t st)
     return b;
 }
 
-static GridDev make_grid(const Bbox& b, double h, double radius, long long max_cells)
+// Morton keys -> radix sort -> permutation; returns the sorted permutation in P.sort_vals[1]
+static void morton_sort(Pair& P, const float4* pts, int n, const TreeGeom& g, cudaStream_t st)
 {
-    GridDev g{};
-    double ext[3];
-    for (int k = 0; k < 3; ++k) ext[k] = std::max(0.0, static_cast<double>(b.hi[k]) - b.lo[k]);
-    for (;;) {
-        const float inv = static_cast<float>(1.0 / h);
-        long long cells = 1;
-        int dims[3];
-        for (int k = 0; k < 3; ++k) {
-            dims[k] = static_cast<int>(std::floor(static_cast<float>(b.hi[k] - b.lo[k]) * inv)) + 2;
-            cells *= dims[k];
-        }
-        if (cells <= max_cells) {
-            g.ox = b.lo[0];
-            g.oy = b.lo[1];
-            g.oz = b.lo[2];
-            g.inv_h = inv;
-            g.nx = dims[0];
-            g.ny = dims[1];
-            g.nz = dims[2];
-            g.n_cells = static_cast<int>(cells);
-            break;
-        }
-        h *= std::cbrt(static_cast<double>(cells) / static_cast<double>(max_cells)) * 1.02;
+    P.sort_keys[0].reserve(n); P.sort_keys[1].reserve(n);
+    P.sort_vals[0].reserve(n); P.sort_vals[1].reserve(n);
+    k_tree_keys<<<ceil_div(n, 256), 256, 0, st>>>(pts, n, g, P.sort_keys[0].p, P.sort_vals[0].p);
+    CK(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, P.sort_keys[0].p, P.sort_keys[1].p, P.sort_vals[0].p,
+                                       P.sort_vals[1].p, n, 0, 3 * kTreeBits, st));
+    P.sort_tmp.reserve(tmp_bytes);
+    CK(cub::DeviceRadixSort::SortPairs(P.sort_tmp.p, tmp_bytes, P.sort_keys[0].p, P.sort_keys[1].p, P.sort_vals[0].p,
+                                       P.sort_vals[1].p, n, 0, 3 * kTreeBits, st));
+    note_launches(1 + 8);  // keys + the radix sort's passes (histogram, scan, 6 x onesweep)
+}
+
+static TreeGeom make_tree_geom(const Bbox& b, int leaf_cap, int n)
+{
+    TreeGeom g{};
+    double span = 0.0, mag = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        span = std::max(span, static_cast<double>(b.hi[k]) - b.lo[k]);
+        mag = std::max({mag, std::fabs(static_cast<double>(b.lo[k])), std::fabs(static_cast<double>(b.hi[k]))});
     }
-    g.h_cover = static_cast<float>((1.0 / static_cast<double>(g.inv_h)) * (1.0 - 1e-6));
-    const double span = std::max({ext[0], ext[1], ext[2]}) + radius;
-    g.cover_slack = static_cast<float>(16.0 * FLT_EPSILON * span + 1e-30);
+    span = std::max(span, 1e-6 * std::max(mag, 1e-30)) * (1.0 + 1e-5);
+    if (!(span > 0.0)) span = 1.0;
+    g.ox = b.lo[0];
+    g.oy = b.lo[1];
+    g.oz = b.lo[2];
+    g.inv_hf = static_cast<float>(static_cast<double>(1 << kTreeBits) / span);
+    g.hf = static_cast<float>(1.0 / static_cast<double>(g.inv_hf));
+    // bound on the float fuzz of binning a point ((v - o) * inv_hf: three roundings on a value <= span) plus the
+    // rounding of node centres (o + k * half: two roundings on a value <= mag + span), with a wide margin
+    g.slack = static_cast<float>(1e-6 * span + 1e-6 * (mag + span) + 1e-30);
+    g.leaf_cap = leaf_cap;
+    g.n_nodes_cap = static_cast<int>(std::min<long long>(64ll + 8ll * (2ll * n / std::max(leaf_cap, 1) + 8), 1ll << 28));
     return g;
 }
 
-// counting sort of the target into grid cells; chooses the cell edge from the measured occupancy
-static void build_target_grid(Engine& E, Pair& P, float cell_size_opt, long long max_cells)
+// Morton sort of the target + level-by-level octree construction (replaces the kd-tree build)
+static void build_target_tree(Engine& E, Pair& P, int leaf_cap)
 {
     cudaStream_t st = E.stream;
     const int n = static_cast<int>(P.n_tgt);
-    const double radius = E.params.radius;
-    const int m = P.dev.m;
     const Bbox bb = cloud_bbox(P.tgt_raw.p, n, P, st);
     for (int k = 0; k < 3; ++k)
         if (!std::isfinite(bb.lo[k]) || !std::isfinite(bb.hi[k]))
             throw StatusError{PPCR_ERR_INVALID, "target cloud contains non-finite coordinates"};
-    double ext[3];
-    for (int k = 0; k < 3; ++k) ext[k] = std::max(1e-6, static_cast<double>(bb.hi[k]) - bb.lo[k]);
-    std::sort(ext, ext + 3);
-    const double target_occ = std::max(1.5, m / 3.0);
-    double h;
-    const bool fixed = cell_size_opt > 0.f;
-    if (fixed) {
-        h = cell_size_opt;
-    } else {
-        h = std::sqrt(ext[2] * ext[1] * target_occ / std::max(1, n));  // surface-like first guess
-    }
-    const double h_min = radius / 32.0, h_max = radius;
-    h = std::min(std::max(h, h_min), h_max);
-    P.cell_of.reserve(n);
-    P.rank.reserve(n);
-    P.scratch_ull.reserve(2);
-    GridDev g{};
-    for (int trial = 0; trial < 5; ++trial) {
-        g = make_grid(bb, h, radius, max_cells);
-        P.cell_start.reserve(static_cast<size_t>(g.n_cells) + 2);
-        CK(cudaMemsetAsync(P.cell_start.p, 0, (static_cast<size_t>(g.n_cells) + 2) * sizeof(int), st));
-        k_cell_count<<<ceil_div(n, 256), 256, 0, st>>>(P.tgt_raw.p, n, g, P.cell_start.p, P.cell_of.p, P.rank.p);
-        CK(cudaGetLastError());
-        note_launches(1);
-        if (fixed || trial == 4) break;
-        CK(cudaMemsetAsync(P.scratch_ull.p, 0, sizeof(unsigned long long), st));
-        k_count_occupied<<<std::min(ceil_div(g.n_cells, 256), 8 * std::max(g_sm_count, 1)), 256, 0, st>>>(P.cell_start.p, g.n_cells, P.scratch_ull.p);
-        note_launches(1);
-        unsigned long long occ = 0;
-        CK(cudaMemcpyAsync(&occ, P.scratch_ull.p, sizeof(occ), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        const double avg = static_cast<double>(n) / static_cast<double>(std::max<unsigned long long>(occ, 1));
-        const double h_eff = 1.0 / static_cast<double>(g.inv_h);
-        if (avg > target_occ / 1.5 && avg < target_occ * 1.5) break;
-        double h_new = h_eff * std::pow(target_occ / avg, 0.45);
-        h_new = std::min(std::max(h_new, h_min), h_max);
-        if (std::fabs(h_new - h_eff) < 0.05 * h_eff) break;
-        h = h_new;
-    }
-    exclusive_scan(P.cell_start.p, g.n_cells, P.scan_sums, true, st);
+    const TreeGeom g = make_tree_geom(bb, leaf_cap, n);
+    morton_sort(P, P.tgt_raw.p, n, g, st);
     P.tgt_sorted.reserve(n);
-    k_cell_scatter<<<ceil_div(n, 256), 256, 0, st>>>(P.tgt_raw.p, n, P.cell_start.p, P.cell_of.p, P.rank.p, P.tgt_sorted.p);
+    k_tree_gather<<<ceil_div(n, 256), 256, 0, st>>>(P.tgt_raw.p, P.sort_vals[1].p, n, 0, P.tgt_sorted.p);
+    CK(cudaGetLastError());
+    P.nodes.reserve(static_cast<size_t>(g.n_nodes_cap) + 8);
+    P.tree_counters.reserve(1);
+    CK(cudaMemsetAsync(P.nodes.p, 0xff, (static_cast<size_t>(g.n_nodes_cap) + 8) * sizeof(TreeNode), st));
+    k_tree_root<<<1, 32, 0, st>>>(P.nodes.p, n, g, P.tree_counters.p);
+    long long level_nodes = 1;
+    for (int level = 0; level < kTreeBits; ++level) {
+        const int blocks = static_cast<int>(std::min<long long>((level_nodes + 127) / 128, 8ll * std::max(g_sm_count, 1)));
+        k_tree_split_level<<<blocks, 128, 0, st>>>(g, P.sort_keys[1].p, P.nodes.p, P.tree_counters.p, level);
+        level_nodes = std::min<long long>(level_nodes * 8, g.n_nodes_cap);
+    }
+    CK(cudaGetLastError());
+    note_launches(2 + kTreeBits);
+    P.dev.tree = g;
+    P.dev.nodes = P.nodes.p;
+    P.dev.tgt_sorted = P.tgt_sorted.p;
+    P.dev.tgt_raw = P.tgt_raw.p;
+}
+
+// Sorts the (tagged) source cloud along the target tree's Morton curve: the queries of one warp then open the same
+// nodes.  Done once; the cloud moves rigidly and by little, so the locality survives the outer iterations.
+static void sort_source(Engine& E, Pair& P)
+{
+    cudaStream_t st = E.stream;
+    const int n = static_cast<int>(P.n_src);
+    if (n <= 1) return;
+    morton_sort(P, P.src.p, n, P.dev.tree, st);
+    P.tmp_cloud.reserve(n);
+    k_tree_gather<<<ceil_div(n, 256), 256, 0, st>>>(P.src.p, P.sort_vals[1].p, n, 1, P.tmp_cloud.p);
     CK(cudaGetLastError());
     note_launches(1);
-    P.dev.grid = g;
-    P.dev.tgt_sorted = P.tgt_sorted.p;
-    P.dev.cell_start = P.cell_start.p;
+    std::swap(P.src, P.tmp_cloud);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -417,7 +417,7 @@ static void upload_cloud(DevBuf<float4>& dst, const float* src, int64_t n, bool 
 // Everything the reference constructor does (registration.cc:15-49) plus the grid build that replaces the
 // per-iteration kd-tree construction (:66-67; the target never changes after the constructor).
 static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, const float* tgt, int64_t n_tgt,
-                       bool on_device, long long max_cells)
+                       bool on_device)
 {
     if (n_src < 0 || n_tgt < 0 || (n_src > 0 && !src) || (n_tgt > 0 && !tgt)) throw StatusError{PPCR_ERR_INVALID, "null cloud"};
     if (n_src > INT_MAX / 2 || n_tgt > INT_MAX / 2) throw StatusError{PPCR_ERR_UNSUPPORTED, "clouds above 2^30 points are not supported"};
@@ -448,26 +448,30 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     if (D.n_pad == 0) D.n_pad = 32;
     D.m = static_cast<int>(std::min<int64_t>(prm.max_neighbours, std::max<int64_t>(P.n_tgt, 1)));
     D.r2f = static_cast<float>(prm.radius * prm.radius);
-    D.rpad = std::nextafter(static_cast<float>(prm.radius * (1.0 + 1e-5)), INFINITY);
     D.src = P.src.p;
     if (D.n_src > 0) {
         k_tag_index<<<ceil_div(D.n_src, 256), 256, 0, st>>>(P.src.p, D.n_src);
         CK(cudaGetLastError());
         note_launches(1);
     }
+    const int leaf_cap = E.opts.leaf_capacity > 0 ? E.opts.leaf_capacity : kDefaultLeafCap;
     if (P.n_tgt > 0) {
-        build_target_grid(E, P, E.opts.cell_size, max_cells);
+        build_target_tree(E, P, leaf_cap);
     } else {
-        // an empty target: a 1-cell grid with no points, every search returns nothing
-        P.cell_start.reserve(4);
-        CK(cudaMemsetAsync(P.cell_start.p, 0, 4 * sizeof(int), st));
+        // an empty target: a root with no points, every search returns nothing
+        Bbox bb{};
+        bb.hi[0] = bb.hi[1] = bb.hi[2] = 1.f;
+        P.nodes.reserve(16);
         P.tgt_sorted.reserve(1);
-        GridDev g{};
-        g.inv_h = 1.f; g.h_cover = 1.f; g.cover_slack = 0.f; g.nx = g.ny = g.nz = 1; g.n_cells = 1;
-        D.grid = g;
+        const TreeGeom g = make_tree_geom(bb, leaf_cap, 0);
+        CK(cudaMemsetAsync(P.nodes.p, 0xff, 16 * sizeof(TreeNode), st));
+        D.tree = g;
+        D.nodes = P.nodes.p;
         D.tgt_sorted = P.tgt_sorted.p;
-        D.cell_start = P.cell_start.p;
+        D.tgt_raw = P.tgt_raw.p;
     }
+    sort_source(E, P);
+    D.src = P.src.p;
     const size_t plane = static_cast<size_t>(D.m) * D.n_pad;
     P.nbr_x.reserve(plane); P.nbr_y.reserve(plane); P.nbr_z.reserve(plane); P.nbr_idx.reserve(plane);
     P.nbr_cnt.reserve(D.n_pad);
@@ -535,12 +539,6 @@ static void engine_init(Engine& E, const ppcr_params& params, const ppcr_options
     if (env && E.opts.driver == 0) E.opts.driver = atoi(env);
 }
 
-template <int R>
-static void set_search_attr(size_t smem)
-{
-    CK(cudaFuncSetAttribute(k_search<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-}
-
 // publishes the PairDev array and derives the launch geometry
 static void engine_commit(Engine& E)
 {
@@ -559,12 +557,9 @@ static void engine_commit(Engine& E)
     CK(cudaMemcpyAsync(E.d_pairs.p, host.data(), sizeof(PairDev) * np, cudaMemcpyHostToDevice, E.stream));
     CK(cudaStreamSynchronize(E.stream));
     const int cap_m = E.params.max_neighbours;
-    E.lists_R = cap_m <= 32 ? 1 : (cap_m <= 64 ? 2 : 4);
-    E.search_smem = static_cast<size_t>(cap_m) * kTileQ * 20;
-    if (E.lists_R == 1) set_search_attr<1>(E.search_smem);
-    else if (E.lists_R == 2) set_search_attr<2>(E.search_smem);
-    else set_search_attr<4>(E.search_smem);
-    const int tiles = ceil_div(max_src, kTileQ);
+    E.list_cap = cap_m <= 4 ? 4 : cap_m <= 8 ? 8 : cap_m <= 12 ? 12 : cap_m <= 16 ? 16 : cap_m <= 20 ? 20
+               : cap_m <= 24 ? 24 : cap_m <= 32 ? 32 : 0;
+    const int tiles = ceil_div(max_src, kSearchThreads);
     const int trb = std::max(1, std::min(ceil_div(max_src, 256), 8 * std::max(g_sm_count, 1)));
     if (tiles > E.max_tiles || max_eval > E.max_eval_blocks || trb > E.max_tr_blocks) {
         E.max_tiles = std::max(E.max_tiles, tiles);
@@ -609,9 +604,16 @@ static void launch_search(Engine& E)
 {
     const int np = static_cast<int>(E.pairs.size());
     dim3 grid(E.max_tiles, np);
-    if (E.lists_R == 1) k_search<1><<<grid, kSearchWarps * 32, E.search_smem, E.stream>>>(E.d_pairs.p);
-    else if (E.lists_R == 2) k_search<2><<<grid, kSearchWarps * 32, E.search_smem, E.stream>>>(E.d_pairs.p);
-    else k_search<4><<<grid, kSearchWarps * 32, E.search_smem, E.stream>>>(E.d_pairs.p);
+    switch (E.list_cap) {
+        case 4: k_search<4><<<grid, kSearchThreads, 0, E.stream>>>(E.d_pairs.p); break;
+        case 8: k_search<8><<<grid, kSearchThreads, 0, E.stream>>>(E.d_pairs.p); break;
+        case 12: k_search<12><<<grid, kSearchThreads, 0, E.stream>>>(E.d_pairs.p); break;
+        case 16: k_search<16><<<grid, kSearchThreads, 0, E.stream>>>(E.d_pairs.p); break;
+        case 20: k_search<20><<<grid, kSearchThreads, 0, E.stream>>>(E.d_pairs.p); break;
+        case 24: k_search<24><<<grid, kSearchThreads, 0, E.stream>>>(E.d_pairs.p); break;
+        case 32: k_search<32><<<grid, kSearchThreads, 0, E.stream>>>(E.d_pairs.p); break;
+        default: k_search<0><<<grid, kSearchThreads, 0, E.stream>>>(E.d_pairs.p); break;
+    }
 }
 
 static void launch_eval(Engine& E)
@@ -764,6 +766,24 @@ static void set_phase(Engine& E, int p, int phase)
     CK(cudaStreamSynchronize(E.stream));
 }
 
+// original (caller-order) index of every device row of the Morton-sorted source
+static std::vector<int> source_order(Engine& E, int p)
+{
+    Pair& P = E.pairs[p];
+    const int n = P.dev.n_src;
+    std::vector<float4> h(static_cast<size_t>(std::max(n, 1)));
+    if (n > 0) CK(cudaMemcpyAsync(h.data(), P.src.p, static_cast<size_t>(n) * sizeof(float4), cudaMemcpyDeviceToHost, E.stream));
+    CK(cudaStreamSynchronize(E.stream));
+    std::vector<int> order(static_cast<size_t>(n));
+    for (int j = 0; j < n; ++j) {
+        int w;
+        memcpy(&w, &h[j].w, 4);
+        if (w < 0 || w >= n) throw StatusError{PPCR_ERR_CUDA, "corrupt source index tag"};
+        order[j] = w;
+    }
+    return order;
+}
+
 // slot-major device planes -> row-major [n_src][max_nn] host arrays
 static void download_association(Engine& E, int p, int32_t* idx, float* d2, int32_t* count, int64_t n_src, int max_nn)
 {
@@ -780,13 +800,15 @@ static void download_association(Engine& E, int p, int32_t* idx, float* d2, int3
         CK(cudaMemcpyAsync(h_d2.data(), D.nbr_d2, h_d2.size() * sizeof(float), cudaMemcpyDeviceToHost, E.stream));
     }
     CK(cudaStreamSynchronize(E.stream));
-    for (int64_t i = 0; i < n_src; ++i) {
-        const int c = h_cnt[i];
+    const std::vector<int> order = source_order(E, p);
+    for (int64_t j = 0; j < n_src; ++j) {  // device row j is the caller's point order[j]
+        const int64_t i = order[j];
+        const int c = h_cnt[j];
         count[i] = c;
         for (int k = 0; k < max_nn; ++k) {
             const bool have = k < c && k < D.m;
-            idx[i * max_nn + k] = have ? h_idx[static_cast<size_t>(k) * D.n_pad + i] : -1;
-            if (d2) d2[i * max_nn + k] = have ? h_d2[static_cast<size_t>(k) * D.n_pad + i] : 0.f;
+            idx[i * max_nn + k] = have ? h_idx[static_cast<size_t>(k) * D.n_pad + j] : -1;
+            if (d2) d2[i * max_nn + k] = have ? h_d2[static_cast<size_t>(k) * D.n_pad + j] : 0.f;
         }
     }
 }
@@ -801,15 +823,17 @@ static void upload_association(Engine& E, int p, const float* tgt_xyzw, int64_t 
     std::vector<float> hx(plane, 0.f), hy(plane, 0.f), hz(plane, 0.f);
     std::vector<int> hi(plane, -1), hc(D.n_pad, 0);
     int64_t K = 0;
-    for (int64_t i = 0; i < D.n_src; ++i) {
+    const std::vector<int> order = source_order(E, p);
+    for (int64_t row = 0; row < D.n_src; ++row) {  // device row `row` is the caller's point order[row]
+        const int64_t i = order[row];
         const int c = count[i];
         if (c < 0 || c > max_nn || c > D.m) throw StatusError{PPCR_ERR_INVALID, "association count out of range"};
-        hc[i] = c;
+        hc[row] = c;
         K += c;
         for (int k = 0; k < c; ++k) {
             const int j = idx[i * max_nn + k];
             if (j < 0 || j >= n_tgt) throw StatusError{PPCR_ERR_INVALID, "association index out of range"};
-            const size_t o = static_cast<size_t>(k) * D.n_pad + i;
+            const size_t o = static_cast<size_t>(k) * D.n_pad + row;
             hx[o] = tgt_xyzw[4 * static_cast<size_t>(j)];
             hy[o] = tgt_xyzw[4 * static_cast<size_t>(j) + 1];
             hz[o] = tgt_xyzw[4 * static_cast<size_t>(j) + 2];
@@ -895,7 +919,7 @@ ppcr_status ppcr_create_ex(const float* src, int64_t n_src, const float* tgt, in
         Engine& E = h->eng;
         engine_init(E, *params, options);
         E.pairs.resize(1);
-        pair_setup(E, E.pairs[0], src, n_src, tgt, n_tgt, E.opts.input_on_device != 0, 1ll << 26);
+        pair_setup(E, E.pairs[0], src, n_src, tgt, n_tgt, E.opts.input_on_device != 0);
         engine_commit(E);
     });
     if (s != PPCR_OK) {
@@ -972,6 +996,7 @@ ppcr_status ppcr_iteration_stats(ppcr_handle* h, ppcr_iter_stats* out, int32_t* 
     });
 }
 
+// clear_w: the cloud is the index-tagged, Morton-sorted source -- hand it back in the caller's order with w = 1
 static void download_cloud(Engine& E, const float4* dev, int64_t n, float* out, int64_t* n_inout, bool clear_w)
 {
     if (!n_inout) throw StatusError{PPCR_ERR_INVALID, "null argument"};
@@ -980,11 +1005,22 @@ static void download_cloud(Engine& E, const float4* dev, int64_t n, float* out, 
         if (out) throw StatusError{PPCR_ERR_SMALL_BUFFER, "output buffer too small"};
         return;
     }
-    if (n > 0) {
+    if (n > 0 && !clear_w) {
         CK(cudaMemcpyAsync(out, dev, static_cast<size_t>(n) * sizeof(float4), cudaMemcpyDeviceToHost, E.stream));
         CK(cudaStreamSynchronize(E.stream));
-        if (clear_w)
-            for (int64_t i = 0; i < n; ++i) out[4 * i + 3] = 1.0f;
+    } else if (n > 0) {
+        std::vector<float4> h(static_cast<size_t>(n));
+        CK(cudaMemcpyAsync(h.data(), dev, static_cast<size_t>(n) * sizeof(float4), cudaMemcpyDeviceToHost, E.stream));
+        CK(cudaStreamSynchronize(E.stream));
+        for (int64_t j = 0; j < n; ++j) {
+            int w;
+            memcpy(&w, &h[j].w, 4);
+            if (w < 0 || w >= n) throw StatusError{PPCR_ERR_CUDA, "corrupt source index tag"};
+            out[4 * static_cast<int64_t>(w)] = h[j].x;
+            out[4 * static_cast<int64_t>(w) + 1] = h[j].y;
+            out[4 * static_cast<int64_t>(w) + 2] = h[j].z;
+            out[4 * static_cast<int64_t>(w) + 3] = 1.0f;
+        }
     }
     *n_inout = n;
 }
@@ -1061,7 +1097,7 @@ ppcr_status ppcr_time_kernel(ppcr_handle* h, int32_t which, int32_t reps, int32_
                 case 0: launch_search(E); break;
                 case 1: launch_eval(E); break;
                 case 2: k_transform<<<dim3(E.max_tr_blocks, 1), 256, 0, E.stream>>>(E.d_pairs.p, 1, E.d_active.p, E.cond, 0); break;
-                default: build_target_grid(E, P, 1.0f / D.grid.inv_h, 1ll << 26); break;
+                default: build_target_tree(E, P, D.tree.leaf_cap); break;
             }
             CK(cudaEventRecord(ev[2 * r + 1], E.stream));
         }
@@ -1083,7 +1119,7 @@ ppcr_status ppcr_time_kernel(ppcr_handle* h, int32_t which, int32_t reps, int32_
                 case 0: *algorithmic_bytes = 16.0 * ns + 16.0 * nt + 4.0 * ns + 16.0 * K; break;  // query, target, count, 3 planes + idx
                 case 1: *algorithmic_bytes = 16.0 * ns + 4.0 * ns + 12.0 * K; break;              // source, count, 3 planes
                 case 2: *algorithmic_bytes = 32.0 * ns; break;
-                default: *algorithmic_bytes = 36.0 * nt + 8.0 * D.grid.n_cells; break;
+                default: *algorithmic_bytes = 44.0 * nt; break;  // read 16, key+value 12, sorted write 16
             }
         }
         CK(cudaMemcpyAsync(P.state.p, &saved, sizeof(saved), cudaMemcpyHostToDevice, E.stream));
@@ -1119,7 +1155,7 @@ ppcr_status ppcr_voxel_filter(const float* xyzw, int64_t n, double leaf, float* 
 }
 
 ppcr_status ppcr_radius_search(const float* src, int64_t n_src, const float* tgt, int64_t n_tgt, double radius,
-                               int32_t max_nn, float cell_size, int32_t* out_idx, float* out_d2, int32_t* out_count)
+                               int32_t max_nn, int32_t leaf_capacity, int32_t* out_idx, float* out_d2, int32_t* out_count)
 {
     if (!out_idx || !out_count) return fail(PPCR_ERR_INVALID, "null output");
     return guarded([&] {
@@ -1129,12 +1165,12 @@ ppcr_status ppcr_radius_search(const float* src, int64_t n_src, const float* tgt
         prm.max_neighbours = max_nn;
         ppcr_options opt;
         ppcr_default_options(&opt);
-        opt.cell_size = cell_size;
+        opt.leaf_capacity = leaf_capacity;
         Engine E;
         engine_init(E, prm, &opt);
         E.pairs.resize(1);
         E.pairs[0].want_d2 = true;
-        pair_setup(E, E.pairs[0], src, n_src, tgt, n_tgt, false, 1ll << 26);
+        pair_setup(E, E.pairs[0], src, n_src, tgt, n_tgt, false);
         engine_commit(E);
         set_phase(E, 0, PH_SEARCH);
         if (n_src > 0) launch_search(E);
@@ -1161,11 +1197,10 @@ ppcr_status ppcr_weights_normal_eq(const float* src, int64_t n_src, const float*
         ppcr_options opt;
         ppcr_default_options(&opt);
         opt.fast_weights = fast_weights;
-        opt.cell_size = 1.0f;
         Engine E;
         engine_init(E, prm, &opt);
         E.pairs.resize(1);
-        pair_setup(E, E.pairs[0], src, n_src, tgt, n_tgt, false, 1ll << 22);
+        pair_setup(E, E.pairs[0], src, n_src, tgt, n_tgt, false);
         E.pairs[0].dev.wcfg = make_weight_cfg(dof, dimension > 0 ? dimension : 3);
         engine_commit(E);
         upload_association(E, 0, tgt, n_tgt, idx, count, max_nn);
@@ -1197,9 +1232,12 @@ ppcr_status ppcr_weights_normal_eq(const float* src, int64_t n_src, const float*
             std::vector<double> hw(plane);
             CK(cudaMemcpyAsync(hw.data(), dw.p, plane * sizeof(double), cudaMemcpyDeviceToHost, E.stream));
             CK(cudaStreamSynchronize(E.stream));
-            for (int64_t i = 0; i < n_src; ++i)
+            const std::vector<int> order = source_order(E, 0);
+            for (int64_t row = 0; row < n_src; ++row) {
+                const int64_t i = order[row];
                 for (int k = 0; k < max_nn; ++k)
-                    weights[i * max_nn + k] = (k < count[i]) ? hw[static_cast<size_t>(k) * D.n_pad + i] : 0.0;
+                    weights[i * max_nn + k] = (k < count[i]) ? hw[static_cast<size_t>(k) * D.n_pad + row] : 0.0;
+            }
             dw.release();
         }
     });
@@ -1219,12 +1257,11 @@ ppcr_status ppcr_iteration_solve(const float* src, int64_t n_src, const float* t
         ppcr_options opt;
         ppcr_default_options(&opt);
         opt.function_tolerance = function_tolerance;
-        opt.cell_size = static_cast<float>(prm.radius);
         opt.driver = 1;
         Engine E;
         engine_init(E, prm, &opt);
         E.pairs.resize(1);
-        pair_setup(E, E.pairs[0], src, n_src, tgt, n_tgt, false, 1ll << 22);
+        pair_setup(E, E.pairs[0], src, n_src, tgt, n_tgt, false);
         engine_commit(E);
         E.skip_search = true;
         // align_begin would reset K, so arm the state by hand: first loop test passed, association given
@@ -1290,7 +1327,7 @@ ppcr_status ppcr_align_batch(const ppcr_pair* pairs, int32_t n_pairs, const ppcr
             const int wave = std::min(slots, n_pairs - base);
             for (int s = 0; s < slots; ++s) {
                 const ppcr_pair& pr = pairs[base + std::min(s, wave - 1)];  // pad a short last wave with a repeat
-                pair_setup(E, E.pairs[s], pr.src_xyzw, pr.n_src, pr.tgt_xyzw, pr.n_tgt, on_dev, 1ll << 24);
+                pair_setup(E, E.pairs[s], pr.src_xyzw, pr.n_src, pr.tgt_xyzw, pr.n_tgt, on_dev);
             }
             engine_commit(E);
             run_to_completion(E);

@@ -1,7 +1,8 @@
 // ppcr_kernels.cuh -- sm_100a kernels of the registration hot path.
 //
-//   grid build      k_bbox, k_cell_count, k_scan_*, k_cell_scatter   (replaces the kd-tree build, registration.cc:66-67)
-//   radius search   k_search<R>                                       (replaces the radiusSearch loop, :72-81, and the
+//   tree build      k_bbox, k_tree_keys, (radix sort), k_tree_gather, k_tree_root, k_tree_split_level
+//                                                                     (replaces the kd-tree build, registration.cc:66-67)
+//   radius search   k_search<CAP>                                     (replaces the radiusSearch loop, :72-81, and the
 //                                                                      CSR assembly, :69-83)
 //   weights + J^TWJ k_eval<FAST>                                      (WeightUpdaterCallback, ProbabilisticWeights,
 //                                                                      ErrorTerm + Ceres' Jacobian evaluation)
@@ -11,9 +12,11 @@
 //   voxel filter    k_voxel_* (+ a radix sort of the voxel keys)      (pcl::VoxelGrid, :24-41)
 //
 // Data layout in HBM (per pair):
-//   tgt_sorted  float4[n_tgt]      target points counting-sorted by grid cell, .w = original index (int bits)
-//   cell_start  int[n_cells + 1]   CSR over cells, x fastest, so a run of x-adjacent cells is one contiguous range
-//   src         float4[n_src]      the moving source cloud (filtered), .w = original index
+//   tgt_sorted  float4[n_tgt]      target points in Morton order, .w = original index (int bits)
+//   tgt_raw     float4[n_tgt]      target points in caller order (coordinate gather of the found neighbours)
+//   nodes       TreeNode[]         linear octree over tgt_sorted (ppcr_tree.h), 32-byte records, 8 children adjacent
+//   src         float4[n_src]      the moving source cloud (filtered), Morton-sorted once so that the 32 queries of a
+//                                  warp walk the same part of the tree; .w = original index
 //   nbr_x/y/z   float[m][n_pad]    slot-major neighbour coordinates: entry (k, i) is the k-th nearest target of
 //   nbr_idx     int[m][n_pad]      source i, so one warp reads 32 consecutive floats per slot (fully coalesced)
 //   nbr_cnt     int[n_pad]
@@ -27,34 +30,25 @@
 
 #include "ppcr_eval.h"
 #include "ppcr_lm.h"
+#include "ppcr_tree.h"
 
 namespace ppcr {
 
-constexpr int kTileQ = 32;        // queries per search block (one output tile)
-constexpr int kSearchWarps = 8;   // warps per search block
+constexpr int kSearchThreads = 128;  // one query per thread
 constexpr int kEvalThreads = 256;
 constexpr unsigned kFull = 0xffffffffu;
 
-struct GridDev {
-    float ox, oy, oz;   // origin = min corner of the target bounding box
-    float inv_h;        // 1 / cell edge
-    float h_cover;      // cell edge, rounded down: used for the "covered radius" bound of the shell scan
-    float cover_slack;  // absolute slack for float cell-boundary fuzz
-    int nx, ny, nz;
-    int n_cells;
-};
-
 struct PairDev {
     const float4* tgt_sorted;
-    const int* cell_start;
-    GridDev grid;
+    const float4* tgt_raw;
+    const TreeNode* nodes;
+    TreeGeom tree;
     int n_tgt;
     float4* src;
     int n_src;
     int n_pad;
     int m;          // result capacity = min(max_neighbours, n_tgt)
     float r2f;      // float(radius * radius): strict membership bound (FLANN)
-    float rpad;     // radius padded upwards, for the conservative cell window
     float* nbr_x;
     float* nbr_y;
     float* nbr_z;
@@ -79,29 +73,7 @@ struct PairDev {
 constexpr int kMailDoubles = 32;  // 24 moments + K + sequence stamp, padded
 
 // ------------------------------------------------------------------------------------------------------------
-// small helpers
-// ------------------------------------------------------------------------------------------------------------
-
-__device__ __forceinline__ int cell_coord(float v, float origin, float inv_h)
-{
-    // the same expression bins targets and locates queries; monotone in v, saturating conversion
-    return __float2int_rd(__fmul_rn(__fsub_rn(v, origin), inv_h));
-}
-
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
-
-__device__ __forceinline__ float dist2_exact(float qx, float qy, float qz, float px, float py, float pz)
-{
-    // FLANN L2_Simple<float>: ((dx*dx) + dy*dy) + dz*dz in float32 with NO fused multiply-add
-    const float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
-    float acc = __fmul_rn(dx, dx);
-    acc = __fadd_rn(acc, __fmul_rn(dy, dy));
-    acc = __fadd_rn(acc, __fmul_rn(dz, dz));
-    return acc;
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// grid build
+// bounding box
 // ------------------------------------------------------------------------------------------------------------
 
 // min / max corner of a cloud: out[0..2] = min, out[3..5] = max, encoded as order-preserving uints
@@ -150,35 +122,10 @@ __global__ void k_bbox(const float4* __restrict__ pts, int n, unsigned* __restri
     }
 }
 
-__device__ __forceinline__ int cell_of_point(const GridDev& g, float x, float y, float z)
-{
-    const int cx = clampi(cell_coord(x, g.ox, g.inv_h), 0, g.nx - 1);
-    const int cy = clampi(cell_coord(y, g.oy, g.inv_h), 0, g.ny - 1);
-    const int cz = clampi(cell_coord(z, g.oz, g.inv_h), 0, g.nz - 1);
-    return (cz * g.ny + cy) * g.nx + cx;
-}
+// ------------------------------------------------------------------------------------------------------------
+// exclusive scan, three passes; each block owns kScanTile consecutive items (used by the voxel filter)
+// ------------------------------------------------------------------------------------------------------------
 
-// pass 1 of the counting sort: cell of every point and its arrival rank inside the cell
-__global__ void k_cell_count(const float4* __restrict__ pts, int n, GridDev g, int* __restrict__ counts,
-                             int* __restrict__ cell_of, int* __restrict__ rank)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 p = pts[i];
-    const int c = cell_of_point(g, p.x, p.y, p.z);
-    cell_of[i] = c;
-    rank[i] = atomicAdd(counts + c, 1);
-}
-
-__global__ void k_count_occupied(const int* __restrict__ counts, int n_cells, unsigned long long* __restrict__ out)
-{
-    int local = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += gridDim.x * blockDim.x) local += counts[i] > 0;
-    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(kFull, local, o);
-    if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, static_cast<unsigned long long>(local));
-}
-
-// exclusive scan, three passes; each block owns kScanTile consecutive items
 constexpr int kScanThreads = 256;
 constexpr int kScanPerThread = 8;
 constexpr int kScanTile = kScanThreads * kScanPerThread;
@@ -266,286 +213,159 @@ __global__ void k_scan_add(int* __restrict__ data, int n, const int* __restrict_
     (void)total_slot;
 }
 
-// pass 3 of the counting sort: scatter into cell order; .w carries the original index
-__global__ void k_cell_scatter(const float4* __restrict__ pts, int n, const int* __restrict__ cell_start,
-                               const int* __restrict__ cell_of, const int* __restrict__ rank,
-                               float4* __restrict__ sorted)
+// ------------------------------------------------------------------------------------------------------------
+// octree build over the Morton-sorted target (ppcr_tree.h)
+// ------------------------------------------------------------------------------------------------------------
+
+__global__ void k_tree_keys(const float4* __restrict__ pts, int n, TreeGeom g, unsigned long long* __restrict__ keys,
+                            unsigned* __restrict__ vals)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float4 p = pts[i];
-    p.w = __int_as_float(i);
-    sorted[cell_start[cell_of[i]] + rank[i]] = p;
+    const float4 p = pts[i];
+    keys[i] = tree_key(g, p.x, p.y, p.z);
+    vals[i] = static_cast<unsigned>(i);
 }
 
-// tag every point with its own index in .w (source cloud kept in caller order)
+// sorted[j] = pts[vals[j]] with .w = the original index.  keep_w: the input's own .w is carried instead (a cloud that
+// is already tagged, i.e. re-sorting the source)
+__global__ void k_tree_gather(const float4* __restrict__ pts, const unsigned* __restrict__ vals, int n, int keep_w,
+                              float4* __restrict__ sorted)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const unsigned i = vals[j];
+    float4 p = pts[i];
+    if (!keep_w) p.w = __int_as_float(static_cast<int>(i));
+    sorted[j] = p;
+}
+
+// tag every point with its own index in .w (the source keeps its caller-order identity through the Morton sort)
 __global__ void k_tag_index(float4* __restrict__ pts, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) pts[i].w = __int_as_float(i);
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// radius search: one warp per query, Chebyshev shells of grid cells, warp-resident sorted result list
-// ------------------------------------------------------------------------------------------------------------
-
-constexpr unsigned long long kKeyInf = 0xffffffffffffffffull;
-
-template <int R>
-struct WarpList {  // entry e = 32*r + lane holds the e-th smallest (d2, index) key found so far
-    unsigned long long key[R];
-    int spos[R];  // position of that target in tgt_sorted
+struct TreeCounters {
+    int n_nodes;
+    int level_begin[kTreeBits + 3];  // nodes of level l are [level_begin[l], level_begin[l+1])
+    int ticket[kTreeBits + 1];
 };
 
-template <int R>
-__device__ __forceinline__ void list_insert(WarpList<R>& L, unsigned long long k, int sp, int lane, int m)
+__global__ void k_tree_root(TreeNode* __restrict__ nodes, int n, TreeGeom g, TreeCounters* __restrict__ tc)
 {
-    int pos = 0;
-#pragma unroll
-    for (int r = 0; r < R; ++r) pos += __popc(__ballot_sync(kFull, L.key[r] < k));
-#pragma unroll
-    for (int r = R - 1; r >= 0; --r) {
-        const int base = 32 * r;
-        if (pos >= base + 32) continue;  // warp-uniform
-        unsigned long long up_k = __shfl_up_sync(kFull, L.key[r], 1);
-        int up_s = __shfl_up_sync(kFull, L.spos[r], 1);
-        if (r > 0) {
-            const unsigned long long ck = __shfl_sync(kFull, L.key[r > 0 ? r - 1 : 0], 31);
-            const int cs = __shfl_sync(kFull, L.spos[r > 0 ? r - 1 : 0], 31);
-            if (lane == 0) {
-                up_k = ck;
-                up_s = cs;
-            }
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    TreeNode r;
+    r.begin = 0;
+    r.end = n;
+    r.child = -1;
+    r.mask = 0;
+    tree_node_box(g, 0, 0ull, &r);
+    nodes[0] = r;
+    tc->n_nodes = 1;
+    for (int l = 0; l < kTreeBits + 3; ++l) tc->level_begin[l] = l == 0 ? 0 : 1;
+    for (int l = 0; l < kTreeBits + 1; ++l) tc->ticket[l] = 0;
+}
+
+// one thread per node of `level`: split it when it holds more than leaf_cap points
+__global__ void k_tree_split_level(TreeGeom g, const unsigned long long* __restrict__ keys, TreeNode* __restrict__ nodes,
+                                   TreeCounters* __restrict__ tc, int level)
+{
+    const int lb = tc->level_begin[level], le = tc->level_begin[level + 1];
+    for (int ni = lb + blockIdx.x * blockDim.x + threadIdx.x; ni < le; ni += gridDim.x * blockDim.x) {
+        const int count = nodes[ni].end - nodes[ni].begin;
+        if (count > g.leaf_cap) {
+            const int base = atomicAdd(&tc->n_nodes, 8);
+            if (base + 8 <= g.n_nodes_cap) tree_split_node(g, keys, nodes, ni, base);  // else: stays a (large) leaf
         }
-        const int e = base + lane;
-        if (e > pos) {
-            L.key[r] = up_k;
-            L.spos[r] = up_s;
-        } else if (e == pos) {
-            L.key[r] = k;
-            L.spos[r] = sp;
-        }
-        if (e >= m) L.key[r] = kKeyInf;  // the element pushed past the capacity falls off
+    }
+    __threadfence();
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&tc->ticket[level], 1) == static_cast<int>(gridDim.x) - 1);
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        // slots whose allocation did not fit were never written: the buffer is pre-filled with empty leaves
+        const int nn = min(*reinterpret_cast<volatile int*>(&tc->n_nodes), g.n_nodes_cap);
+        for (int l = level + 2; l < kTreeBits + 3; ++l) tc->level_begin[l] = nn;
     }
 }
 
-template <int R>
-__device__ __forceinline__ unsigned long long list_worst(const WarpList<R>& L, int m)
+// ------------------------------------------------------------------------------------------------------------
+// radius search: one thread per query walks the octree with a register-resident sorted top-m list
+// ------------------------------------------------------------------------------------------------------------
+
+template <int CAP, class List>
+__device__ __forceinline__ void search_one(const PairDev& P, int i, List& L, int* stack)
 {
-    // key of entry m-1: kKeyInf until the list is full, the current worst kept candidate afterwards
-    const int e = m - 1;
-    unsigned long long worst = kKeyInf;
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-        if ((e >> 5) == r) worst = __shfl_sync(kFull, L.key[r], e & 31);
-    return worst;
+    const float4 q = P.src[i];
+    L.init(P.m);
+    tree_search(P.tree, P.nodes, P.tgt_sorted, q.x, q.y, q.z, P.r2f, L, stack);
 }
 
-// Offers one candidate per lane.  tau is the strict bound a candidate must beat: the squared radius until the
-// list is full, the current worst afterwards (FLANN's KNNRadiusResultSet rule).
-template <int R>
-__device__ __forceinline__ void offer_chunk(WarpList<R>& L, unsigned long long ckey, int csp, int lane, int m,
-                                            unsigned long long r2key, unsigned long long& worst,
-                                            unsigned long long& tau)
+__device__ __forceinline__ void search_store(const PairDev& P, int i, int e, unsigned long long key)
 {
-    unsigned mask = __ballot_sync(kFull, ckey < tau);
-    while (mask) {
-        const int b = __ffs(mask) - 1;
-        const unsigned long long k = __shfl_sync(kFull, ckey, b);
-        const int sp = __shfl_sync(kFull, csp, b);
-        list_insert<R>(L, k, sp, lane, m);
-        worst = list_worst<R>(L, m);
-        tau = worst < r2key ? worst : r2key;
-        mask &= mask - 1;
-        mask &= __ballot_sync(kFull, ckey < tau);
-    }
+    const int idx = key_index(key);
+    const float4 p = __ldg(P.tgt_raw + idx);
+    const size_t o = static_cast<size_t>(e) * P.n_pad + i;
+    P.nbr_x[o] = p.x;
+    P.nbr_y[o] = p.y;
+    P.nbr_z[o] = p.z;
+    P.nbr_idx[o] = idx;
+    if (P.nbr_d2) P.nbr_d2[o] = key_d2(key);
 }
 
-// Scans the target grid around query q and leaves the (at most m) nearest in-radius targets in L, sorted.
-template <int R>
-__device__ void warp_search(const PairDev& P, float qx, float qy, float qz, int lane, WarpList<R>& L)
+__device__ __forceinline__ void search_count(PairState* st, int cnt)
 {
-    const GridDev& g = P.grid;
-    const int m = P.m;
-    const unsigned long long r2key = static_cast<unsigned long long>(__float_as_uint(P.r2f)) << 32;
-    unsigned long long tau = r2key, worst = kKeyInf;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        L.key[r] = kKeyInf;
-        L.spos[r] = 0;
-    }
-    // conservative cell window of the radius ball (directed rounding keeps it a superset)
-    int lo[3], hi[3], qc[3];
-    lo[0] = cell_coord(__fsub_rd(qx, P.rpad), g.ox, g.inv_h);
-    hi[0] = cell_coord(__fadd_ru(qx, P.rpad), g.ox, g.inv_h);
-    lo[1] = cell_coord(__fsub_rd(qy, P.rpad), g.oy, g.inv_h);
-    hi[1] = cell_coord(__fadd_ru(qy, P.rpad), g.oy, g.inv_h);
-    lo[2] = cell_coord(__fsub_rd(qz, P.rpad), g.oz, g.inv_h);
-    hi[2] = cell_coord(__fadd_ru(qz, P.rpad), g.oz, g.inv_h);
-    qc[0] = cell_coord(qx, g.ox, g.inv_h);
-    qc[1] = cell_coord(qy, g.oy, g.inv_h);
-    qc[2] = cell_coord(qz, g.oz, g.inv_h);
-    const int dims[3] = {g.nx, g.ny, g.nz};
-    int s_min = 0, s_max = 0;
-    bool empty = false;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        lo[a] = max(lo[a], 0);
-        hi[a] = min(hi[a], dims[a] - 1);
-        empty |= lo[a] > hi[a];
-        // keep the shell arithmetic in range for queries far outside the grid
-        qc[a] = clampi(qc[a], lo[a] - (1 << 20), hi[a] + (1 << 20));
-        s_min = max(s_min, max(lo[a] - qc[a], qc[a] - hi[a]));
-        s_max = max(s_max, max(qc[a] - lo[a], hi[a] - qc[a]));
-    }
-    if (empty) return;
-    s_min = max(s_min, 0);
-
-    for (int s = s_min; s <= s_max; ++s) {
-        const int side = 2 * s + 1;
-        const int n_rows = side * side;
-        for (int row0 = 0; row0 < n_rows; row0 += 32) {
-            // lane -> one (dy, dz) row of the shell; up to two x-runs per row
-            const int r = row0 + lane;
-            int begA = 0, lenA = 0, begB = 0, lenB = 0;
-            if (r < n_rows) {
-                const int dz = r / side - s, dy = r % side - s;
-                const int cy = qc[1] + dy, cz = qc[2] + dz;
-                if (cy >= lo[1] && cy <= hi[1] && cz >= lo[2] && cz <= hi[2]) {
-                    const int row_base = (cz * g.ny + cy) * g.nx;
-                    const bool face = (abs(dy) == s) || (abs(dz) == s);
-                    if (face) {
-                        const int x0 = max(lo[0], qc[0] - s), x1 = min(hi[0], qc[0] + s);
-                        if (x0 <= x1) {
-                            begA = __ldg(P.cell_start + row_base + x0);
-                            lenA = __ldg(P.cell_start + row_base + x1 + 1) - begA;
-                        }
-                    } else {
-                        const int xa = qc[0] - s, xb = qc[0] + s;
-                        if (xa >= lo[0] && xa <= hi[0]) {
-                            begA = __ldg(P.cell_start + row_base + xa);
-                            lenA = __ldg(P.cell_start + row_base + xa + 1) - begA;
-                        }
-                        if (xb >= lo[0] && xb <= hi[0]) {
-                            begB = __ldg(P.cell_start + row_base + xb);
-                            lenB = __ldg(P.cell_start + row_base + xb + 1) - begB;
-                        }
-                    }
-                }
-            }
-            // flatten the runs of the 32 rows into one candidate stream
-            const int len = lenA + lenB;
-            int incl = len;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(kFull, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const int total = __shfl_sync(kFull, incl, 31);
-            for (int it = 0; it < total; it += 32) {
-                const int gidx = it + lane;
-                // owner = first lane whose inclusive prefix exceeds gidx
-                int owner = 0;
-#pragma unroll
-                for (int step = 16; step > 0; step >>= 1) {
-                    const int probe = __shfl_sync(kFull, incl, owner + step - 1);
-                    if (probe <= gidx) owner += step;
-                }
-                owner = min(owner, 31);
-                const int o_incl = __shfl_sync(kFull, incl, owner);
-                const int o_len = __shfl_sync(kFull, len, owner);
-                const int o_begA = __shfl_sync(kFull, begA, owner);
-                const int o_lenA = __shfl_sync(kFull, lenA, owner);
-                const int o_begB = __shfl_sync(kFull, begB, owner);
-                unsigned long long ckey = kKeyInf;
-                int csp = 0;
-                if (gidx < total) {
-                    const int within = gidx - (o_incl - o_len);
-                    csp = within < o_lenA ? o_begA + within : o_begB + (within - o_lenA);
-                    const float4 p = __ldg(P.tgt_sorted + csp);
-                    const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
-                    ckey = (static_cast<unsigned long long>(__float_as_uint(d2)) << 32) |
-                           static_cast<unsigned>(__float_as_int(p.w));
-                }
-                offer_chunk<R>(L, ckey, csp, lane, m, r2key, worst, tau);
-            }
-        }
-        // every target not scanned yet lies farther than s*h (minus float slack) along some axis: once the list is
-        // full and its worst entry is inside that covered radius, no later shell can change the result
-        if (worst != kKeyInf) {
-            const double cover = static_cast<double>(s) * g.h_cover - g.cover_slack;
-            const double worst_d2 = __uint_as_float(static_cast<unsigned>(worst >> 32));
-            if (cover > 0.0 && worst_d2 < cover * cover) break;
-        }
-    }
+    // association size: warp sum, one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&st->K), static_cast<unsigned long long>(cnt));
 }
 
-// block = 8 warps, one tile of 32 consecutive queries; results leave through shared memory so that the
-// slot-major planes are written 128 bytes at a time
-template <int R>
-__global__ void __launch_bounds__(kSearchWarps * 32) k_search(const PairDev* __restrict__ pairs)
+// CAP > 0: list of CAP registers (m <= CAP).  CAP == 0: any m, list in local memory.
+template <int CAP>
+__global__ void __launch_bounds__(kSearchThreads) k_search(const PairDev* __restrict__ pairs)
 {
-    extern __shared__ unsigned char smem_raw[];
     const PairDev& P = pairs[blockIdx.y];
     PairState* st = P.state;
     // the increment published by the previous tick has been consumed by k_transform: retire the flag
     if (blockIdx.x == 0 && threadIdx.x == 0) st->apply_dT = 0;
     if (st->phase != PH_SEARCH) return;
-    const int tile0 = blockIdx.x * kTileQ;
-    if (tile0 >= P.n_src) return;
+    if (static_cast<int>(blockIdx.x) * kSearchThreads >= P.n_src) return;
+    const int i = blockIdx.x * kSearchThreads + threadIdx.x;
     const int m = P.m;
-    float* t_x = reinterpret_cast<float*>(smem_raw);
-    float* t_y = t_x + m * kTileQ;
-    float* t_z = t_y + m * kTileQ;
-    int* t_i = reinterpret_cast<int*>(t_z + m * kTileQ);
-    float* t_d = reinterpret_cast<float*>(t_i + m * kTileQ);
-    __shared__ int t_cnt[kTileQ];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    for (int qi = warp; qi < kTileQ; qi += kSearchWarps) {
-        const int i = tile0 + qi;
-        int cnt = 0;
-        if (i < P.n_src) {
-            const float4 q = P.src[i];
-            WarpList<R> L;
-            warp_search<R>(P, q.x, q.y, q.z, lane, L);
+    int stack[kTreeStack];
+    int cnt = 0;
+    if (i < P.n_src) {
+        if constexpr (CAP > 0) {
+            TopList<CAP> L;
+            search_one<CAP>(P, i, L, stack);
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const bool have = L.key[r] != kKeyInf;
-                cnt += __popc(__ballot_sync(kFull, have));
-                const int e = 32 * r + lane;
-                if (have) {
-                    const float4 p = __ldg(P.tgt_sorted + L.spos[r]);
-                    t_x[e * kTileQ + qi] = p.x;
-                    t_y[e * kTileQ + qi] = p.y;
-                    t_z[e * kTileQ + qi] = p.z;
-                    t_i[e * kTileQ + qi] = __float_as_int(p.w);
-                    t_d[e * kTileQ + qi] = __uint_as_float(static_cast<unsigned>(L.key[r] >> 32));
+            for (int s = 0; s < CAP; ++s) {
+                const int e = m - 1 - s;  // ascending rank of slot s
+                if (e >= 0 && L.k[s] != kKeyInf) {
+                    search_store(P, i, e, L.k[s]);
+                    ++cnt;
+                }
+            }
+        } else {
+            unsigned long long buf[128];
+            TopListDyn L;
+            L.k = buf;
+            search_one<0>(P, i, L, stack);
+            for (int s = 0; s < m; ++s) {
+                if (buf[s] != kKeyInf) {
+                    search_store(P, i, m - 1 - s, buf[s]);
+                    ++cnt;
                 }
             }
         }
-        if (lane == 0) t_cnt[qi] = cnt;
+        P.nbr_cnt[i] = cnt;
     }
-    __syncthreads();
-    // coalesced write-out: one warp per slot row
-    const int my_cnt = t_cnt[lane];
-    const int i_out = tile0 + lane;
-    for (int e = warp; e < m; e += kSearchWarps) {
-        if (i_out < P.n_src && e < my_cnt) {
-            const size_t o = static_cast<size_t>(e) * P.n_pad + i_out;
-            P.nbr_x[o] = t_x[e * kTileQ + lane];
-            P.nbr_y[o] = t_y[e * kTileQ + lane];
-            P.nbr_z[o] = t_z[e * kTileQ + lane];
-            P.nbr_idx[o] = t_i[e * kTileQ + lane];
-            if (P.nbr_d2) P.nbr_d2[o] = t_d[e * kTileQ + lane];
-        }
-    }
-    if (warp == 0) {
-        if (i_out < P.n_src) P.nbr_cnt[i_out] = my_cnt;
-        int total = (i_out < P.n_src) ? my_cnt : 0;
-        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
-        if (lane == 0 && total) atomicAdd(reinterpret_cast<unsigned long long*>(&st->K), static_cast<unsigned long long>(total));
-    }
+    search_count(st, cnt);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,318 @@
+// ppcr_tree.h -- the neighbour-search structure: a linear octree over the Morton-sorted target cloud, and the
+// per-query traversal with a register-resident top-m list.
+//
+// Replaces pcl::KdTreeFLANN::setInputCloud + radiusSearch (src/prob_point_cloud_registration.cc:66-67,72-81).
+// Semantics reproduced exactly: d2 = ((dx*dx) + dy*dy) + dz*dz in float32 without contraction,
+// membership d2 < float(radius*radius) strictly, at most m results = the m smallest under (d2, index), returned
+// ascending.  The result is a pure function of the point sets, so the tree shape / traversal order cannot change it
+// as long as pruning is conservative.
+//
+// Why a tree and not a uniform grid: LiDAR-like clouds span three orders of magnitude in density.  A cell edge that
+// keeps dense regions cheap makes sparse queries walk tens of thousands of empty cells, and one that suits sparse
+// regions makes dense queries test thousands of candidates.  The octree adapts: every query opens O(depth) nodes
+// and scans a handful of leaves of at most `leaf_cap` points.
+//
+// Layout: the target is sorted by the 3*kTreeBits-bit Morton key of its quantised coordinates, so every octree
+// node is one contiguous range [begin,end) of tgt_sorted; nodes are 32-byte records, the 8 children of a node are
+// consecutive.  Plain C++ qualified PPCR_HD: the search kernel and the CPU tests (tests/emu) share this source.
+#ifndef PPCR_TREE_H
+#define PPCR_TREE_H
+
+#include <stdint.h>
+
+#include "ppcr_lm.h"  // PPCR_HD
+
+#if !defined(__CUDACC__)
+struct float4 {  // host-only builds (tests/emu): the 16-byte pcl::PointXYZ record
+    float x, y, z, w;
+};
+#endif
+
+namespace ppcr {
+
+constexpr int kTreeBits = 16;            // quantisation bits per axis -> 48-bit Morton keys
+constexpr int kTreeStack = 7 * kTreeBits + 9;
+constexpr unsigned long long kKeyInf = 0xffffffffffffffffull;
+
+struct TreeGeom {
+    float ox, oy, oz;   // min corner of the root cube
+    float inv_hf;       // 1 / finest cell edge
+    float hf;           // finest cell edge
+    float slack;        // absolute bound on the float fuzz of binning + node centres; inflates every box
+    int n_nodes_cap;
+    int leaf_cap;       // a node holding more points than this is split (unless it is at the finest level)
+};
+
+struct TreeNode {       // 32 bytes
+    float cx, cy, cz;   // cube centre
+    float half;         // half edge (not inflated)
+    int begin, end;     // range in the Morton-sorted target
+    int child;          // first of 8 consecutive children, -1 = leaf
+    int mask;           // bits 0..7: non-empty children; bits 8..15: level
+};
+
+// ---- bit-exact float helpers ---------------------------------------------------------------------------------
+
+PPCR_HD float f_sub(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+PPCR_HD float f_mul(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+PPCR_HD float f_add(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+
+// FLANN L2_Simple<float>: ((dx*dx) + dy*dy) + dz*dz in float32 with NO fused multiply-add
+PPCR_HD float dist2_exact(float qx, float qy, float qz, float px, float py, float pz)
+{
+    const float dx = f_sub(qx, px), dy = f_sub(qy, py), dz = f_sub(qz, pz);
+    float acc = f_mul(dx, dx);
+    acc = f_add(acc, f_mul(dy, dy));
+    acc = f_add(acc, f_mul(dz, dz));
+    return acc;
+}
+
+PPCR_HD uint32_t float_bits(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c;
+    c.f = f;
+    return c.u;
+#endif
+}
+PPCR_HD float bits_float(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    union { float f; uint32_t u; } c;
+    c.u = u;
+    return c.f;
+#endif
+}
+
+// (d2, index) packed so that integer order = lexicographic order; +1 keeps every real key above the 0 that pins
+// the unused slots of a list
+PPCR_HD unsigned long long make_key(float d2, int idx)
+{
+    return ((static_cast<unsigned long long>(float_bits(d2)) << 32) | static_cast<uint32_t>(idx)) + 1ull;
+}
+PPCR_HD float key_d2(unsigned long long k) { return bits_float(static_cast<uint32_t>((k - 1ull) >> 32)); }
+PPCR_HD int key_index(unsigned long long k) { return static_cast<int>(static_cast<uint32_t>(k - 1ull)); }
+
+// ---- Morton keys ---------------------------------------------------------------------------------------------
+
+PPCR_HD unsigned long long spread3(uint32_t v)  // 16 bits -> every third bit
+{
+    unsigned long long x = v & 0xffffull;
+    x = (x | (x << 16)) & 0x0000ff0000ffull;
+    x = (x | (x << 8)) & 0x00f00f00f00full;
+    x = (x | (x << 4)) & 0x0c30c30c30c3ull;
+    x = (x | (x << 2)) & 0x249249249249ull;
+    return x;
+}
+
+PPCR_HD uint32_t compact3(unsigned long long x)
+{
+    x &= 0x249249249249ull;
+    x = (x | (x >> 2)) & 0x0c30c30c30c3ull;
+    x = (x | (x >> 4)) & 0x00f00f00f00full;
+    x = (x | (x >> 8)) & 0x0000ff0000ffull;
+    x = (x | (x >> 16)) & 0xffffull;
+    return static_cast<uint32_t>(x);
+}
+
+PPCR_HD int tree_coord(float v, float origin, float inv_hf)
+{
+    // monotone in v; clamped so that queries and fuzz at the faces stay inside the root cube
+    float t = f_mul(f_sub(v, origin), inv_hf);
+    if (!(t > 0.f)) t = 0.f;
+    const float top = static_cast<float>((1 << kTreeBits) - 1);
+    if (t > top) t = top;
+    return static_cast<int>(t);
+}
+
+PPCR_HD unsigned long long tree_key(const TreeGeom& g, float x, float y, float z)
+{
+    const uint32_t ix = static_cast<uint32_t>(tree_coord(x, g.ox, g.inv_hf));
+    const uint32_t iy = static_cast<uint32_t>(tree_coord(y, g.oy, g.inv_hf));
+    const uint32_t iz = static_cast<uint32_t>(tree_coord(z, g.oz, g.inv_hf));
+    return spread3(ix) | (spread3(iy) << 1) | (spread3(iz) << 2);  // bit 0 = x, bit 1 = y, bit 2 = z of each digit
+}
+
+// node geometry from its level and the Morton prefix of any key inside it
+PPCR_HD void tree_node_box(const TreeGeom& g, int level, unsigned long long key_in_node, TreeNode* n)
+{
+    const int shift = 3 * (kTreeBits - level);
+    const unsigned long long prefix = shift >= 48 ? 0ull : (key_in_node >> shift);
+    const uint32_t ix = compact3(prefix), iy = compact3(prefix >> 1), iz = compact3(prefix >> 2);
+    const float half = g.hf * static_cast<float>(1u << (kTreeBits - level)) * 0.5f;  // exact power-of-two scaling
+    n->cx = g.ox + static_cast<float>(2u * ix + 1u) * half;
+    n->cy = g.oy + static_cast<float>(2u * iy + 1u) * half;
+    n->cz = g.oz + static_cast<float>(2u * iz + 1u) * half;
+    n->half = half;
+}
+
+// first position in keys[lo,hi) whose octal digit at `shift` is >= digit (keys of one node: the digit is monotone)
+PPCR_HD int tree_digit_lower_bound(const unsigned long long* keys, int lo, int hi, int shift, unsigned digit)
+{
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (static_cast<unsigned>((keys[mid] >> shift) & 7ull) < digit) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// Splits node `ni` (level < kTreeBits, more than leaf_cap points) into 8 children written at nodes[base..base+8).
+PPCR_HD void tree_split_node(const TreeGeom& g, const unsigned long long* keys, TreeNode* nodes, int ni, int base)
+{
+    TreeNode parent = nodes[ni];
+    const int level = (parent.mask >> 8) & 0xff;
+    const int shift = 3 * (kTreeBits - level - 1);
+    int bound[9];
+    bound[0] = parent.begin;
+    bound[8] = parent.end;
+    for (unsigned c = 1; c < 8; ++c) bound[c] = tree_digit_lower_bound(keys, bound[c - 1], parent.end, shift, c);
+    int mask = 0;
+    const unsigned long long prefix = keys[parent.begin] >> (shift + 3);
+    for (int c = 0; c < 8; ++c) {
+        TreeNode ch;
+        ch.begin = bound[c];
+        ch.end = bound[c + 1];
+        ch.child = -1;
+        ch.mask = (level + 1) << 8;
+        tree_node_box(g, level + 1, ((prefix << 3) | static_cast<unsigned long long>(c)) << shift, &ch);
+        if (ch.end > ch.begin) mask |= 1 << c;
+        nodes[base + c] = ch;
+    }
+    parent.child = base;
+    parent.mask = (level << 8) | mask;
+    nodes[ni] = parent;
+}
+
+// ---- top-m list ----------------------------------------------------------------------------------------------
+//
+// Kept DESCENDING: k[0] is the current worst of the m best, k[m-1] the best; slots >= m are pinned to 0 (below
+// every real key) so the fully unrolled insertion needs no dynamic register indexing.  Empty slots hold kKeyInf.
+
+template <int CAP>
+struct TopList {
+    unsigned long long k[CAP];
+
+    PPCR_HD void init(int m)
+    {
+#pragma unroll
+        for (int i = 0; i < CAP; ++i) k[i] = i < m ? kKeyInf : 0ull;
+    }
+    PPCR_HD unsigned long long worst() const { return k[0]; }
+    // pre: x < k[0]
+    PPCR_HD void insert(unsigned long long x)
+    {
+#pragma unroll
+        for (int i = 0; i < CAP - 1; ++i) k[i] = (k[i + 1] > x) ? k[i + 1] : (k[i] > x ? x : k[i]);
+        k[CAP - 1] = k[CAP - 1] > x ? x : k[CAP - 1];
+    }
+};
+
+// any m: the same list in addressable (local) memory, loops not unrolled
+struct TopListDyn {
+    unsigned long long* k;
+    int m;
+    PPCR_HD void init(int m_)
+    {
+        m = m_;
+        for (int i = 0; i < m; ++i) k[i] = kKeyInf;
+    }
+    PPCR_HD unsigned long long worst() const { return k[0]; }
+    PPCR_HD void insert(unsigned long long x)
+    {
+        int i = 0;
+        for (; i < m - 1 && k[i + 1] > x; ++i) k[i] = k[i + 1];
+        k[i] = x;
+    }
+};
+
+// ---- traversal -----------------------------------------------------------------------------------------------
+
+PPCR_HD float box_lower_bound(float qx, float qy, float qz, float cx, float cy, float cz, float hi)
+{
+    // squared distance from q to the cube |p - c| <= hi per axis, shaved so that float rounding can only make it
+    // smaller than the exact float32 distance to any point binned into the cube
+    float dx = fabsf(qx - cx) - hi, dy = fabsf(qy - cy) - hi, dz = fabsf(qz - cz) - hi;
+    dx = dx > 0.f ? dx : 0.f;
+    dy = dy > 0.f ? dy : 0.f;
+    dz = dz > 0.f ? dz : 0.f;
+    return (dx * dx + dy * dy + dz * dz) * 0.99999f;
+}
+
+// Leaves the (at most m) nearest targets with d2 < r2f in L.  pts = Morton-sorted target, .w = original index.
+// `stack` must hold kTreeStack ints.
+template <class List>
+PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, const float4* __restrict__ pts,
+                         float qx, float qy, float qz, float r2f, List& L, int* stack)
+{
+    const unsigned long long r2key = static_cast<unsigned long long>(float_bits(r2f)) << 32;  // keys of d2 >= r2f are > this
+    float bound_d2 = r2f;  // no unseen point farther than this can enter the list
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        const int ni = stack[--sp];
+        const TreeNode n = nodes[ni];
+        if (n.end <= n.begin) continue;
+        if (box_lower_bound(qx, qy, qz, n.cx, n.cy, n.cz, n.half + g.slack) > bound_d2) continue;
+        if (n.child < 0) {
+            for (int j = n.begin; j < n.end; ++j) {
+                const float4 p = pts[j];
+                const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+                if (d2 <= bound_d2) {
+                    const unsigned long long key = make_key(d2, static_cast<int>(float_bits(p.w)));
+                    if (key <= r2key && key < L.worst()) {  // key <= r2key  <=>  d2 < r2f (keys carry +1)
+                        L.insert(key);
+                        const unsigned long long w = L.worst();
+                        if (w != kKeyInf) {
+                            const float wd = key_d2(w);
+                            bound_d2 = wd < r2f ? wd : r2f;
+                        }
+                    }
+                }
+            }
+            continue;
+        }
+        // children, pushed far-to-near so that the octant holding q is opened first
+        const int oct = (qx >= n.cx ? 1 : 0) | (qy >= n.cy ? 2 : 0) | (qz >= n.cz ? 4 : 0);
+        const float ch = n.half * 0.5f;
+        const float hi = ch + g.slack;
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+            const int c = oct ^ k;
+            if (!((n.mask >> c) & 1)) continue;
+            const float ccx = n.cx + ((c & 1) ? ch : -ch);
+            const float ccy = n.cy + ((c & 2) ? ch : -ch);
+            const float ccz = n.cz + ((c & 4) ? ch : -ch);
+            if (box_lower_bound(qx, qy, qz, ccx, ccy, ccz, hi) > bound_d2) continue;
+            stack[sp++] = n.child + c;
+        }
+    }
+}
+
+}  // namespace ppcr
+#endif

@@ -36,7 +36,7 @@ def emu():
     here = os.path.join(ROOT, "tests", "emu")
     so = os.path.join(here, "libppcr_emu.so")
     src = os.path.join(here, "emu_host_logic.cpp")
-    hdrs = [os.path.join(ROOT, "probabilistic_point_clouds_registration_b200", "csrc", h) for h in ("ppcr_lm.h", "ppcr_eval.h")]
+    hdrs = [os.path.join(ROOT, "probabilistic_point_clouds_registration_b200", "csrc", h) for h in ("ppcr_lm.h", "ppcr_eval.h", "ppcr_tree.h")]
     if (not os.path.exists(so)) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in [src, *hdrs]):
         gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.check_call([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src])

@@ -13,6 +13,7 @@
 
 #include "../../probabilistic_point_clouds_registration_b200/csrc/ppcr_eval.h"
 #include "../../probabilistic_point_clouds_registration_b200/csrc/ppcr_lm.h"
+#include "../../probabilistic_point_clouds_registration_b200/csrc/ppcr_tree.h"
 
 using namespace ppcr;
 
@@ -160,6 +161,118 @@ void emu_normal_eq(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, 
     for (int r = 0; r < kNP; ++r) normal_eq36[o++] = g[r];
     normal_eq36[o] = cost;
     if (moments24) std::memcpy(moments24, S, sizeof(S));
+}
+
+
+// The product's octree (csrc/ppcr_tree.h): serial build with the same split routine the build kernel calls, then the
+// same traversal the search kernel runs, one query at a time.  Rows come back sorted ascending by (d2, index).
+// list_kind: 0 = register list sized like the kernel's dispatch, 1 = the addressable list used for m > 32.
+int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, int64_t n_tgt, double radius,
+                        int max_nn, int leaf_cap, int list_kind, int* out_idx, float* out_d2, int* out_cnt,
+                        int* out_n_nodes)
+{
+    const int m = static_cast<int>(std::min<int64_t>(max_nn, std::max<int64_t>(n_tgt, 1)));
+    const float r2f = static_cast<float>(radius * radius);
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t i = 0; i < n_tgt; ++i)
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::min(lo[a], tgt_xyzw[4 * i + a]);
+            hi[a] = std::max(hi[a], tgt_xyzw[4 * i + a]);
+        }
+    if (n_tgt == 0) { lo[0] = lo[1] = lo[2] = 0.f; hi[0] = hi[1] = hi[2] = 1.f; }
+    // make_tree_geom of ppcr_capi.cu
+    TreeGeom g{};
+    double span = 0.0, mag = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        span = std::max(span, static_cast<double>(hi[k]) - lo[k]);
+        mag = std::max({mag, std::fabs(static_cast<double>(lo[k])), std::fabs(static_cast<double>(hi[k]))});
+    }
+    span = std::max(span, 1e-6 * std::max(mag, 1e-30)) * (1.0 + 1e-5);
+    if (!(span > 0.0)) span = 1.0;
+    g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2];
+    g.inv_hf = static_cast<float>(static_cast<double>(1 << kTreeBits) / span);
+    g.hf = static_cast<float>(1.0 / static_cast<double>(g.inv_hf));
+    g.slack = static_cast<float>(1e-6 * span + 1e-6 * (mag + span) + 1e-30);
+    g.leaf_cap = leaf_cap;
+    g.n_nodes_cap = static_cast<int>(64ll + 8ll * (2ll * n_tgt / std::max(leaf_cap, 1) + 8));
+    std::vector<std::pair<unsigned long long, int>> kv(static_cast<size_t>(n_tgt));
+    for (int64_t i = 0; i < n_tgt; ++i)
+        kv[i] = {tree_key(g, tgt_xyzw[4 * i], tgt_xyzw[4 * i + 1], tgt_xyzw[4 * i + 2]), static_cast<int>(i)};
+    std::stable_sort(kv.begin(), kv.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    std::vector<unsigned long long> keys(static_cast<size_t>(n_tgt));
+    std::vector<float4> pts(static_cast<size_t>(std::max<int64_t>(n_tgt, 1)));
+    for (int64_t j = 0; j < n_tgt; ++j) {
+        keys[j] = kv[j].first;
+        const float* p = tgt_xyzw + 4 * static_cast<int64_t>(kv[j].second);
+        pts[j].x = p[0]; pts[j].y = p[1]; pts[j].z = p[2];
+        pts[j].w = bits_float(static_cast<uint32_t>(kv[j].second));
+    }
+    std::vector<TreeNode> nodes(static_cast<size_t>(g.n_nodes_cap) + 8);
+    std::memset(nodes.data(), 0xff, nodes.size() * sizeof(TreeNode));
+    TreeNode root;
+    root.begin = 0; root.end = static_cast<int>(n_tgt); root.child = -1; root.mask = 0;
+    tree_node_box(g, 0, 0ull, &root);
+    nodes[0] = root;
+    int n_nodes = 1, lb = 0, le = 1;
+    for (int level = 0; level < kTreeBits; ++level) {
+        for (int ni = lb; ni < le; ++ni) {
+            if (nodes[ni].end - nodes[ni].begin > g.leaf_cap) {
+                const int base = n_nodes;
+                n_nodes += 8;
+                if (base + 8 <= g.n_nodes_cap) tree_split_node(g, keys.data(), nodes.data(), ni, base);
+            }
+        }
+        lb = le;
+        le = std::min(n_nodes, g.n_nodes_cap);
+    }
+    if (out_n_nodes) *out_n_nodes = n_nodes;
+    int64_t total = 0;
+    int stack[kTreeStack];
+    std::vector<unsigned long long> buf(static_cast<size_t>(std::max(m, 1)));
+    for (int64_t i = 0; i < n_src; ++i) {
+        const float* q = src_xyzw + 4 * i;
+        std::vector<unsigned long long> found;
+        auto take = [&](const unsigned long long* k, int cap) {
+            for (int s2 = 0; s2 < cap; ++s2) {
+                const int e = m - 1 - s2;
+                if (e >= 0 && k[s2] != kKeyInf) found.push_back(k[s2]);
+            }
+        };
+        const int cap = m <= 4 ? 4 : m <= 8 ? 8 : m <= 12 ? 12 : m <= 16 ? 16 : m <= 20 ? 20 : m <= 24 ? 24 : m <= 32 ? 32 : 0;
+        if (list_kind == 0 && cap > 0) {
+#define EMU_RUN(C)                                                                                  \
+    {                                                                                               \
+        TopList<C> L;                                                                               \
+        L.init(m);                                                                                  \
+        tree_search(g, nodes.data(), pts.data(), q[0], q[1], q[2], r2f, L, stack);                  \
+        take(L.k, C);                                                                               \
+    }
+            switch (cap) {
+                case 4: EMU_RUN(4) break;
+                case 8: EMU_RUN(8) break;
+                case 12: EMU_RUN(12) break;
+                case 16: EMU_RUN(16) break;
+                case 20: EMU_RUN(20) break;
+                case 24: EMU_RUN(24) break;
+                default: EMU_RUN(32) break;
+            }
+#undef EMU_RUN
+        } else {
+            TopListDyn L;
+            L.k = buf.data();
+            L.init(m);
+            tree_search(g, nodes.data(), pts.data(), q[0], q[1], q[2], r2f, L, stack);
+            take(buf.data(), m);
+        }
+        std::sort(found.begin(), found.end());
+        out_cnt[i] = static_cast<int>(found.size());
+        for (size_t k = 0; k < found.size(); ++k) {
+            out_idx[i * max_nn + static_cast<int64_t>(k)] = key_index(found[k]);
+            out_d2[i * max_nn + static_cast<int64_t>(k)] = key_d2(found[k]);
+        }
+        total += static_cast<int64_t>(found.size());
+    }
+    return total;
 }
 
 }  // extern "C"

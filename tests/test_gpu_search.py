@@ -9,8 +9,8 @@ from probabilistic_point_clouds_registration_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def _compare(capi, oracle, src, tgt, radius, m, cell_size=0.0):
-    gi, gd, gc = capi.radius_search(src, tgt, radius, m, cell_size)
+def _compare(capi, oracle, src, tgt, radius, m, leaf_capacity=0):
+    gi, gd, gc = capi.radius_search(src, tgt, radius, m, leaf_capacity)
     oi, od, oc, _ = oracle.radius_search(src, tgt, radius, m, use_grid=len(tgt) > 4000)
     cap = oi.shape[1]
     assert np.array_equal(gc, oc), f"counts differ at {np.nonzero(gc != oc)[0][:10]}"
@@ -39,10 +39,10 @@ def test_lidar_like(capi, oracle, outliers):
     _compare(capi, oracle, src, tgt, 0.5, 10)
 
 
-@pytest.mark.parametrize("cell", [0.11, 0.25, 0.5, 1.0])
-def test_result_independent_of_cell_size(capi, oracle, cell):
+@pytest.mark.parametrize("leaf", [1, 3, 8, 64, 100000])
+def test_result_independent_of_tree_shape(capi, oracle, leaf):
     src, tgt, _ = synth.lidar_pair(9, 16, 500)
-    _compare(capi, oracle, src, tgt, 1.0, 12, cell_size=cell)
+    _compare(capi, oracle, src, tgt, 1.0, 12, leaf_capacity=leaf)
 
 
 @pytest.mark.parametrize("m", [3, 5, 20])
