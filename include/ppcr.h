@@ -59,7 +59,8 @@ typedef struct ppcr_options {
     int32_t ticks_per_sync;    /* host-stepped driver: ticks enqueued between flag read-backs (default 4) */
     double function_tolerance; /* inner LM tolerance; 0 = the reference's 10e-6 (src/..registration.cc:97) */
     int32_t leaf_capacity;     /* octree nodes holding more target points than this are split; 0 = default (32) */
-    int32_t fast_weights;      /* 0: fp64 log1p/exp for the weights (default); 1: fp32 transcendentals */
+    int32_t exact_weights;     /* 0 (default): float32 row arithmetic for the weights (|dw/w| ~ 1e-7, the bar is 1e-5),
+                                  float64 sums across rows; 1: float64 log1p/exp per correspondence */
     void* stream;              /* cudaStream_t to run on; NULL = the handle creates its own */
     int32_t record_stage_times;/* 1: bracket kernels with CUDA events (host-stepped driver only) */
     int32_t reserved[7];
@@ -90,7 +91,7 @@ void ppcr_default_params(ppcr_params* p);   /* struct defaults, params.hpp:6-17 
 void ppcr_default_options(ppcr_options* o);
 
 /* Replaces the ProbPointCloudRegistration constructor (src/prob_point_cloud_registration.cc:15-49): copies the
- * source, voxel-filters source and target when the leaf sizes are > 0, builds the target grid.
+ * source, voxel-filters source and target when the leaf sizes are > 0, builds the target octree.
  * max_neighbours must be in [1, 128] (the reference also allows 0 / negative = unlimited: PPCR_ERR_UNSUPPORTED). */
 ppcr_status ppcr_create(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, int64_t n_tgt,
                         const ppcr_params* params, ppcr_handle** out);
@@ -122,8 +123,9 @@ ppcr_status ppcr_association(ppcr_handle* h, int32_t* idx, int32_t* count, int64
 ppcr_status ppcr_get_stage_times(ppcr_handle* h, ppcr_stage_times* out);
 
 /* Re-runs one kernel of the handle's current state `reps` times between two CUDA events on the handle's stream
- * and returns the average milliseconds and the algorithmic bytes of one launch.  which: 0 search, 1 eval
- * (weights + normal equations), 2 transform, 3 grid build. */
+ * and returns the average milliseconds and the algorithmic bytes of one launch.  which: 0 search from scratch
+ * (pruning bound = the radius), 1 weights + normal equations + controller, 2 cloud move, 3 target tree build,
+ * 4 search fused with an (identity) cloud move and warm-started from the previous search's m-th distances. */
 ppcr_status ppcr_time_kernel(ppcr_handle* h, int32_t which, int32_t reps, int32_t flush_l2, float* avg_ms,
                              double* algorithmic_bytes);
 
@@ -157,8 +159,8 @@ ppcr_status ppcr_weights_normal_eq(const float* src_xyzw, int64_t n_src, const f
  * out_pose = (w,x,y,z,tx,ty,tz) as Ceres leaves it; out_T = row-major 4x4. */
 ppcr_status ppcr_iteration_solve(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, int64_t n_tgt,
                                  const int32_t* idx, const int32_t* count, int32_t max_nn,
-                                 const ppcr_params* params, double function_tolerance, double* out_pose,
-                                 double* out_T, ppcr_iter_stats* stats);
+                                 const ppcr_params* params, const ppcr_options* options /* may be NULL */,
+                                 double function_tolerance, double* out_pose, double* out_T, ppcr_iter_stats* stats);
 
 /* pcl::transformPointCloud(cloud, cloud, Affine3d) at :110-112: double math, float store, in place. */
 ppcr_status ppcr_transform(float* xyzw, int64_t n, const double* T4x4_rowmajor);

@@ -58,7 +58,7 @@ class Options(C.Structure):
         ("ticks_per_sync", C.c_int32),
         ("function_tolerance", C.c_double),
         ("leaf_capacity", C.c_int32),
-        ("fast_weights", C.c_int32),
+        ("exact_weights", C.c_int32),
         ("stream", C.c_void_p),
         ("record_stage_times", C.c_int32),
         ("reserved", C.c_int32 * 7),
@@ -122,7 +122,7 @@ def lib():
         L.ppcr_voxel_filter.argtypes = [vp, i64, f64, vp, C.POINTER(i64)]
         L.ppcr_radius_search.argtypes = [vp, i64, vp, i64, f64, i32, i32, vp, vp, vp]
         L.ppcr_weights_normal_eq.argtypes = [vp, i64, vp, i64, vp, vp, i32, f64, i32, vp, vp, i32, vp, vp]
-        L.ppcr_iteration_solve.argtypes = [vp, i64, vp, i64, vp, vp, i32, C.POINTER(Params), f64, vp, vp, vp]
+        L.ppcr_iteration_solve.argtypes = [vp, i64, vp, i64, vp, vp, i32, C.POINTER(Params), C.POINTER(Options), f64, vp, vp, vp]
         L.ppcr_transform.argtypes = [vp, i64, vp]
         L.ppcr_align_batch.argtypes = [C.POINTER(PairDesc), i32, C.POINTER(Params), C.POINTER(Options), i32, vp, vp, vp]
         L.ppcr_shard_export.argtypes = [vp, i32, i32, vp]
@@ -166,7 +166,7 @@ def make_params(max_neighbours=20, dof=5.0, radius=1.0, n_iter=1000, cost_drop_t
 
 
 def make_options(device=0, input_on_device=False, driver=0, ticks_per_sync=0, function_tolerance=0.0, leaf_capacity=0,
-                 fast_weights=False, stream=None, record_stage_times=False) -> Options:
+                 exact_weights=False, stream=None, record_stage_times=False) -> Options:
     o = Options()
     lib().ppcr_default_options(C.byref(o))
     o.device = int(device)
@@ -175,7 +175,7 @@ def make_options(device=0, input_on_device=False, driver=0, ticks_per_sync=0, fu
     o.ticks_per_sync = int(ticks_per_sync)
     o.function_tolerance = float(function_tolerance)
     o.leaf_capacity = int(leaf_capacity)
-    o.fast_weights = int(bool(fast_weights))
+    o.exact_weights = int(bool(exact_weights))
     o.stream = C.c_void_p(stream) if stream else None
     o.record_stage_times = int(bool(record_stage_times))
     return o
@@ -319,7 +319,7 @@ def weights_normal_eq(src, tgt, idx, count, dof, pose_w, pose_e, fast_weights=Fa
     return w, ne
 
 
-def iteration_solve(src, tgt, idx, count, params: Params, function_tolerance=1e-5):
+def iteration_solve(src, tgt, idx, count, params: Params, function_tolerance=1e-5, options: Options | None = None):
     src, tgt = _cloud(src), _cloud(tgt)
     idx = np.ascontiguousarray(idx, dtype=np.int32)
     if idx.ndim == 1:
@@ -329,7 +329,8 @@ def iteration_solve(src, tgt, idx, count, params: Params, function_tolerance=1e-
     T = np.zeros(16)
     st = IterStats()
     _check(lib().ppcr_iteration_solve(src.ctypes.data, len(src), tgt.ctypes.data, len(tgt), idx.ctypes.data,
-                                      count.ctypes.data, idx.shape[1], C.byref(params), float(function_tolerance),
+                                      count.ctypes.data, idx.shape[1], C.byref(params),
+                                      C.byref(options) if options is not None else None, float(function_tolerance),
                                       pose.ctypes.data, T.ctypes.data, C.byref(st)))
     return pose, T.reshape(4, 4), dict(initial_cost=st.initial_cost, final_cost=st.final_cost,
                                        lm_iterations=st.lm_iterations, num_successful_steps=st.num_successful_steps,

@@ -6,6 +6,7 @@
 #include "../../include/ppcr.h"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cuda_profiler_api.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -68,23 +69,36 @@ struct StatusError {
 // device buffers (grow-only, so batch slots can be reused without re-allocating)
 // ------------------------------------------------------------------------------------------------------------
 
+// Stream-ordered allocations from the device's default memory pool (release threshold raised to "never"), so that
+// creating and destroying handles in a loop -- one per scan pair -- re-uses the same blocks without a device-wide
+// synchronisation or a trip to the driver's allocator.
+static thread_local cudaStream_t g_alloc_stream = nullptr;
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;
+    cudaStream_t owner = nullptr;
+    bool plain = false;  // cudaMalloc instead of the pool (memory exported over CUDA IPC)
     void reserve(size_t n)
     {
         if (n <= cap) return;
-        if (p) CK(cudaFree(p));
-        p = nullptr;
-        cap = 0;
+        release();
         size_t want = n + n / 8 + 64;
-        CK(cudaMalloc(&p, want * sizeof(T)));
+        if (plain) {
+            CK(cudaMalloc(&p, want * sizeof(T)));
+        } else {
+            owner = g_alloc_stream;
+            CK(cudaMallocAsync(&p, want * sizeof(T), owner));
+        }
         cap = want;
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) {
+            if (plain) cudaFree(p);
+            else cudaFreeAsync(p, owner);
+        }
         p = nullptr;
         cap = 0;
     }
@@ -113,7 +127,7 @@ struct Pair {
     DevBuf<unsigned long long> sort_keys[2];
     DevBuf<unsigned> sort_vals[2];
     DevBuf<unsigned char> sort_tmp;
-    DevBuf<float> nbr_x, nbr_y, nbr_z, nbr_d2;
+    DevBuf<float> nbr_x, nbr_y, nbr_z, nbr_d2, nbr_kth;
     DevBuf<double> partials, history, mailbox;
     DevBuf<PairState> state;
     DevBuf<Config> cfg;
@@ -129,7 +143,7 @@ struct Pair {
         src.release(); tgt_raw.release(); tgt_sorted.release(); tmp_cloud.release();
         nodes.release(); tree_counters.release(); sort_keys[0].release(); sort_keys[1].release();
         sort_vals[0].release(); sort_vals[1].release(); sort_tmp.release(); nbr_idx.release(); nbr_cnt.release();
-        scan_sums.release(); nbr_x.release(); nbr_y.release(); nbr_z.release(); nbr_d2.release();
+        scan_sums.release(); nbr_x.release(); nbr_y.release(); nbr_z.release(); nbr_d2.release(); nbr_kth.release();
         partials.release(); history.release(); mailbox.release(); state.release(); cfg.release(); stats.release();
         scratch_u.release(); scratch_ull.release();
     }
@@ -148,8 +162,9 @@ struct Engine {
     ppcr_options opts{};
     std::vector<Pair> pairs;
     DevBuf<PairDev> d_pairs;
-    DevBuf<int> d_active;
+    DevBuf<LoopCtl> d_loop;
     int* h_active = nullptr;  // pinned
+    int eval_blocks_per_sm = 2, search_blocks_per_sm = 8;
     int list_cap = 0;  // register capacity of the search kernel's top-m list; 0 = local-memory list (m > 32)
     // launch geometry (capacity based, so a captured graph stays valid while the slots are refilled)
     int max_tiles = 1, max_eval_blocks = 1, max_tr_blocks = 1;
@@ -184,10 +199,12 @@ struct Engine {
             if (peer_ptrs[r] && static_cast<int>(r) != rank) cudaIpcCloseMemHandle(peer_ptrs[r]);
         for (auto& p : pairs) p.release();
         d_pairs.release();
-        d_active.release();
+        d_loop.release();
         flush.release();
         if (h_active) cudaFreeHost(h_active);
+        if (stream) cudaStreamSynchronize(stream);  // the frees above are stream-ordered
         if (own_stream && stream) cudaStreamDestroy(stream);
+        if (g_alloc_stream == stream) g_alloc_stream = nullptr;
     }
 };
 
@@ -214,6 +231,14 @@ static void select_device(int device)
     if (prop.major != 10)
         throw StatusError{PPCR_ERR_NO_DEVICE, std::string("libppcr_cuda is built for sm_100a only; device is ") + prop.name};
     g_sm_count = prop.multiProcessorCount;
+    static bool pool_ready[64] = {};
+    if (device < 64 && !pool_ready[device]) {
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pool_ready[device] = true;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -475,12 +500,15 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     const size_t plane = static_cast<size_t>(D.m) * D.n_pad;
     P.nbr_x.reserve(plane); P.nbr_y.reserve(plane); P.nbr_z.reserve(plane); P.nbr_idx.reserve(plane);
     P.nbr_cnt.reserve(D.n_pad);
+    P.nbr_kth.reserve(D.n_pad);
+    D.nbr_kth = P.nbr_kth.p;
+    CK(cudaMemsetAsync(P.nbr_kth.p, 0x7f, static_cast<size_t>(D.n_pad) * sizeof(float), st));  // "nothing known yet"
     if (P.want_d2) P.nbr_d2.reserve(plane);
     D.nbr_x = P.nbr_x.p; D.nbr_y = P.nbr_y.p; D.nbr_z = P.nbr_z.p; D.nbr_idx = P.nbr_idx.p;
     D.nbr_d2 = P.want_d2 ? P.nbr_d2.p : nullptr;
     D.nbr_cnt = P.nbr_cnt.p;
     CK(cudaMemsetAsync(P.nbr_cnt.p, 0, static_cast<size_t>(D.n_pad) * sizeof(int), st));
-    D.n_eval_blocks = std::max(1, std::min(ceil_div(std::max(D.n_src, 1), kEvalThreads), 4 * std::max(g_sm_count, 1)));
+    D.n_eval_blocks = std::max(1, std::min(ceil_div(std::max(D.n_src, 1), kEvalThreads), E.eval_blocks_per_sm * std::max(g_sm_count, 1)));
     P.partials.reserve(static_cast<size_t>(D.n_eval_blocks) * kNSum);
     D.partials = P.partials.p;
     CK(cudaMemsetAsync(P.partials.p, 0, static_cast<size_t>(D.n_eval_blocks) * kNSum * sizeof(double), st));
@@ -503,7 +531,7 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     c.n_iter = prm.n_iter;
     c.max_lm_iterations = INT_MAX;
     c.is_normal = !(prm.dof < DBL_MAX);
-    c.fast_weights = E.opts.fast_weights;
+    c.fast_weights = E.opts.exact_weights ? 0 : 1;
     D.wcfg = make_weight_cfg(prm.dof);
     PairState hs;
     memset(&hs, 0, sizeof(hs));
@@ -532,7 +560,9 @@ static void engine_init(Engine& E, const ppcr_params& params, const ppcr_options
         CK(cudaStreamCreateWithFlags(&E.stream, cudaStreamNonBlocking));
         E.own_stream = true;
     }
-    E.d_active.reserve(4);
+    g_alloc_stream = E.stream;
+    E.d_loop.reserve(1);
+    CK(cudaMemsetAsync(E.d_loop.p, 0, sizeof(LoopCtl), E.stream));
     CK(cudaMallocHost(&E.h_active, 4 * sizeof(int)));
     if (E.opts.ticks_per_sync <= 0) E.opts.ticks_per_sync = 4;
     const char* env = getenv("PPCR_DRIVER");
@@ -559,7 +589,7 @@ static void engine_commit(Engine& E)
     const int cap_m = E.params.max_neighbours;
     E.list_cap = cap_m <= 4 ? 4 : cap_m <= 8 ? 8 : cap_m <= 12 ? 12 : cap_m <= 16 ? 16 : cap_m <= 20 ? 20
                : cap_m <= 24 ? 24 : cap_m <= 32 ? 32 : 0;
-    const int tiles = ceil_div(max_src, kSearchThreads);
+    const int tiles = std::max(1, std::min(ceil_div(max_src, kSearchChunk), E.search_blocks_per_sm * std::max(g_sm_count, 1)));
     const int trb = std::max(1, std::min(ceil_div(max_src, 256), 8 * std::max(g_sm_count, 1)));
     if (tiles > E.max_tiles || max_eval > E.max_eval_blocks || trb > E.max_tr_blocks) {
         E.max_tiles = std::max(E.max_tiles, tiles);
@@ -616,34 +646,42 @@ static void launch_search(Engine& E)
     }
 }
 
-static void launch_eval(Engine& E)
+// weights + moments + (in its last block) reduction, controller and loop condition
+static void launch_evalctl(Engine& E, bool use_cond)
 {
     const int np = static_cast<int>(E.pairs.size());
     dim3 grid(E.max_eval_blocks, np);
-    if (E.opts.fast_weights) k_eval<true><<<grid, kEvalThreads, 0, E.stream>>>(E.d_pairs.p);
-    else k_eval<false><<<grid, kEvalThreads, 0, E.stream>>>(E.d_pairs.p);
+    if (!E.opts.exact_weights)
+        k_evalctl<true><<<grid, kEvalThreads, 0, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, use_cond ? 1 : 0, E.max_ticks);
+    else
+        k_evalctl<false><<<grid, kEvalThreads, 0, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, use_cond ? 1 : 0, E.max_ticks);
 }
+
+static int launches_per_tick(const Engine& E) { return E.skip_search ? 1 : 2; }
 
 static void launch_tick(Engine& E, bool use_cond, bool rec)
 {
-    const int np = static_cast<int>(E.pairs.size());
     if (!E.skip_search) {
         stage_begin(E, rec, ST_SEARCH);
         launch_search(E);
         stage_end(E, rec);
     }
     stage_begin(E, rec, ST_EVAL);
-    launch_eval(E);
-    stage_end(E, rec);
-    stage_begin(E, rec, ST_CTRL);
-    k_controller<<<np, kCtrlThreads, 0, E.stream>>>(E.d_pairs.p, E.max_ticks);
-    stage_end(E, rec);
-    stage_begin(E, rec, ST_TRANSFORM);
-    k_transform<<<dim3(E.max_tr_blocks, np), 256, 0, E.stream>>>(E.d_pairs.p, np, E.d_active.p, E.cond, use_cond ? 1 : 0);
+    launch_evalctl(E, use_cond);
     stage_end(E, rec);
     CK(cudaGetLastError());
     E.times.ticks += 1;
-    E.times.total_launches += E.skip_search ? 3 : 4;
+    E.times.total_launches += launches_per_tick(E);
+}
+
+// epilogue of align(): the cloud move of the last outer iteration
+static void launch_final_transform(Engine& E)
+{
+    const int np = static_cast<int>(E.pairs.size());
+    k_transform_final<<<dim3(E.max_tr_blocks, np), 256, 0, E.stream>>>(E.d_pairs.p);
+    k_transform_done<<<ceil_div(np, 64), 64, 0, E.stream>>>(E.d_pairs.p, np);
+    CK(cudaGetLastError());
+    E.times.total_launches += 2;
 }
 
 static void collect_stage_times(Engine& E)
@@ -664,7 +702,7 @@ static void collect_stage_times(Engine& E)
     E.events.clear();
 }
 
-// body graph = one tick, wrapped in a WHILE node whose condition k_transform sets on the device
+// body graph = one tick, wrapped in a WHILE node whose condition k_evalctl sets on the device
 static bool build_graph(Engine& E)
 {
     if (E.graph_ready) return true;
@@ -694,7 +732,7 @@ static bool build_graph(Engine& E)
             goto bad;
         }
         E.times.ticks -= 1;
-        E.times.total_launches -= E.skip_search ? 3 : 4;
+        E.times.total_launches -= launches_per_tick(E);
         e = cudaStreamEndCapture(E.stream, nullptr);
         if (e != cudaSuccess) goto bad;
     }
@@ -717,7 +755,7 @@ bad:
 static void run_to_completion(Engine& E)
 {
     const int np = static_cast<int>(E.pairs.size());
-    k_align_begin<<<ceil_div(np, 64), 64, 0, E.stream>>>(E.d_pairs.p, np);
+    k_align_begin<<<ceil_div(np, 64), 64, 0, E.stream>>>(E.d_pairs.p, np, E.d_loop.p);
     CK(cudaGetLastError());
     E.times.total_launches += 1;
     const bool rec = E.opts.record_stage_times != 0;
@@ -725,19 +763,30 @@ static void run_to_completion(Engine& E)
     if (use_graph) use_graph = build_graph(E);
     if (use_graph) {
         CK(cudaGraphLaunch(E.graph_exec, E.stream));
+        launch_final_transform(E);
         CK(cudaStreamSynchronize(E.stream));
     } else {
         long long guard = 0;
         for (;;) {
             for (int t = 0; t < E.opts.ticks_per_sync; ++t) launch_tick(E, false, rec);
-            CK(cudaMemcpyAsync(E.h_active, E.d_active.p, sizeof(int), cudaMemcpyDeviceToHost, E.stream));
+            CK(cudaMemcpyAsync(E.h_active, E.d_loop.p, sizeof(int), cudaMemcpyDeviceToHost, E.stream));
             CK(cudaStreamSynchronize(E.stream));
             if (!E.h_active[0]) break;
             guard += E.opts.ticks_per_sync;
             if (guard > static_cast<long long>(E.max_ticks) + 64) throw StatusError{PPCR_ERR_CUDA, "tick guard exceeded"};
         }
+        launch_final_transform(E);
+        CK(cudaStreamSynchronize(E.stream));
         if (rec) collect_stage_times(E);
     }
+}
+
+// every entry point that works on an existing handle starts here
+static void use_engine(Engine& E)
+{
+    CK(cudaSetDevice(E.device));
+    g_alloc_stream = E.stream;
+    g_launch_sink = &E.times.total_launches;
 }
 
 static PairState download_state(Engine& E, int p)
@@ -762,6 +811,9 @@ static void set_phase(Engine& E, int p, int phase)
 {
     PairState s = download_state(E, p);
     s.phase = phase;
+    s.search_cursor = 0;
+    s.eval_ticket = 0;
+    s.apply_dT = 0;
     CK(cudaMemcpyAsync(E.pairs[p].state.p, &s, sizeof(s), cudaMemcpyHostToDevice, E.stream));
     CK(cudaStreamSynchronize(E.stream));
 }
@@ -851,14 +903,14 @@ static void upload_association(Engine& E, int p, const float* tgt_xyzw, int64_t 
     CK(cudaStreamSynchronize(E.stream));
 }
 
-// the 24 moments, reduced exactly like k_controller does (warp-strided partial sums, then warps in order)
+// the 24 moments, reduced exactly like the last block of k_evalctl does (interleaved chains, then chains in order)
 static void reduce_partials_like_controller(Engine& E, int p, double* S)
 {
     const PairDev& D = E.pairs[p].dev;
     std::vector<double> part(static_cast<size_t>(D.n_eval_blocks) * kNSum);
     CK(cudaMemcpyAsync(part.data(), D.partials, part.size() * sizeof(double), cudaMemcpyDeviceToHost, E.stream));
     CK(cudaStreamSynchronize(E.stream));
-    const int W = kCtrlThreads / 32;
+    const int W = kCtrlGroups;
     for (int k = 0; k < kNSum; ++k) {
         double total = 0.0;
         for (int w = 0; w < W; ++w) {
@@ -943,7 +995,7 @@ ppcr_status ppcr_align(ppcr_handle* h)
     if (!h) return fail(PPCR_ERR_INVALID, "null handle");
     return guarded([&] {
         Engine& E = h->eng;
-        CK(cudaSetDevice(E.device));
+        use_engine(E);
         run_to_completion(E);
         check_state_error(download_state(E, 0));
     });
@@ -954,7 +1006,7 @@ ppcr_status ppcr_has_converged(ppcr_handle* h, int32_t* out)
     if (!h || !out) return fail(PPCR_ERR_INVALID, "null argument");
     return guarded([&] {
         Engine& E = h->eng;
-        CK(cudaSetDevice(E.device));
+        use_engine(E);
         PairState s = download_state(E, 0);
         *out = has_converged(&s, &E.pairs[0].hcfg) ? 1 : 0;  // mutates the counter, like the reference
         CK(cudaMemcpyAsync(E.pairs[0].state.p, &s, sizeof(s), cudaMemcpyHostToDevice, E.stream));
@@ -967,7 +1019,7 @@ ppcr_status ppcr_history(ppcr_handle* h, double* T, int32_t* n_inout)
     if (!h || !n_inout) return fail(PPCR_ERR_INVALID, "null argument");
     return guarded([&] {
         Engine& E = h->eng;
-        CK(cudaSetDevice(E.device));
+        use_engine(E);
         PairState s = download_state(E, 0);
         const int n = std::min(s.current_iteration, E.pairs[0].dev.max_hist);
         const int take = std::min(n, *n_inout);
@@ -984,7 +1036,7 @@ ppcr_status ppcr_iteration_stats(ppcr_handle* h, ppcr_iter_stats* out, int32_t* 
     if (!h || !n_inout) return fail(PPCR_ERR_INVALID, "null argument");
     return guarded([&] {
         Engine& E = h->eng;
-        CK(cudaSetDevice(E.device));
+        use_engine(E);
         PairState s = download_state(E, 0);
         const int n = std::min(s.current_iteration, E.pairs[0].dev.max_hist);
         const int take = std::min(n, *n_inout);
@@ -1030,7 +1082,7 @@ ppcr_status ppcr_filtered_source(ppcr_handle* h, float* out, int64_t* n_inout)
     if (!h) return fail(PPCR_ERR_INVALID, "null handle");
     return guarded([&] {
         Engine& E = h->eng;
-        CK(cudaSetDevice(E.device));
+        use_engine(E);
         download_cloud(E, E.pairs[0].src.p, E.pairs[0].n_src, out, n_inout, true);
     });
 }
@@ -1040,7 +1092,7 @@ ppcr_status ppcr_filtered_target(ppcr_handle* h, float* out, int64_t* n_inout)
     if (!h) return fail(PPCR_ERR_INVALID, "null handle");
     return guarded([&] {
         Engine& E = h->eng;
-        CK(cudaSetDevice(E.device));
+        use_engine(E);
         download_cloud(E, E.pairs[0].tgt_raw.p, E.pairs[0].n_tgt, out, n_inout, false);
     });
 }
@@ -1050,7 +1102,7 @@ ppcr_status ppcr_association(ppcr_handle* h, int32_t* idx, int32_t* count, int64
     if (!h || !idx || !count) return fail(PPCR_ERR_INVALID, "null argument");
     return guarded([&] {
         Engine& E = h->eng;
-        CK(cudaSetDevice(E.device));
+        use_engine(E);
         download_association(E, 0, idx, nullptr, count, n_src, max_neighbours);
     });
 }
@@ -1060,12 +1112,12 @@ ppcr_status ppcr_get_stage_times(ppcr_handle* h, ppcr_stage_times* out)
     if (!h || !out) return fail(PPCR_ERR_INVALID, "null argument");
     return guarded([&] {
         Engine& E = h->eng;
-        CK(cudaSetDevice(E.device));
+        use_engine(E);
         *out = E.times;
         if (E.graph_ready) {  // the WHILE graph loops on the device: one body execution (4 kernels) per tick
             const PairState s = download_state(E, 0);
             out->ticks = s.ticks;
-            out->total_launches = E.times.total_launches + (E.skip_search ? 3 : 4) * s.ticks;
+            out->total_launches = E.times.total_launches + launches_per_tick(E) * s.ticks;
         }
     });
 }
@@ -1076,30 +1128,46 @@ ppcr_status ppcr_time_kernel(ppcr_handle* h, int32_t which, int32_t reps, int32_
     if (!h || !avg_ms || reps <= 0) return fail(PPCR_ERR_INVALID, "bad argument");
     return guarded([&] {
         Engine& E = h->eng;
-        CK(cudaSetDevice(E.device));
+        use_engine(E);
         Pair& P = E.pairs[0];
         const PairDev& D = P.dev;
         PairState saved = download_state(E, 0);
         PairState tmp = saved;
-        tmp.phase = (which == 0) ? PH_SEARCH : PH_LM;
-        tmp.apply_dT = (which == 2) ? 1 : 0;
-        if (which == 2)
+        const bool is_search = (which == 0 || which == 4);
+        tmp.phase = is_search ? PH_SEARCH : PH_LM;
+        tmp.search_cursor = 0;
+        tmp.eval_ticket = 0;
+        tmp.K = 0;
+        tmp.apply_dT = (which == 2 || which == 4) ? 1 : 0;
+        if (tmp.apply_dT)
             for (int k = 0; k < 16; ++k) tmp.dT[k] = (k % 5 == 0) ? 1.0 : 0.0;  // identity: the cloud is unchanged
-        CK(cudaMemcpyAsync(P.state.p, &tmp, sizeof(tmp), cudaMemcpyHostToDevice, E.stream));
         const size_t flush_n = (256ull << 20) / sizeof(float4);
         if (flush_l2) E.flush.reserve(flush_n);
         std::vector<cudaEvent_t> ev(2 * static_cast<size_t>(reps));
         for (auto& e : ev) CK(cudaEventCreate(&e));
+        double K_sum = 0;
+        // PPCR_PROFILE_KERNEL=<which>: bracket exactly these launches for `ncu --profile-from-start off`
+        const char* prof_env = getenv("PPCR_PROFILE_KERNEL");
+        const bool prof = prof_env && atoi(prof_env) == which;
         for (int r = 0; r < reps; ++r) {
+            // every launch starts from the same state (the controller / the work cursor mutate it)
+            CK(cudaMemcpyAsync(P.state.p, &tmp, sizeof(tmp), cudaMemcpyHostToDevice, E.stream));
+            CK(cudaStreamSynchronize(E.stream));
             if (flush_l2) k_fill<<<4 * std::max(g_sm_count, 1), 256, 0, E.stream>>>(E.flush.p, flush_n, static_cast<float>(r));
+            if (prof) cudaProfilerStart();
             CK(cudaEventRecord(ev[2 * r], E.stream));
             switch (which) {
-                case 0: launch_search(E); break;
-                case 1: launch_eval(E); break;
-                case 2: k_transform<<<dim3(E.max_tr_blocks, 1), 256, 0, E.stream>>>(E.d_pairs.p, 1, E.d_active.p, E.cond, 0); break;
+                case 0: case 4: launch_search(E); break;
+                case 1: launch_evalctl(E, false); break;
+                case 2: k_transform_final<<<dim3(E.max_tr_blocks, 1), 256, 0, E.stream>>>(E.d_pairs.p); break;
                 default: build_target_tree(E, P, D.tree.leaf_cap); break;
             }
             CK(cudaEventRecord(ev[2 * r + 1], E.stream));
+            if (prof) {
+                CK(cudaStreamSynchronize(E.stream));
+                cudaProfilerStop();
+            }
+            if (is_search) K_sum += static_cast<double>(download_state(E, 0).K);
         }
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(E.stream));
@@ -1111,12 +1179,13 @@ ppcr_status ppcr_time_kernel(ppcr_handle* h, int32_t which, int32_t reps, int32_
         }
         for (auto& e : ev) cudaEventDestroy(e);
         *avg_ms = static_cast<float>(total / reps);
-        PairState after = download_state(E, 0);
-        const double K = (which == 0) ? static_cast<double>(after.K - tmp.K) / reps : static_cast<double>(saved.K);
+        const double K = is_search ? K_sum / reps : static_cast<double>(saved.K);
         if (algorithmic_bytes) {
             const double ns = D.n_src, nt = D.n_tgt;
             switch (which) {
-                case 0: *algorithmic_bytes = 16.0 * ns + 16.0 * nt + 4.0 * ns + 16.0 * K; break;  // query, target, count, 3 planes + idx
+                // query (+ write-back when moving), target, count + k-th distance, 3 planes + index per correspondence
+                case 0: *algorithmic_bytes = 16.0 * ns + 16.0 * nt + 8.0 * ns + 16.0 * K; break;
+                case 4: *algorithmic_bytes = 32.0 * ns + 16.0 * nt + 12.0 * ns + 16.0 * K; break;
                 case 1: *algorithmic_bytes = 16.0 * ns + 4.0 * ns + 12.0 * K; break;              // source, count, 3 planes
                 case 2: *algorithmic_bytes = 32.0 * ns; break;
                 default: *algorithmic_bytes = 44.0 * nt; break;  // read 16, key+value 12, sorted write 16
@@ -1174,6 +1243,7 @@ ppcr_status ppcr_radius_search(const float* src, int64_t n_src, const float* tgt
         engine_commit(E);
         set_phase(E, 0, PH_SEARCH);
         if (n_src > 0) launch_search(E);
+        note_launches(1);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(E.stream));
         download_association(E, 0, out_idx, out_d2, out_count, n_src, max_nn);
@@ -1196,7 +1266,7 @@ ppcr_status ppcr_weights_normal_eq(const float* src, int64_t n_src, const float*
         prm.radius = 1.0;
         ppcr_options opt;
         ppcr_default_options(&opt);
-        opt.fast_weights = fast_weights;
+        opt.exact_weights = fast_weights ? 0 : 1;
         Engine E;
         engine_init(E, prm, &opt);
         E.pairs.resize(1);
@@ -1209,7 +1279,7 @@ ppcr_status ppcr_weights_normal_eq(const float* src, int64_t n_src, const float*
         pose7_to_state(pose_e, &s.pose_e);
         pose7_to_state(pose_w, &s.pose_w);
         CK(cudaMemcpyAsync(E.pairs[0].state.p, &s, sizeof(s), cudaMemcpyHostToDevice, E.stream));
-        launch_eval(E);
+        launch_evalctl(E, false);  // its controller tail runs on a scratch state; only the partial sums are used
         CK(cudaGetLastError());
         double S[kNSum];
         reduce_partials_like_controller(E, 0, S);
@@ -1245,7 +1315,8 @@ ppcr_status ppcr_weights_normal_eq(const float* src, int64_t n_src, const float*
 
 ppcr_status ppcr_iteration_solve(const float* src, int64_t n_src, const float* tgt, int64_t n_tgt, const int32_t* idx,
                                  const int32_t* count, int32_t max_nn, const ppcr_params* params,
-                                 double function_tolerance, double* out_pose, double* out_T, ppcr_iter_stats* stats)
+                                 const ppcr_options* options, double function_tolerance, double* out_pose, double* out_T,
+                                 ppcr_iter_stats* stats)
 {
     if (!idx || !count || !params) return fail(PPCR_ERR_INVALID, "null argument");
     return guarded([&] {
@@ -1256,6 +1327,7 @@ ppcr_status ppcr_iteration_solve(const float* src, int64_t n_src, const float* t
         prm.target_filter_size = 0;
         ppcr_options opt;
         ppcr_default_options(&opt);
+        if (options) opt = *options;
         opt.function_tolerance = function_tolerance;
         opt.driver = 1;
         Engine E;
@@ -1275,7 +1347,7 @@ ppcr_status ppcr_iteration_solve(const float* src, int64_t n_src, const float* t
         long long guard = 0;
         for (;;) {
             for (int t = 0; t < E.opts.ticks_per_sync; ++t) launch_tick(E, false, false);
-            CK(cudaMemcpyAsync(E.h_active, E.d_active.p, sizeof(int), cudaMemcpyDeviceToHost, E.stream));
+            CK(cudaMemcpyAsync(E.h_active, E.d_loop.p, sizeof(int), cudaMemcpyDeviceToHost, E.stream));
             CK(cudaStreamSynchronize(E.stream));
             if (!E.h_active[0]) break;
             if (++guard > 100000) throw StatusError{PPCR_ERR_CUDA, "inner solve did not terminate"};
@@ -1293,6 +1365,7 @@ ppcr_status ppcr_transform(float* xyzw, int64_t n, const double* T)
     if ((n > 0 && !xyzw) || !T || n < 0) return fail(PPCR_ERR_INVALID, "bad argument");
     return guarded([&] {
         select_device(0);
+        g_alloc_stream = nullptr;  // the legacy default stream, like the copies and the launch below
         if (n == 0) return;
         DevBuf<float4> d;
         DevBuf<double> dT;
@@ -1350,11 +1423,12 @@ ppcr_status ppcr_shard_export(ppcr_handle* h, int32_t rank, int32_t world, uint8
     return guarded([&] {
         static_assert(sizeof(cudaIpcMemHandle_t) <= PPCR_SHARD_TOKEN_BYTES, "token size");
         Engine& E = h->eng;
-        CK(cudaSetDevice(E.device));
+        use_engine(E);
         Pair& P = E.pairs[0];
         E.rank = rank;
         E.world = world;
         // a dedicated allocation: IPC handles cover whole cudaMalloc blocks
+        P.mailbox.plain = true;
         P.mailbox.reserve(2ull * 8 * kMailDoubles);
         CK(cudaMemset(P.mailbox.p, 0, P.mailbox.cap * sizeof(double)));
         cudaIpcMemHandle_t mh;
@@ -1369,7 +1443,7 @@ ppcr_status ppcr_shard_connect(ppcr_handle* h, const uint8_t* tokens)
     if (!h || !tokens) return fail(PPCR_ERR_INVALID, "bad argument");
     return guarded([&] {
         Engine& E = h->eng;
-        CK(cudaSetDevice(E.device));
+        use_engine(E);
         Pair& P = E.pairs[0];
         if (!P.mailbox.p) throw StatusError{PPCR_ERR_INVALID, "call ppcr_shard_export first"};
         E.peer_ptrs.assign(E.world, nullptr);

@@ -23,6 +23,8 @@ struct WeightCfg {
     double inv_dof;    // 1 / v is NOT used for the log argument (the reference divides); kept for the fp32 path
     int32_t is_normal; // v == +inf: Gaussian model, w = softmax(-r^2/2)
     int32_t pad;
+    // float32 copies for the fast path
+    float f_dof, f_t_exponent, f_dof_plus_d, f_inv_dof;
 };
 
 PPCR_HD WeightCfg make_weight_cfg(double dof, int dimension = 3)
@@ -35,6 +37,10 @@ PPCR_HD WeightCfg make_weight_cfg(double dof, int dimension = 3)
     w.dof_plus_d = dof + dim;
     w.inv_dof = w.is_normal ? 0.0 : 1.0 / dof;
     w.pad = 0;
+    w.f_dof = w.is_normal ? 0.f : static_cast<float>(dof);
+    w.f_t_exponent = static_cast<float>(w.t_exponent);
+    w.f_dof_plus_d = w.is_normal ? 0.f : static_cast<float>(w.dof_plus_d);
+    w.f_inv_dof = static_cast<float>(w.inv_dof);
     return w;
 }
 
@@ -138,6 +144,123 @@ PPCR_HD void row_end(const RowAcc* a, double sx, double sy, double sz, double* a
     acc[M_C + 8] += sz * rho[2];
     acc[M_COST] += 0.5 * a->ac * inv;
     acc[M_ROWS] += 1.0;
+}
+
+// ---- fast path ------------------------------------------------------------------------------------------------
+//
+// The same row arithmetic with float32 transcendentals and float32 in-row sums.  The residuals keep (nearly) full
+// float32 relative precision although they are differences of ~10..100 m coordinates: the transformed source point
+// is held as an unevaluated float pair (hi + lo), and y - hi is exact or within one rounding, so
+// r = (y - hi) - lo carries ~1e-7 relative error instead of 1e-7 * |y| absolute.  Weights then agree with the
+// float64 formula to a few 1e-7 relative (the bar is 1e-5); everything that is summed ACROSS rows stays float64.
+
+struct PointHL {  // p = hi + lo, component-wise
+    float hi[3], lo[3];
+};
+
+PPCR_HD void split_point(const double* p, PointHL* out)
+{
+    for (int k = 0; k < 3; ++k) {
+        out->hi[k] = static_cast<float>(p[k]);
+        out->lo[k] = static_cast<float>(p[k] - static_cast<double>(out->hi[k]));
+    }
+}
+
+struct RowAccF {
+    float m;      // running max of the log-probabilities
+    float a0;     // sum exp(l - m)
+    float a1;     // sum exp(l - m) e
+    float ar[3];  // sum exp(l - m) e r
+    float ac;     // sum exp(l - m) e |r|^2
+};
+
+PPCR_HD void rowf_begin(RowAccF* a)
+{
+    a->m = -3.0e38f;
+    a->a0 = a->a1 = a->ac = 0.f;
+    a->ar[0] = a->ar[1] = a->ar[2] = 0.f;
+}
+
+PPCR_HD float residual_hl(float y, float hi, float lo)
+{
+#if defined(__CUDA_ARCH__)
+    return __fsub_rn(__fsub_rn(y, hi), lo);
+#else
+    return (y - hi) - lo;
+#endif
+}
+
+// same_pose: pose_w == pose_e (first evaluation of an outer iteration), the weight residual is the cost residual
+PPCR_HD void rowf_add(RowAccF* a, const WeightCfg& wc, float yx, float yy, float yz, const PointHL& pe, const PointHL& pw,
+                      bool same_pose)
+{
+    const float rx = residual_hl(yx, pe.hi[0], pe.lo[0]);
+    const float ry = residual_hl(yy, pe.hi[1], pe.lo[1]);
+    const float rz = residual_hl(yz, pe.hi[2], pe.lo[2]);
+    const float r2e = rx * rx + ry * ry + rz * rz;
+    float r2w = r2e;
+    if (!same_pose) {
+        const float wx = residual_hl(yx, pw.hi[0], pw.lo[0]);
+        const float wy = residual_hl(yy, pw.hi[1], pw.lo[1]);
+        const float wz = residual_hl(yz, pw.hi[2], pw.lo[2]);
+        r2w = wx * wx + wy * wy + wz * wz;
+    }
+    float lp, ex;
+    if (wc.is_normal) {
+        lp = -0.5f * r2w;
+        ex = 1.f;
+    } else {
+        lp = wc.f_t_exponent * log1pf(r2w * wc.f_inv_dof);
+        ex = wc.f_dof_plus_d / (wc.f_dof + r2w);
+    }
+    if (lp > a->m) {  // new row maximum: rescale what has been accumulated so far
+        const float sc = expf(a->m - lp);
+        a->a0 *= sc;
+        a->a1 *= sc;
+        a->ar[0] *= sc;
+        a->ar[1] *= sc;
+        a->ar[2] *= sc;
+        a->ac *= sc;
+        a->m = lp;
+    }
+    const float p = expf(lp - a->m);
+    const float pw_ = p * ex;
+    a->a0 += p;
+    a->a1 += pw_;
+    a->ar[0] += pw_ * rx;
+    a->ar[1] += pw_ * ry;
+    a->ar[2] += pw_ * rz;
+    a->ac += pw_ * r2e;
+}
+
+PPCR_HD void rowf_end(const RowAccF* a, double sx, double sy, double sz, double* acc)
+{
+    RowAcc d;
+    d.m = a->m;
+    d.a0 = a->a0;
+    d.a1 = a->a1;
+    d.ar[0] = a->ar[0];
+    d.ar[1] = a->ar[1];
+    d.ar[2] = a->ar[2];
+    d.ac = a->ac;
+    row_end(&d, sx, sy, sz, acc);
+}
+
+PPCR_HD float rowf_finished_weight(const RowAccF* a, const WeightCfg& wc, float yx, float yy, float yz, const PointHL& pw)
+{
+    const float wx = residual_hl(yx, pw.hi[0], pw.lo[0]);
+    const float wy = residual_hl(yy, pw.hi[1], pw.lo[1]);
+    const float wz = residual_hl(yz, pw.hi[2], pw.lo[2]);
+    const float r2w = wx * wx + wy * wy + wz * wz;
+    float lp, ex;
+    if (wc.is_normal) {
+        lp = -0.5f * r2w;
+        ex = 1.f;
+    } else {
+        lp = wc.f_t_exponent * log1pf(r2w * wc.f_inv_dof);
+        ex = wc.f_dof_plus_d / (wc.f_dof + r2w);
+    }
+    return expf(lp - a->m) / a->a0 * ex;
 }
 
 PPCR_HD void apply_pose(const Pose& p, double sx, double sy, double sz, double* out)

@@ -36,6 +36,7 @@ namespace ppcr {
 
 constexpr int kSearchThreads = 128;  // one query per thread
 constexpr int kEvalThreads = 256;
+constexpr int kMailDoubles = 32;  // 24 moments + K + sequence stamp, padded
 constexpr unsigned kFull = 0xffffffffu;
 
 struct PairDev {
@@ -54,6 +55,7 @@ struct PairDev {
     float* nbr_z;
     int* nbr_idx;   // original target index
     float* nbr_d2;  // optional (stage API only), may be null
+    float* nbr_kth; // d2 of the m-th neighbour found by the last search (+inf when fewer were found): warm start
     int* nbr_cnt;
     double* partials;
     int n_eval_blocks;
@@ -69,8 +71,6 @@ struct PairDev {
     int rank, world;
     long long spin_limit;
 };
-
-constexpr int kMailDoubles = 32;  // 24 moments + K + sequence stamp, padded
 
 // ------------------------------------------------------------------------------------------------------------
 // bounding box
@@ -297,12 +297,14 @@ __global__ void k_tree_split_level(TreeGeom g, const unsigned long long* __restr
 // radius search: one thread per query walks the octree with a register-resident sorted top-m list
 // ------------------------------------------------------------------------------------------------------------
 
-template <int CAP, class List>
-__device__ __forceinline__ void search_one(const PairDev& P, int i, List& L, int* stack)
+__device__ __forceinline__ float transform_row(const double* T, double x, double y, double z)
 {
-    const float4 q = P.src[i];
-    L.init(P.m);
-    tree_search(P.tree, P.nodes, P.tgt_sorted, q.x, q.y, q.z, P.r2f, L, stack);
+    // pcl::transformPointCloud: double arithmetic without contraction, then one rounding to float
+    double acc = __dmul_rn(T[0], x);
+    acc = __dadd_rn(acc, __dmul_rn(T[1], y));
+    acc = __dadd_rn(acc, __dmul_rn(T[2], z));
+    acc = __dadd_rn(acc, T[3]);
+    return __double2float_rn(acc);
 }
 
 __device__ __forceinline__ void search_store(const PairDev& P, int i, int e, unsigned long long key)
@@ -317,32 +319,61 @@ __device__ __forceinline__ void search_store(const PairDev& P, int i, int e, uns
     if (P.nbr_d2) P.nbr_d2[o] = key_d2(key);
 }
 
-__device__ __forceinline__ void search_count(PairState* st, int cnt)
-{
-    // association size: warp sum, one atomic per warp
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
-    if ((threadIdx.x & 31) == 0 && cnt)
-        atomicAdd(reinterpret_cast<unsigned long long*>(&st->K), static_cast<unsigned long long>(cnt));
-}
+constexpr int kSearchChunk = kSearchThreads;  // queries handed out per grab of the work cursor
 
+// Persistent blocks pull chunks of 128 consecutive (Morton-sorted) queries from a cursor in the pair state, so dense
+// and sparse parts of the cloud balance across SMs and an idle launch (LM phase) costs one block wave of early exits.
+//
+// Fused into the load of the query: the cloud move of the PREVIOUS outer iteration (registration.cc:110-112,
+// x <- float(dT * x) in double arithmetic, written back in place) -- every search of an align() except the first
+// follows a pose update -- and the warm start of the pruning bound: the m targets found last time lie within
+// sqrt(d_m) + |dx| of the moved query, so nothing farther than that can be among the m nearest now.
+//
 // CAP > 0: list of CAP registers (m <= CAP).  CAP == 0: any m, list in local memory.
 template <int CAP>
 __global__ void __launch_bounds__(kSearchThreads) k_search(const PairDev* __restrict__ pairs)
 {
     const PairDev& P = pairs[blockIdx.y];
     PairState* st = P.state;
-    // the increment published by the previous tick has been consumed by k_transform: retire the flag
-    if (blockIdx.x == 0 && threadIdx.x == 0) st->apply_dT = 0;
     if (st->phase != PH_SEARCH) return;
-    if (static_cast<int>(blockIdx.x) * kSearchThreads >= P.n_src) return;
-    const int i = blockIdx.x * kSearchThreads + threadIdx.x;
+    __shared__ double s_T[12];
+    __shared__ int s_chunk;
+    const bool moving = st->apply_dT != 0;
+    if (threadIdx.x < 12) s_T[threadIdx.x] = st->dT[threadIdx.x];
     const int m = P.m;
+    const int n_chunks = (P.n_src + kSearchChunk - 1) / kSearchChunk;
     int stack[kTreeStack];
-    int cnt = 0;
-    if (i < P.n_src) {
+    int cnt_total = 0;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_chunk = atomicAdd(&st->search_cursor, 1);
+        __syncthreads();
+        const int chunk = s_chunk;
+        if (chunk >= n_chunks) break;
+        const int i = chunk * kSearchChunk + threadIdx.x;
+        if (i >= P.n_src) continue;
+        float4 q = P.src[i];
+        float bound0 = P.r2f;
+        if (moving) {
+            const double x = q.x, y = q.y, z = q.z;
+            const float nx = transform_row(s_T, x, y, z), ny = transform_row(s_T + 4, x, y, z),
+                        nz = transform_row(s_T + 8, x, y, z);
+            const float prev = P.nbr_kth[i];  // d2 of the m-th neighbour of the last search, +inf if it found fewer
+            const float ddx = nx - q.x, ddy = ny - q.y, ddz = nz - q.z;
+            const float move = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz) * 1.000001f;
+            const float reach = sqrtf(prev) * 1.000001f + move;
+            bound0 = fminf(P.r2f, reach * reach * 1.00001f);  // inf stays inf -> r2f
+            q.x = nx;
+            q.y = ny;
+            q.z = nz;
+            P.src[i] = q;
+        }
+        int cnt = 0;
+        float kth = __int_as_float(0x7f800000);
         if constexpr (CAP > 0) {
             TopList<CAP> L;
-            search_one<CAP>(P, i, L, stack);
+            L.init(m);
+            tree_search(P.tree, P.nodes, P.tgt_sorted, q.x, q.y, q.z, P.r2f, bound0, L, stack);
 #pragma unroll
             for (int s = 0; s < CAP; ++s) {
                 const int e = m - 1 - s;  // ascending rank of slot s
@@ -351,36 +382,79 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(const PairDev* __rest
                     ++cnt;
                 }
             }
+            if (L.k[0] != kKeyInf) kth = key_d2(L.k[0]);
         } else {
             unsigned long long buf[128];
             TopListDyn L;
             L.k = buf;
-            search_one<0>(P, i, L, stack);
+            L.init(m);
+            tree_search(P.tree, P.nodes, P.tgt_sorted, q.x, q.y, q.z, P.r2f, bound0, L, stack);
             for (int s = 0; s < m; ++s) {
                 if (buf[s] != kKeyInf) {
                     search_store(P, i, m - 1 - s, buf[s]);
                     ++cnt;
                 }
             }
+            if (buf[0] != kKeyInf) kth = key_d2(buf[0]);
         }
         P.nbr_cnt[i] = cnt;
+        P.nbr_kth[i] = kth;
+        cnt_total += cnt;
     }
-    search_count(st, cnt);
+    // association size: warp sum, one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) cnt_total += __shfl_xor_sync(kFull, cnt_total, o);
+    if ((threadIdx.x & 31) == 0 && cnt_total)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&st->K), static_cast<unsigned long long>(cnt_total));
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // weights + normal-equation moments
 // ------------------------------------------------------------------------------------------------------------
 
+constexpr int kCtrlGroups = kEvalThreads / 32;  // partial sums are folded in kCtrlGroups interleaved chains
+
+__device__ __forceinline__ double ld_volatile_f64(const double* p)
+{
+    return *reinterpret_cast<const volatile double*>(p);
+}
+
+// The scalar LM / outer-loop state machine (ppcr_lm.h), one thread.  Kept out of line so that its register appetite
+// (a 7x7 Cholesky and the moment expansion, all float64) does not set the register count of the streaming part.
+__device__ __noinline__ void run_controller(const PairDev& P, const double* sums, int max_ticks)
+{
+    PairState* st = P.state;
+    double S[kNSum];
+    for (int k = 0; k < kNSum; ++k) S[k] = sums[k];
+    st->evals += 1;
+    controller_tick(st, P.cfg, S, P.history, P.stats, P.max_hist);
+    if (st->ticks >= max_ticks && st->phase != PH_DONE) {  // never spin forever on the device
+        st->error = 1;
+        st->phase = PH_DONE;
+    }
+}
+
+struct LoopCtl {   // one per engine
+    int active;      // any pair still running (read back by the host-stepped driver)
+    int pairs_done;  // pairs whose controller has finished this tick
+};
+
+// The per-iteration kernel: weights + moments over the association (every block), then -- in the block that
+// publishes its partial sums last -- the fixed-order reduction, the cross-rank exchange (sharded mode), the LM /
+// outer-loop controller and the loop condition of the tick graph.  One launch per LM iteration.
 template <bool kFast>
-__global__ void __launch_bounds__(kEvalThreads) k_eval(const PairDev* __restrict__ pairs)
+__global__ void __launch_bounds__(kEvalThreads, 2) k_evalctl(const PairDev* __restrict__ pairs, int n_pairs,
+                                                          LoopCtl* __restrict__ loop, cudaGraphConditionalHandle cond,
+                                                          int use_cond, int max_ticks)
 {
     const PairDev& P = pairs[blockIdx.y];
-    const PairState* st = P.state;
-    if (st->phase == PH_DONE) return;
-    if (static_cast<int>(blockIdx.x) >= P.n_eval_blocks) return;
+    PairState* st = P.state;
     __shared__ Pose s_pe, s_pw;
     __shared__ double s_red[kEvalThreads / 32][kNSum];
+    __shared__ double s_sum[kMailDoubles];
+    __shared__ int s_flag;
+    const bool live = st->phase != PH_DONE;
+    if (live) {
+    if (static_cast<int>(blockIdx.x) >= P.n_eval_blocks) return;
     if (threadIdx.x < 12) {
         const double* pe = reinterpret_cast<const double*>(&st->pose_e);
         const double* pw = reinterpret_cast<const double*>(&st->pose_w);
@@ -396,22 +470,64 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval(const PairDev* __restrict
     for (int k = 0; k < kNSum; ++k) acc[k] = 0.0;
     const int stride = P.n_eval_blocks * kEvalThreads;
     const size_t n_pad = P.n_pad;
-    for (int i = blockIdx.x * kEvalThreads + threadIdx.x; i < P.n_src; i += stride) {
-        const int cnt = P.nbr_cnt[i];
-        if (cnt == 0) continue;
-        const float4 sp = P.src[i];
-        const double sx = sp.x, sy = sp.y, sz = sp.z;
-        double pte[3], ptw[3];
-        apply_pose(pe, sx, sy, sz, pte);
-        apply_pose(pw, sx, sy, sz, ptw);
-        RowAcc row;
-        row_begin(&row);
-        for (int k = 0; k < cnt; ++k) {
-            const size_t o = static_cast<size_t>(k) * n_pad + i;
-            const float yx = __ldg(P.nbr_x + o), yy = __ldg(P.nbr_y + o), yz = __ldg(P.nbr_z + o);
-            row_add<kFast>(&row, wc, yx, yy, yz, pte, ptw);
+    if constexpr (kFast) {
+        // pose_w == pose_e on the first evaluation of every outer iteration: one residual serves both uses
+        bool same = true;
+#pragma unroll
+        for (int k = 0; k < 12; ++k)
+            same = same && (reinterpret_cast<const double*>(&s_pe)[k] == reinterpret_cast<const double*>(&s_pw)[k]);
+        for (int i = blockIdx.x * kEvalThreads + threadIdx.x; i < P.n_src; i += stride) {
+            const int cnt = P.nbr_cnt[i];
+            if (cnt == 0) continue;
+            const float4 sp = P.src[i];
+            const double sx = sp.x, sy = sp.y, sz = sp.z;
+            double pte[3], ptw[3];
+            apply_pose(pe, sx, sy, sz, pte);
+            PointHL he, hw;
+            split_point(pte, &he);
+            hw = he;
+            if (!same) {
+                apply_pose(pw, sx, sy, sz, ptw);
+                split_point(ptw, &hw);
+            }
+            RowAccF row;
+            rowf_begin(&row);
+            constexpr int kU = 8;  // loads of kU correspondences are issued before their arithmetic
+            for (int k0 = 0; k0 < cnt; k0 += kU) {
+                float yx[kU], yy[kU], yz[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    if (k0 + u < cnt) {
+                        const size_t o = static_cast<size_t>(k0 + u) * n_pad + i;
+                        yx[u] = __ldg(P.nbr_x + o);
+                        yy[u] = __ldg(P.nbr_y + o);
+                        yz[u] = __ldg(P.nbr_z + o);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u)
+                    if (k0 + u < cnt) rowf_add(&row, wc, yx[u], yy[u], yz[u], he, hw, same);
+            }
+            rowf_end(&row, sx, sy, sz, acc);
         }
-        row_end(&row, sx, sy, sz, acc);
+    } else {
+        for (int i = blockIdx.x * kEvalThreads + threadIdx.x; i < P.n_src; i += stride) {
+            const int cnt = P.nbr_cnt[i];
+            if (cnt == 0) continue;
+            const float4 sp = P.src[i];
+            const double sx = sp.x, sy = sp.y, sz = sp.z;
+            double pte[3], ptw[3];
+            apply_pose(pe, sx, sy, sz, pte);
+            apply_pose(pw, sx, sy, sz, ptw);
+            RowAcc row;
+            row_begin(&row);
+            for (int k = 0; k < cnt; ++k) {
+                const size_t o = static_cast<size_t>(k) * n_pad + i;
+                const float yx = __ldg(P.nbr_x + o), yy = __ldg(P.nbr_y + o), yz = __ldg(P.nbr_z + o);
+                row_add<false>(&row, wc, yx, yy, yz, pte, ptw);
+            }
+            row_end(&row, sx, sy, sz, acc);
+        }
     }
     // fixed-shape reduction: xor-shuffle tree inside the warp, then warps in index order
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -428,65 +544,39 @@ __global__ void __launch_bounds__(kEvalThreads) k_eval(const PairDev* __restrict
         for (int w = 0; w < kEvalThreads / 32; ++w) v += s_red[w][threadIdx.x];
         P.partials[static_cast<size_t>(blockIdx.x) * kNSum + threadIdx.x] = v;
     }
-}
-
-// weights of the current association at pose_w, written slot-major (parity dumps only)
-template <bool kFast>
-__global__ void k_dump_weights(const PairDev* __restrict__ pairs, double* __restrict__ out)
-{
-    const PairDev& P = pairs[0];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_src) return;
-    const int cnt = P.nbr_cnt[i];
-    if (cnt == 0) return;
-    const Pose pw = P.state->pose_w;
-    const float4 sp = P.src[i];
-    double ptw[3];
-    apply_pose(pw, sp.x, sp.y, sp.z, ptw);
-    RowAcc row;
-    row_begin(&row);
-    const size_t n_pad = P.n_pad;
-    for (int k = 0; k < cnt; ++k) {
-        const size_t o = static_cast<size_t>(k) * n_pad + i;
-        row_add<kFast>(&row, P.wcfg, P.nbr_x[o], P.nbr_y[o], P.nbr_z[o], ptw, ptw);
-    }
-    for (int k = 0; k < cnt; ++k) {
-        const size_t o = static_cast<size_t>(k) * n_pad + i;
-        out[o] = finished_weight<kFast>(&row, P.wcfg, P.nbr_x[o], P.nbr_y[o], P.nbr_z[o], ptw);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// controller: reduce the per-block moments in a fixed order, then run the LM / outer-loop state machine
-// ------------------------------------------------------------------------------------------------------------
-
-constexpr int kCtrlThreads = 256;
-
-__device__ __forceinline__ double ld_volatile_f64(const double* p)
-{
-    return *reinterpret_cast<const volatile double*>(p);
-}
-
-__global__ void __launch_bounds__(kCtrlThreads) k_controller(const PairDev* __restrict__ pairs, int max_ticks)
-{
-    const PairDev& P = pairs[blockIdx.x];
-    PairState* st = P.state;
-    if (st->phase == PH_DONE) return;
-    __shared__ double s_part[kCtrlThreads / 32][kNSum];
-    __shared__ double s_sum[kMailDoubles];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double v = 0.0;
-    if (lane < kNSum)
-        for (int b = warp; b < P.n_eval_blocks; b += kCtrlThreads / 32) v += P.partials[static_cast<size_t>(b) * kNSum + lane];
-    if (lane < kNSum) s_part[warp][lane] = v;
+    // ---- last block standing runs the controller --------------------------------------------------------------
+    __threadfence();
     __syncthreads();
-    if (threadIdx.x < kNSum) {
-        double t = 0.0;
+    if (threadIdx.x == 0) s_flag = (atomicAdd(&st->eval_ticket, 1) == P.n_eval_blocks - 1);
+    __syncthreads();
+    if (!s_flag) return;
+    __threadfence();
+    if (threadIdx.x == 0) st->eval_ticket = 0;
+    {
+        // group g folds blocks g, g + G, g + 2G, ... in order (loads issued eight at a time), then the groups in order
+        double v = 0.0;
+        if (lane < kNSum) {
+            const double* base = P.partials + lane;
+            int b = warp;
+            for (; b + 7 * kCtrlGroups < P.n_eval_blocks; b += 8 * kCtrlGroups) {
+                double t[8];
 #pragma unroll
-        for (int w = 0; w < kCtrlThreads / 32; ++w) t += s_part[w][threadIdx.x];
-        s_sum[threadIdx.x] = t;
+                for (int u = 0; u < 8; ++u) t[u] = __ldcg(base + static_cast<size_t>(b + u * kCtrlGroups) * kNSum);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v += t[u];
+            }
+            for (; b < P.n_eval_blocks; b += kCtrlGroups) v += __ldcg(base + static_cast<size_t>(b) * kNSum);
+            s_red[warp][lane] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < kNSum) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kCtrlGroups; ++w) t += s_red[w][threadIdx.x];
+            s_sum[threadIdx.x] = t;
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     if (P.world > 1) {
         // Sharded pair: every rank adds the other ranks' moments (and association sizes) in rank order, so all
@@ -535,66 +625,100 @@ __global__ void __launch_bounds__(kCtrlThreads) k_controller(const PairDev* __re
                 st->error = PH_DONE + 100;
                 st->phase = PH_DONE;
             }
-            return;
+        } else {
+            if (threadIdx.x <= kNSum) {
+                const int parity = seq & 1;
+                double t = 0.0;
+                for (int r = 0; r < P.world; ++r)
+                    t += ld_volatile_f64(P.mailbox + (static_cast<size_t>(parity) * P.world + r) * kMailDoubles + threadIdx.x);
+                s_sum[threadIdx.x] = t;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0 && st->phase == PH_SEARCH) st->K = static_cast<int64_t>(s_sum[kNSum]);
         }
-        if (threadIdx.x <= kNSum) {
-            const int parity = seq & 1;
-            double t = 0.0;
-            for (int r = 0; r < P.world; ++r)
-                t += ld_volatile_f64(P.mailbox + (static_cast<size_t>(parity) * P.world + r) * kMailDoubles + threadIdx.x);
-            s_sum[threadIdx.x] = t;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0 && st->phase == PH_SEARCH) st->K = static_cast<int64_t>(s_sum[kNSum]);
         __syncthreads();
     }
 
+    if (threadIdx.x == 0 && st->phase != PH_DONE) run_controller(P, s_sum, max_ticks);
+    } else if (blockIdx.x != 0) {
+        return;  // a finished pair: one block keeps the tick protocol going
+    }
+    // ---- loop condition: the last pair to finish its tick publishes "is anything still running" ----------------
     if (threadIdx.x == 0) {
-        double S[kNSum];
-        for (int k = 0; k < kNSum; ++k) S[k] = s_sum[k];
-        st->evals += 1;
-        controller_tick(st, P.cfg, S, P.history, P.stats, P.max_hist);
-        if (st->ticks >= max_ticks && st->phase != PH_DONE) {  // never spin forever on the device
-            st->error = 1;
-            st->phase = PH_DONE;
+        __threadfence();
+        if (atomicAdd(&loop->pairs_done, 1) == n_pairs - 1) {
+            __threadfence();
+            loop->pairs_done = 0;
+            int active = 0;
+            for (int p = 0; p < n_pairs; ++p) active |= (*reinterpret_cast<volatile int*>(&pairs[p].state->phase) != PH_DONE);
+            loop->active = active;
+            if (use_cond) cudaGraphSetConditional(cond, active ? 1u : 0u);
         }
     }
 }
 
-// align() entry: the first hasConverged() test
-__global__ void k_align_begin(const PairDev* __restrict__ pairs, int n_pairs)
+// weights of the current association at pose_w, written slot-major (parity dumps only)
+template <bool kFast>
+__global__ void k_dump_weights(const PairDev* __restrict__ pairs, double* __restrict__ out)
+{
+    const PairDev& P = pairs[0];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_src) return;
+    const int cnt = P.nbr_cnt[i];
+    if (cnt == 0) return;
+    const Pose pw = P.state->pose_w;
+    const float4 sp = P.src[i];
+    double ptw[3];
+    apply_pose(pw, sp.x, sp.y, sp.z, ptw);
+    const size_t n_pad = P.n_pad;
+    if constexpr (kFast) {
+        PointHL hw;
+        split_point(ptw, &hw);
+        RowAccF row;
+        rowf_begin(&row);
+        for (int k = 0; k < cnt; ++k) {
+            const size_t o = static_cast<size_t>(k) * n_pad + i;
+            rowf_add(&row, P.wcfg, P.nbr_x[o], P.nbr_y[o], P.nbr_z[o], hw, hw, true);
+        }
+        for (int k = 0; k < cnt; ++k) {
+            const size_t o = static_cast<size_t>(k) * n_pad + i;
+            out[o] = rowf_finished_weight(&row, P.wcfg, P.nbr_x[o], P.nbr_y[o], P.nbr_z[o], hw);
+        }
+    } else {
+        RowAcc row;
+        row_begin(&row);
+        for (int k = 0; k < cnt; ++k) {
+            const size_t o = static_cast<size_t>(k) * n_pad + i;
+            row_add<false>(&row, P.wcfg, P.nbr_x[o], P.nbr_y[o], P.nbr_z[o], ptw, ptw);
+        }
+        for (int k = 0; k < cnt; ++k) {
+            const size_t o = static_cast<size_t>(k) * n_pad + i;
+            out[o] = finished_weight<false>(&row, P.wcfg, P.nbr_x[o], P.nbr_y[o], P.nbr_z[o], ptw);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// align() entry and exit
+// ------------------------------------------------------------------------------------------------------------
+
+// the first hasConverged() test of align() (:65); also arms the loop condition for the first tick
+__global__ void k_align_begin(const PairDev* __restrict__ pairs, int n_pairs, LoopCtl* __restrict__ loop)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p < n_pairs) align_begin(pairs[p].state, pairs[p].cfg);
+    if (p == 0) {
+        loop->active = 1;
+        loop->pairs_done = 0;
+    }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// cloud move + loop condition
-// ------------------------------------------------------------------------------------------------------------
-
-__device__ __forceinline__ float transform_row(const double* T, double x, double y, double z)
-{
-    // pcl::transformPointCloud: double arithmetic without contraction, then one rounding to float
-    double acc = __dmul_rn(T[0], x);
-    acc = __dadd_rn(acc, __dmul_rn(T[1], y));
-    acc = __dadd_rn(acc, __dmul_rn(T[2], z));
-    acc = __dadd_rn(acc, T[3]);
-    return __double2float_rn(acc);
-}
-
-// Applies the increment of a finished outer iteration to the source cloud in place (registration.cc:110-112).
-// Block (0,0) also publishes "is any pair still running" for the loop around the tick.
-__global__ void k_transform(const PairDev* __restrict__ pairs, int n_pairs, int* __restrict__ active_flag,
-                            cudaGraphConditionalHandle cond, int use_cond)
+// Epilogue of align(): the increment of the LAST outer iteration (every earlier one is applied by the search that
+// follows it).  registration.cc:110-112.
+__global__ void k_transform_final(const PairDev* __restrict__ pairs)
 {
     const PairDev& P = pairs[blockIdx.y];
     PairState* st = P.state;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
-        int active = 0;
-        for (int p = 0; p < n_pairs; ++p) active |= (pairs[p].state->phase != PH_DONE);
-        *active_flag = active;
-        if (use_cond) cudaGraphSetConditional(cond, active ? 1u : 0u);
-    }
     if (!st->apply_dT) return;
     __shared__ double T[12];
     if (threadIdx.x < 12) T[threadIdx.x] = st->dT[threadIdx.x];
@@ -607,6 +731,12 @@ __global__ void k_transform(const PairDev* __restrict__ pairs, int n_pairs, int*
         p.z = transform_row(T + 8, x, y, z);
         P.src[i] = p;
     }
+}
+
+__global__ void k_transform_done(const PairDev* __restrict__ pairs, int n_pairs)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_pairs) pairs[p].state->apply_dT = 0;
 }
 
 __global__ void k_transform_plain(float4* __restrict__ pts, int n, const double* __restrict__ Tm)

@@ -94,7 +94,10 @@ struct PairState {
     int64_t K;        // correspondences of the current association (search kernel)
     int64_t K_total;  // summed over outer iterations
     int32_t ticks, evals;
-    int32_t error, pad;
+    int32_t error;
+    int32_t search_cursor;  // next chunk of queries to hand out (persistent search kernel)
+    int32_t eval_ticket;    // blocks of the eval kernel that have published their partial sums
+    int32_t pad;
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -463,7 +466,8 @@ PPCR_HD void outer_finish(PairState* s, const Config* cfg, double* history, Iter
         st->num_successful_steps = s->successful;
     }
     s->K_total += s->K;
-    s->apply_dT = 1;
+    s->apply_dT = 1;  // the next search (or the epilogue of align()) moves the cloud by dT first
+    s->search_cursor = 0;
     ++s->current_iteration;
     s->phase = has_converged(s, cfg) ? PH_DONE : PH_SEARCH;
     if (s->phase == PH_SEARCH) lm_reset(s, cfg);
@@ -477,6 +481,7 @@ PPCR_HD void controller_tick(PairState* s, const Config* cfg, const double* S, d
     ++s->ticks;
     bool go;
     if (s->phase == PH_SEARCH) {
+        s->apply_dT = 0;  // the search that fed this evaluation has moved the cloud
         go = lm_begin(s, cfg, S);
         s->phase = PH_LM;
     } else {
@@ -497,6 +502,8 @@ PPCR_HD void state_init(PairState* s, const Config* cfg)
     s->evals = 0;
     s->error = 0;
     s->pad = 0;
+    s->search_cursor = 0;
+    s->eval_ticket = 0;
     for (int k = 0; k < 16; ++k) {
         s->T_total[k] = (k % 5 == 0) ? 1.0 : 0.0;
         s->dT[k] = (k % 5 == 0) ? 1.0 : 0.0;
@@ -509,6 +516,7 @@ PPCR_HD void state_init(PairState* s, const Config* cfg)
 PPCR_HD void align_begin(PairState* s, const Config* cfg)
 {
     s->apply_dT = 0;
+    s->search_cursor = 0;
     if (has_converged(s, cfg)) {
         s->phase = PH_DONE;
     } else {

@@ -265,13 +265,15 @@ PPCR_HD float box_lower_bound(float qx, float qy, float qz, float cx, float cy, 
 }
 
 // Leaves the (at most m) nearest targets with d2 < r2f in L.  pts = Morton-sorted target, .w = original index.
+// bound0 <= r2f is a caller-supplied squared distance within which at least m targets are KNOWN to lie (r2f when
+// nothing is known): points farther than it cannot be among the m nearest, so subtrees beyond it are never opened.
 // `stack` must hold kTreeStack ints.
 template <class List>
 PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, const float4* __restrict__ pts,
-                         float qx, float qy, float qz, float r2f, List& L, int* stack)
+                         float qx, float qy, float qz, float r2f, float bound0, List& L, int* stack)
 {
     const unsigned long long r2key = static_cast<unsigned long long>(float_bits(r2f)) << 32;  // keys of d2 >= r2f are > this
-    float bound_d2 = r2f;  // no unseen point farther than this can enter the list
+    float bound_d2 = bound0 < r2f ? bound0 : r2f;  // no unseen point farther than this can enter the list
     int sp = 0;
     stack[sp++] = 0;
     while (sp > 0) {
@@ -280,19 +282,28 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
         if (n.end <= n.begin) continue;
         if (box_lower_bound(qx, qy, qz, n.cx, n.cy, n.cz, n.half + g.slack) > bound_d2) continue;
         if (n.child < 0) {
-            for (int j = n.begin; j < n.end; ++j) {
-                const float4 p = pts[j];
-                const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
-                if (d2 <= bound_d2) {
-                    const unsigned long long key = make_key(d2, static_cast<int>(float_bits(p.w)));
-                    if (key <= r2key && key < L.worst()) {  // key <= r2key  <=>  d2 < r2f (keys carry +1)
-                        L.insert(key);
-                        const unsigned long long w = L.worst();
-                        if (w != kKeyInf) {
-                            const float wd = key_d2(w);
-                            bound_d2 = wd < r2f ? wd : r2f;
+            // leaf: run ahead to the next candidate that enters the list, then insert.  Written as two nested loops so
+            // that the threads of a warp meet again at the (expensive) insertion instead of serialising it.
+            int j = n.begin;
+            for (;;) {
+                unsigned long long key = kKeyInf;
+                while (j < n.end) {
+                    const float4 p = pts[j++];
+                    const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+                    if (d2 <= bound_d2) {
+                        const unsigned long long k2 = make_key(d2, static_cast<int>(float_bits(p.w)));
+                        if (k2 <= r2key && k2 < L.worst()) {  // k2 <= r2key  <=>  d2 < r2f (keys carry +1)
+                            key = k2;
+                            break;
                         }
                     }
+                }
+                if (key == kKeyInf) break;
+                L.insert(key);
+                const unsigned long long w = L.worst();
+                if (w != kKeyInf) {
+                    const float wd = key_d2(w);
+                    bound_d2 = wd < bound_d2 ? wd : bound_d2;
                 }
             }
             continue;

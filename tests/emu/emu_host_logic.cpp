@@ -52,24 +52,55 @@ void search(const Cloud& src, const Cloud& tgt, double radius, int m, std::vecto
     }
 }
 
+void move_cloud(Cloud& src, const double* dT)
+{
+    for (int64_t i = 0; i < src.n; ++i) {
+        const double x = src.p[4 * i], y = src.p[4 * i + 1], z = src.p[4 * i + 2];
+        for (int r = 0; r < 3; ++r) {
+            const double* T = dT + 4 * r;
+            double acc = T[0] * x;
+            acc = acc + T[1] * y;
+            acc = acc + T[2] * z;
+            acc = acc + T[3];
+            src.p[4 * i + r] = static_cast<float>(acc);
+        }
+    }
+}
+
 template <bool kFast>
 void eval(const Cloud& src, const Cloud& tgt, const std::vector<int>& idx, const std::vector<int>& cnt, int m,
           const PairState& st, const WeightCfg& wc, double* S)
 {
     for (int k = 0; k < kNSum; ++k) S[k] = 0.0;
+    bool same = true;
+    for (int k = 0; k < 12; ++k)
+        same = same && (reinterpret_cast<const double*>(&st.pose_e)[k] == reinterpret_cast<const double*>(&st.pose_w)[k]);
     for (int64_t i = 0; i < src.n; ++i) {
         if (cnt[i] == 0) continue;
         const double sx = src.p[4 * i], sy = src.p[4 * i + 1], sz = src.p[4 * i + 2];
         double pe[3], pw[3];
         apply_pose(st.pose_e, sx, sy, sz, pe);
         apply_pose(st.pose_w, sx, sy, sz, pw);
-        RowAcc row;
-        row_begin(&row);
-        for (int k = 0; k < cnt[i]; ++k) {
-            const float* y = &tgt.p[4 * static_cast<size_t>(idx[i * m + k])];
-            row_add<kFast>(&row, wc, y[0], y[1], y[2], pe, pw);
+        if (kFast) {  // the float32 row path of k_eval<true>
+            PointHL he, hw;
+            split_point(pe, &he);
+            split_point(pw, &hw);
+            RowAccF row;
+            rowf_begin(&row);
+            for (int k = 0; k < cnt[i]; ++k) {
+                const float* y = &tgt.p[4 * static_cast<size_t>(idx[i * m + k])];
+                rowf_add(&row, wc, y[0], y[1], y[2], he, hw, same);
+            }
+            rowf_end(&row, sx, sy, sz, S);
+        } else {
+            RowAcc row;
+            row_begin(&row);
+            for (int k = 0; k < cnt[i]; ++k) {
+                const float* y = &tgt.p[4 * static_cast<size_t>(idx[i * m + k])];
+                row_add<false>(&row, wc, y[0], y[1], y[2], pe, pw);
+            }
+            row_end(&row, sx, sy, sz, S);
         }
-        row_end(&row, sx, sy, sz, S);
     }
 }
 
@@ -107,9 +138,9 @@ int emu_align(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, int64
     double S[kNSum];
     long long guard = 0;
     while (st.phase != PH_DONE && guard++ < 10000000) {
-        // one tick: search (if needed), eval, controller, transform -- the order k_* kernels run in
-        st.apply_dT = 0;
+        // one tick: [move the cloud + search] (if needed), eval, controller -- the order the kernels run in
         if (st.phase == PH_SEARCH) {
+            if (st.apply_dT) move_cloud(src, st.dT);
             search(src, tgt, radius, m, idx, cnt);
             int64_t K = 0;
             for (int c : cnt) K += c;
@@ -117,19 +148,10 @@ int emu_align(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, int64
         }
         if (fast_weights) eval<true>(src, tgt, idx, cnt, m, st, wc, S); else eval<false>(src, tgt, idx, cnt, m, st, wc, S);
         controller_tick(&st, &cfg, S, hist.data(), stv.data(), max_hist);
-        if (st.apply_dT) {
-            for (int64_t i = 0; i < src.n; ++i) {
-                const double x = src.p[4 * i], y = src.p[4 * i + 1], z = src.p[4 * i + 2];
-                for (int r = 0; r < 3; ++r) {
-                    const double* T = st.dT + 4 * r;
-                    double acc = T[0] * x;
-                    acc = acc + T[1] * y;
-                    acc = acc + T[2] * z;
-                    acc = acc + T[3];
-                    src.p[4 * i + r] = static_cast<float>(acc);
-                }
-            }
-        }
+    }
+    if (st.apply_dT) {  // epilogue of align(): the increment of the last outer iteration
+        move_cloud(src, st.dT);
+        st.apply_dT = 0;
     }
     const int n = std::min(st.current_iteration, max_hist);
     if (history) std::memcpy(history, hist.data(), sizeof(double) * 16 * n);
@@ -168,8 +190,8 @@ void emu_normal_eq(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, 
 // same traversal the search kernel runs, one query at a time.  Rows come back sorted ascending by (d2, index).
 // list_kind: 0 = register list sized like the kernel's dispatch, 1 = the addressable list used for m > 32.
 int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, int64_t n_tgt, double radius,
-                        int max_nn, int leaf_cap, int list_kind, int* out_idx, float* out_d2, int* out_cnt,
-                        int* out_n_nodes)
+                        int max_nn, int leaf_cap, int list_kind, const float* bounds, int* out_idx, float* out_d2,
+                        int* out_cnt, int* out_n_nodes)
 {
     const int m = static_cast<int>(std::min<int64_t>(max_nn, std::max<int64_t>(n_tgt, 1)));
     const float r2f = static_cast<float>(radius * radius);
@@ -231,6 +253,7 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
     std::vector<unsigned long long> buf(static_cast<size_t>(std::max(m, 1)));
     for (int64_t i = 0; i < n_src; ++i) {
         const float* q = src_xyzw + 4 * i;
+        const float bound0 = bounds ? bounds[i] : r2f;
         std::vector<unsigned long long> found;
         auto take = [&](const unsigned long long* k, int cap) {
             for (int s2 = 0; s2 < cap; ++s2) {
@@ -244,7 +267,7 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
     {                                                                                               \
         TopList<C> L;                                                                               \
         L.init(m);                                                                                  \
-        tree_search(g, nodes.data(), pts.data(), q[0], q[1], q[2], r2f, L, stack);                  \
+        tree_search(g, nodes.data(), pts.data(), q[0], q[1], q[2], r2f, bound0, L, stack);                  \
         take(L.k, C);                                                                               \
     }
             switch (cap) {
@@ -261,7 +284,7 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
             TopListDyn L;
             L.k = buf.data();
             L.init(m);
-            tree_search(g, nodes.data(), pts.data(), q[0], q[1], q[2], r2f, L, stack);
+            tree_search(g, nodes.data(), pts.data(), q[0], q[1], q[2], r2f, bound0, L, stack);
             take(buf.data(), m);
         }
         std::sort(found.begin(), found.end());

@@ -71,8 +71,9 @@ def rows_as_sets(idx, cnt):
     return [frozenset(idx[i, :cnt[i]].tolist()) for i in range(len(cnt))]
 
 
-def emu_tree_search(lib, src, tgt, radius, m, leaf_cap=32, list_kind=0):
-    """The product's octree build + traversal (csrc/ppcr_tree.h) compiled for the CPU."""
+def emu_tree_search(lib, src, tgt, radius, m, leaf_cap=32, list_kind=0, bounds=None):
+    """The product's octree build + traversal (csrc/ppcr_tree.h) compiled for the CPU.  bounds: optional per-query
+    squared distance within which m targets are known to lie (the warm start of the search kernel)."""
     src = np.ascontiguousarray(src, dtype=np.float32)
     tgt = np.ascontiguousarray(tgt, dtype=np.float32)
     idx = np.full((len(src), m), -1, dtype=np.int32)
@@ -82,6 +83,8 @@ def emu_tree_search(lib, src, tgt, radius, m, leaf_cap=32, list_kind=0):
     fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
     lib.emu_tree_search.restype = C.c_int64
     lib.emu_tree_search(src.ctypes.data_as(fp), C.c_int64(len(src)), tgt.ctypes.data_as(fp), C.c_int64(len(tgt)),
-                        C.c_double(radius), C.c_int(m), C.c_int(leaf_cap), C.c_int(list_kind), idx.ctypes.data_as(ip),
+                        C.c_double(radius), C.c_int(m), C.c_int(leaf_cap), C.c_int(list_kind),
+                        None if bounds is None else np.ascontiguousarray(bounds, dtype=np.float32).ctypes.data_as(fp),
+                        idx.ctypes.data_as(ip),
                         d2.ctypes.data_as(fp), cnt.ctypes.data_as(ip), C.byref(n_nodes))
     return idx, d2, cnt, n_nodes.value

@@ -22,16 +22,18 @@ def _golden_fixture():
     return src, tgt, idx, cnt
 
 
-def test_golden_t_distribution(capi):
+@pytest.mark.parametrize("fast", [False, True])
+def test_golden_t_distribution(capi, fast):
     src, tgt, idx, cnt = _golden_fixture()
-    w, _ = capi.weights_normal_eq(src, tgt, idx, cnt, 5.0, IDENT, IDENT, dimension=1)
+    w, _ = capi.weights_normal_eq(src, tgt, idx, cnt, 5.0, IDENT, IDENT, dimension=1, fast_weights=fast)
     np.testing.assert_allclose(w[0, :3], [1 / 3] * 3, atol=1e-6)
     np.testing.assert_allclose(w[1], [0.7151351, 0.1412613, 0.0241258, 0.0047656], atol=1e-6)  # T_W:42-43
 
 
-def test_golden_gaussian(capi):
+@pytest.mark.parametrize("fast", [False, True])
+def test_golden_gaussian(capi, fast):
     src, tgt, idx, cnt = _golden_fixture()
-    w, _ = capi.weights_normal_eq(src, tgt, idx, cnt, np.inf, IDENT, IDENT, dimension=1)
+    w, _ = capi.weights_normal_eq(src, tgt, idx, cnt, np.inf, IDENT, IDENT, dimension=1, fast_weights=fast)
     np.testing.assert_allclose(w[0, :3], [1 / 3] * 3, atol=1e-6)
     np.testing.assert_allclose(w[1], [0.805153702921689, 0.179654074677018, 0.0147469044726408,
                                       0.000445317928652638], atol=1e-6)  # T_W:59-60
@@ -73,6 +75,9 @@ def test_normal_equations_match_host_logic(capi, emu, oracle, dof):
     ref, _ = emu_normal_eq(emu, src, tgt, idx, cnt, dof, pose_w, pose_e)
     scale = np.abs(ref).max()
     assert np.max(np.abs(ne - ref)) / scale < 1e-12
+    # the default float32 row arithmetic: same system to float32 rounding of the per-row sums
+    _, nf = capi.weights_normal_eq(src, tgt, idx, cnt, dof, pose_w, pose_e, want_weights=False, fast_weights=True)
+    assert np.max(np.abs(nf - ref)) / scale < 2e-6
 
 
 def test_rows_without_neighbours_contribute_nothing(capi):

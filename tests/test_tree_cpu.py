@@ -69,3 +69,19 @@ def test_edge_cases(emu, oracle):
     off = tgt.copy()
     off[:, :3] = off[:, :3] * 40 + np.array([5000.0, -3000.0, 800.0], dtype=np.float32)
     _check(emu, oracle, off[::2], off, 6.0, 7, leaf_cap=2)
+
+
+def test_warm_start_bound_does_not_change_the_result(emu, oracle):
+    """The search kernel seeds the pruning bound with (sqrt(previous m-th distance) + displacement)^2.  Any bound
+    within which m targets really lie must give the identical result; an infinite one degenerates to the radius."""
+    src, tgt, _ = synth.lidar_pair(11, 16, 500)
+    m, radius = 8, 1.5
+    oi, od, oc, _ = oracle.radius_search(src, tgt, radius, m)
+    full = oc == m
+    kth = np.where(full, od[:, m - 1], np.inf).astype(np.float32)
+    for scale in (1.0, 1.00001, 1.7):
+        bounds = np.where(full, kth * np.float32(scale), np.float32(np.inf)).astype(np.float32)
+        gi, gd, gc, _ = emu_tree_search(emu, src, tgt, radius, m, bounds=bounds)
+        assert np.array_equal(gc, oc)
+        valid = np.arange(m)[None, :] < oc[:, None]
+        assert np.array_equal(gi[valid], oi[valid])
