@@ -109,6 +109,10 @@ ppcr_status ppcr_has_converged(ppcr_handle* h, int32_t* out);
 /* transformation_history() / transformation(), prob_point_cloud_registration.h:32-40.
  * T receives up to *n_inout row-major 4x4 doubles; *n_inout returns the number of outer iterations run. */
 ppcr_status ppcr_history(ppcr_handle* h, double* T4x4_rowmajor, int32_t* n_inout);
+/* The increment of every outer iteration (registration.transformation() at :101-112, the transform both source
+ * clouds are moved by), same layout as ppcr_history.  Lets a host replay the per-iteration diagnostics of the
+ * reference (MSE w.r.t. ground truth / previous iteration, :114-129) without a device round trip per iteration. */
+ppcr_status ppcr_increment_history(ppcr_handle* h, double* T4x4_rowmajor, int32_t* n_inout);
 ppcr_status ppcr_iteration_stats(ppcr_handle* h, ppcr_iter_stats* out, int32_t* n_inout);
 
 /* Clouds as the reference holds them after the call: the (voxel-filtered, moved) source and the filtered target

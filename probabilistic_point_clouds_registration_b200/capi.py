@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(_PKG, "csrc", "libppcr_cuda.so")
 
 EXPORTED_SYMBOLS = [
     "ppcr_last_error", "ppcr_version", "ppcr_default_params", "ppcr_default_options", "ppcr_create",
-    "ppcr_create_ex", "ppcr_destroy", "ppcr_align", "ppcr_has_converged", "ppcr_history", "ppcr_iteration_stats",
+    "ppcr_create_ex", "ppcr_destroy", "ppcr_align", "ppcr_has_converged", "ppcr_history", "ppcr_increment_history",
+    "ppcr_iteration_stats",
     "ppcr_filtered_source", "ppcr_filtered_target", "ppcr_association", "ppcr_get_stage_times", "ppcr_time_kernel",
     "ppcr_voxel_filter", "ppcr_radius_search", "ppcr_weights_normal_eq", "ppcr_iteration_solve", "ppcr_transform",
     "ppcr_align_batch", "ppcr_shard_export", "ppcr_shard_connect",
@@ -113,6 +114,7 @@ def lib():
         L.ppcr_align.argtypes = [vp]
         L.ppcr_has_converged.argtypes = [vp, C.POINTER(i32)]
         L.ppcr_history.argtypes = [vp, vp, C.POINTER(i32)]
+        L.ppcr_increment_history.argtypes = [vp, vp, C.POINTER(i32)]
         L.ppcr_iteration_stats.argtypes = [vp, vp, C.POINTER(i32)]
         L.ppcr_filtered_source.argtypes = [vp, vp, C.POINTER(i64)]
         L.ppcr_filtered_target.argtypes = [vp, vp, C.POINTER(i64)]
@@ -230,6 +232,14 @@ class Registration:
         hist = np.zeros((max(n.value, 1), 16))
         cap = C.c_int32(n.value)
         _check(lib().ppcr_history(self._h, hist.ctypes.data, C.byref(cap)))
+        return hist[:n.value].reshape(n.value, 4, 4)
+
+    def increment_history(self) -> np.ndarray:
+        n = C.c_int32(0)
+        _check(lib().ppcr_increment_history(self._h, None, C.byref(n)))
+        hist = np.zeros((max(n.value, 1), 16))
+        cap = C.c_int32(n.value)
+        _check(lib().ppcr_increment_history(self._h, hist.ctypes.data, C.byref(cap)))
         return hist[:n.value].reshape(n.value, 4, 4)
 
     def transformation(self) -> np.ndarray:

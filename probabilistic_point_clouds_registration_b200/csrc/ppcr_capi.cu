@@ -513,7 +513,7 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     D.partials = P.partials.p;
     CK(cudaMemsetAsync(P.partials.p, 0, static_cast<size_t>(D.n_eval_blocks) * kNSum * sizeof(double), st));
     D.max_hist = std::max(1, prm.n_iter);
-    P.history.reserve(static_cast<size_t>(D.max_hist) * 16);
+    P.history.reserve(static_cast<size_t>(D.max_hist) * 32);  // accumulated poses, then the increments
     P.stats.reserve(D.max_hist);
     P.state.reserve(1);
     P.cfg.reserve(1);
@@ -1031,6 +1031,25 @@ ppcr_status ppcr_history(ppcr_handle* h, double* T, int32_t* n_inout)
     });
 }
 
+ppcr_status ppcr_increment_history(ppcr_handle* h, double* T, int32_t* n_inout)
+{
+    if (!h || !n_inout) return fail(PPCR_ERR_INVALID, "null argument");
+    return guarded([&] {
+        Engine& E = h->eng;
+        use_engine(E);
+        PairState s = download_state(E, 0);
+        const int max_hist = E.pairs[0].dev.max_hist;
+        const int n = std::min(s.current_iteration, max_hist);
+        const int take = std::min(n, *n_inout);
+        if (T && take > 0) {
+            CK(cudaMemcpyAsync(T, E.pairs[0].history.p + static_cast<size_t>(max_hist) * 16,
+                               static_cast<size_t>(take) * 16 * sizeof(double), cudaMemcpyDeviceToHost, E.stream));
+            CK(cudaStreamSynchronize(E.stream));
+        }
+        *n_inout = n;
+    });
+}
+
 ppcr_status ppcr_iteration_stats(ppcr_handle* h, ppcr_iter_stats* out, int32_t* n_inout)
 {
     if (!h || !n_inout) return fail(PPCR_ERR_INVALID, "null argument");
@@ -1279,18 +1298,7 @@ ppcr_status ppcr_weights_normal_eq(const float* src, int64_t n_src, const float*
         pose7_to_state(pose_e, &s.pose_e);
         pose7_to_state(pose_w, &s.pose_w);
         CK(cudaMemcpyAsync(E.pairs[0].state.p, &s, sizeof(s), cudaMemcpyHostToDevice, E.stream));
-        launch_evalctl(E, false);  // its controller tail runs on a scratch state; only the partial sums are used
-        CK(cudaGetLastError());
-        double S[kNSum];
-        reduce_partials_like_controller(E, 0, S);
-        double H[kNP * kNP], g[kNP], cost;
-        expand_moments(S, pose_e, H, g, &cost);  // the controller's expansion, same source
-        int o = 0;
-        for (int r = 0; r < kNP; ++r)
-            for (int c = r; c < kNP; ++c) normal_eq[o++] = H[r * kNP + c];
-        for (int r = 0; r < kNP; ++r) normal_eq[o++] = g[r];
-        normal_eq[o] = cost;
-        if (weights) {
+        if (weights) {  // before the evaluation: its controller tail advances the scratch state
             const PairDev& D = E.pairs[0].dev;
             DevBuf<double> dw;
             const size_t plane = static_cast<size_t>(D.m) * D.n_pad;
@@ -1310,6 +1318,17 @@ ppcr_status ppcr_weights_normal_eq(const float* src, int64_t n_src, const float*
             }
             dw.release();
         }
+        launch_evalctl(E, false);  // its controller tail runs on a scratch state; only the partial sums are used
+        CK(cudaGetLastError());
+        double S[kNSum];
+        reduce_partials_like_controller(E, 0, S);
+        double H[kNP * kNP], g[kNP], cost;
+        expand_moments(S, pose_e, H, g, &cost);  // the controller's expansion, same source
+        int o = 0;
+        for (int r = 0; r < kNP; ++r)
+            for (int c = r; c < kNP; ++c) normal_eq[o++] = H[r * kNP + c];
+        for (int r = 0; r < kNP; ++r) normal_eq[o++] = g[r];
+        normal_eq[o] = cost;
     });
 }
 

@@ -456,7 +456,10 @@ PPCR_HD void outer_finish(PairState* s, const Config* cfg, double* history, Iter
     }
     s->cost_drop = (s->initial_cost - s->min_iter_cost) / s->initial_cost;  // NaN for 0/0, like the reference
     if (s->current_iteration < max_hist) {
-        for (int k = 0; k < 16; ++k) history[16 * s->current_iteration + k] = s->T_total[k];
+        for (int k = 0; k < 16; ++k) {
+            history[16 * s->current_iteration + k] = s->T_total[k];         // accumulated pose, registration.cc:101-107
+            history[16 * (max_hist + s->current_iteration) + k] = s->dT[k]; // the increment the clouds are moved by, :110-112
+        }
         IterStats* st = stats + s->current_iteration;
         st->initial_cost = s->initial_cost;
         st->final_cost = s->min_iter_cost;

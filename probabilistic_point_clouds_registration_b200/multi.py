@@ -1,0 +1,70 @@
+"""One-process-per-GPU helpers over the C ABI: the two ways the path partitions.
+
+  * batch of independent scan pairs  -> pairs dealt to ranks, no data-path collective, results gathered at the end
+  * one large pair                   -> source points split into contiguous slices, the target replicated; the only
+                                        exchange is the 24-moment vector (+ association size) per LM iteration, which the
+                                        eval kernel's controller block writes straight into the peers' mailboxes over
+                                        NVLink (ppcr_shard_export / ppcr_shard_connect); torch.distributed only carries
+                                        the 64-byte IPC tokens once, at set-up.
+
+torch.distributed is plumbing here (rendezvous, token exchange, result gather); none of it is on the per-iteration path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+def slice_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced split of n items: the first n % world ranks get one extra."""
+    base, extra = divmod(int(n), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def deal_pairs(n_pairs: int, rank: int, world: int) -> list[int]:
+    """Pairs of a batch owned by `rank` (contiguous blocks, same rule as slice_bounds)."""
+    lo, hi = slice_bounds(n_pairs, rank, world)
+    return list(range(lo, hi))
+
+
+def gather_tokens(token: bytes, dist=None) -> bytes:
+    """All-gathers the 64-byte mailbox tokens of every rank (rank order).  Works on any backend (gloo / nccl)."""
+    import torch
+    if dist is None:
+        import torch.distributed as dist
+    world = dist.get_world_size()
+    assert len(token) == capi.SHARD_TOKEN_BYTES
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    mine = torch.frombuffer(bytearray(token), dtype=torch.uint8).to(dev)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine)
+    return b"".join(bytes(t.cpu().numpy().tobytes()) for t in out)
+
+
+class ShardedRegistration(capi.Registration):
+    """One rank's share of a single large pair: its slice of the source, the whole target."""
+
+    def __init__(self, source_slice, target, params, rank: int, world: int, options=None, dist=None, **kw):
+        super().__init__(source_slice, target, params, options, **kw)
+        self.rank, self.world = rank, world
+        if world > 1:
+            token = (C.c_uint8 * capi.SHARD_TOKEN_BYTES)()
+            capi._check(capi.lib().ppcr_shard_export(self._h, rank, world, token))
+            tokens = gather_tokens(bytes(token), dist)
+            buf = (C.c_uint8 * len(tokens)).from_buffer_copy(tokens)
+            capi._check(capi.lib().ppcr_shard_connect(self._h, buf))
+
+
+def gather_results(local: np.ndarray, dist=None) -> list[np.ndarray]:
+    """Gathers per-rank result arrays (e.g. the [n_local,4,4] poses of a batch) on every rank, in rank order."""
+    import torch
+    if dist is None:
+        import torch.distributed as dist
+    world = dist.get_world_size()
+    objs = [None] * world
+    dist.all_gather_object(objs, np.ascontiguousarray(local))
+    return objs

@@ -133,7 +133,7 @@ int emu_align(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, int64
     align_begin(&st, &cfg);
     const int m = static_cast<int>(std::min<int64_t>(max_neighbours, std::max<int64_t>(n_tgt, 1)));
     std::vector<int> idx, cnt;
-    std::vector<double> hist(static_cast<size_t>(std::max(1, max_hist)) * 16);
+    std::vector<double> hist(static_cast<size_t>(std::max(1, max_hist)) * 32);  // poses, then increments
     std::vector<IterStats> stv(static_cast<size_t>(std::max(1, max_hist)));
     double S[kNSum];
     long long guard = 0;
