@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "csrc", "libppcr_cuda.so")
+LIB_PATH = os.environ.get("PPCR_LIB_PATH") or os.path.join(_PKG, "csrc", "libppcr_cuda.so")  # override: tuning builds
 
 EXPORTED_SYMBOLS = [
     "ppcr_last_error", "ppcr_version", "ppcr_default_params", "ppcr_default_options", "ppcr_create",

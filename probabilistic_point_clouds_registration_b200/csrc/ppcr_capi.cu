@@ -121,13 +121,14 @@ static inline void note_launches(int n) { *g_launch_sink += n; }
 
 struct Pair {
     DevBuf<float4> src, tgt_raw, tgt_sorted, tmp_cloud;
-    DevBuf<int> nbr_idx, nbr_cnt, scan_sums;
+    DevBuf<int> nbr_cnt, scan_sums;
+    DevBuf<float4> nbr;
     DevBuf<TreeNode> nodes;
     DevBuf<TreeCounters> tree_counters;
     DevBuf<unsigned long long> sort_keys[2];
     DevBuf<unsigned> sort_vals[2];
     DevBuf<unsigned char> sort_tmp;
-    DevBuf<float> nbr_x, nbr_y, nbr_z, nbr_d2, nbr_kth;
+    DevBuf<float> nbr_d2, nbr_kth;
     DevBuf<double> partials, history, mailbox;
     DevBuf<PairState> state;
     DevBuf<Config> cfg;
@@ -142,8 +143,8 @@ struct Pair {
     {
         src.release(); tgt_raw.release(); tgt_sorted.release(); tmp_cloud.release();
         nodes.release(); tree_counters.release(); sort_keys[0].release(); sort_keys[1].release();
-        sort_vals[0].release(); sort_vals[1].release(); sort_tmp.release(); nbr_idx.release(); nbr_cnt.release();
-        scan_sums.release(); nbr_x.release(); nbr_y.release(); nbr_z.release(); nbr_d2.release(); nbr_kth.release();
+        sort_vals[0].release(); sort_vals[1].release(); sort_tmp.release(); nbr.release(); nbr_cnt.release();
+        scan_sums.release(); nbr_d2.release(); nbr_kth.release();
         partials.release(); history.release(); mailbox.release(); state.release(); cfg.release(); stats.release();
         scratch_u.release(); scratch_ull.release();
     }
@@ -164,7 +165,7 @@ struct Engine {
     DevBuf<PairDev> d_pairs;
     DevBuf<LoopCtl> d_loop;
     int* h_active = nullptr;  // pinned
-    int eval_blocks_per_sm = 2, search_blocks_per_sm = 8;
+    int eval_blocks_per_sm = PPCR_EVAL_MIN_BLOCKS, search_blocks_per_sm = 8;
     int list_cap = 0;  // register capacity of the search kernel's top-m list; 0 = local-memory list (m > 32)
     // launch geometry (capacity based, so a captured graph stays valid while the slots are refilled)
     int max_tiles = 1, max_eval_blocks = 1, max_tr_blocks = 1;
@@ -498,13 +499,13 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     sort_source(E, P);
     D.src = P.src.p;
     const size_t plane = static_cast<size_t>(D.m) * D.n_pad;
-    P.nbr_x.reserve(plane); P.nbr_y.reserve(plane); P.nbr_z.reserve(plane); P.nbr_idx.reserve(plane);
+    P.nbr.reserve(plane);
     P.nbr_cnt.reserve(D.n_pad);
     P.nbr_kth.reserve(D.n_pad);
     D.nbr_kth = P.nbr_kth.p;
     CK(cudaMemsetAsync(P.nbr_kth.p, 0x7f, static_cast<size_t>(D.n_pad) * sizeof(float), st));  // "nothing known yet"
     if (P.want_d2) P.nbr_d2.reserve(plane);
-    D.nbr_x = P.nbr_x.p; D.nbr_y = P.nbr_y.p; D.nbr_z = P.nbr_z.p; D.nbr_idx = P.nbr_idx.p;
+    D.nbr = P.nbr.p;
     D.nbr_d2 = P.want_d2 ? P.nbr_d2.p : nullptr;
     D.nbr_cnt = P.nbr_cnt.p;
     CK(cudaMemsetAsync(P.nbr_cnt.p, 0, static_cast<size_t>(D.n_pad) * sizeof(int), st));
@@ -842,9 +843,10 @@ static void download_association(Engine& E, int p, int32_t* idx, float* d2, int3
     Pair& P = E.pairs[p];
     const PairDev& D = P.dev;
     if (n_src != D.n_src) throw StatusError{PPCR_ERR_INVALID, "n_src does not match the handle's (filtered) source size"};
-    std::vector<int> h_idx(static_cast<size_t>(D.m) * D.n_pad), h_cnt(D.n_pad);
+    std::vector<float4> h_rec(static_cast<size_t>(D.m) * D.n_pad);
+    std::vector<int> h_idx(h_rec.size()), h_cnt(D.n_pad);
     std::vector<float> h_d2;
-    CK(cudaMemcpyAsync(h_idx.data(), D.nbr_idx, h_idx.size() * sizeof(int), cudaMemcpyDeviceToHost, E.stream));
+    CK(cudaMemcpyAsync(h_rec.data(), D.nbr, h_rec.size() * sizeof(float4), cudaMemcpyDeviceToHost, E.stream));
     CK(cudaMemcpyAsync(h_cnt.data(), D.nbr_cnt, h_cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, E.stream));
     if (d2) {
         if (!D.nbr_d2) throw StatusError{PPCR_ERR_INVALID, "distances were not recorded"};
@@ -852,6 +854,7 @@ static void download_association(Engine& E, int p, int32_t* idx, float* d2, int3
         CK(cudaMemcpyAsync(h_d2.data(), D.nbr_d2, h_d2.size() * sizeof(float), cudaMemcpyDeviceToHost, E.stream));
     }
     CK(cudaStreamSynchronize(E.stream));
+    for (size_t k = 0; k < h_rec.size(); ++k) memcpy(&h_idx[k], &h_rec[k].w, 4);
     const std::vector<int> order = source_order(E, p);
     for (int64_t j = 0; j < n_src; ++j) {  // device row j is the caller's point order[j]
         const int64_t i = order[j];
@@ -872,8 +875,8 @@ static void upload_association(Engine& E, int p, const float* tgt_xyzw, int64_t 
     Pair& P = E.pairs[p];
     const PairDev& D = P.dev;
     const size_t plane = static_cast<size_t>(D.m) * D.n_pad;
-    std::vector<float> hx(plane, 0.f), hy(plane, 0.f), hz(plane, 0.f);
-    std::vector<int> hi(plane, -1), hc(D.n_pad, 0);
+    std::vector<float4> hr(plane, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<int> hc(D.n_pad, 0);
     int64_t K = 0;
     const std::vector<int> order = source_order(E, p);
     for (int64_t row = 0; row < D.n_src; ++row) {  // device row `row` is the caller's point order[row]
@@ -886,16 +889,13 @@ static void upload_association(Engine& E, int p, const float* tgt_xyzw, int64_t 
             const int j = idx[i * max_nn + k];
             if (j < 0 || j >= n_tgt) throw StatusError{PPCR_ERR_INVALID, "association index out of range"};
             const size_t o = static_cast<size_t>(k) * D.n_pad + row;
-            hx[o] = tgt_xyzw[4 * static_cast<size_t>(j)];
-            hy[o] = tgt_xyzw[4 * static_cast<size_t>(j) + 1];
-            hz[o] = tgt_xyzw[4 * static_cast<size_t>(j) + 2];
-            hi[o] = j;
+            hr[o].x = tgt_xyzw[4 * static_cast<size_t>(j)];
+            hr[o].y = tgt_xyzw[4 * static_cast<size_t>(j) + 1];
+            hr[o].z = tgt_xyzw[4 * static_cast<size_t>(j) + 2];
+            memcpy(&hr[o].w, &j, 4);
         }
     }
-    CK(cudaMemcpyAsync(D.nbr_x, hx.data(), plane * sizeof(float), cudaMemcpyHostToDevice, E.stream));
-    CK(cudaMemcpyAsync(D.nbr_y, hy.data(), plane * sizeof(float), cudaMemcpyHostToDevice, E.stream));
-    CK(cudaMemcpyAsync(D.nbr_z, hz.data(), plane * sizeof(float), cudaMemcpyHostToDevice, E.stream));
-    CK(cudaMemcpyAsync(D.nbr_idx, hi.data(), plane * sizeof(int), cudaMemcpyHostToDevice, E.stream));
+    CK(cudaMemcpyAsync(D.nbr, hr.data(), plane * sizeof(float4), cudaMemcpyHostToDevice, E.stream));
     CK(cudaMemcpyAsync(D.nbr_cnt, hc.data(), hc.size() * sizeof(int), cudaMemcpyHostToDevice, E.stream));
     PairState s = download_state(E, p);
     s.K = K;

@@ -23,8 +23,12 @@ struct WeightCfg {
     double inv_dof;    // 1 / v is NOT used for the log argument (the reference divides); kept for the fp32 path
     int32_t is_normal; // v == +inf: Gaussian model, w = softmax(-r^2/2)
     int32_t pad;
-    // float32 copies for the fast path
+    // float32 copies for the fast path: u = s^h with s = 1/(1 + r^2/v), h = (v+d)/2; expected weight = f_c * s
     float f_dof, f_t_exponent, f_dof_plus_d, f_inv_dof;
+    float f_c;         // (v + d) / v
+    float f_h;         // (v + d) / 2
+    int32_t pow_int;   // floor(h) when 2h is an integer <= 31 (h by repeated multiplication, +sqrt for the half), else -1
+    int32_t pow_half;  // 2h odd
 };
 
 PPCR_HD WeightCfg make_weight_cfg(double dof, int dimension = 3)
@@ -41,6 +45,18 @@ PPCR_HD WeightCfg make_weight_cfg(double dof, int dimension = 3)
     w.f_t_exponent = static_cast<float>(w.t_exponent);
     w.f_dof_plus_d = w.is_normal ? 0.f : static_cast<float>(w.dof_plus_d);
     w.f_inv_dof = static_cast<float>(w.inv_dof);
+    w.f_c = w.is_normal ? 0.f : static_cast<float>(w.dof_plus_d / dof);
+    w.f_h = w.is_normal ? 0.f : static_cast<float>(w.dof_plus_d / 2.0);
+    w.pow_int = -1;
+    w.pow_half = 0;
+    if (!w.is_normal) {
+        const double twice = w.dof_plus_d;  // 2h
+        const long long t = static_cast<long long>(twice);
+        if (static_cast<double>(t) == twice && t >= 0 && t <= 31) {
+            w.pow_int = static_cast<int32_t>(t / 2);
+            w.pow_half = static_cast<int32_t>(t & 1);
+        }
+    }
     return w;
 }
 
@@ -117,7 +133,7 @@ PPCR_HD void row_add(RowAcc* a, const WeightCfg& wc, double yx, double yy, doubl
 // fold a finished row into the 24 moments; (sx,sy,sz) is the source point in double
 PPCR_HD void row_end(const RowAcc* a, double sx, double sy, double sz, double* acc)
 {
-    const double inv = 1.0 / a->a0;
+    const double inv = a->a0 > 0.0 ? 1.0 / a->a0 : 0.0;  // every posterior underflowed: the row carries no weight
     const double W = a->a1 * inv;
     const double rho[3] = {a->ar[0] * inv, a->ar[1] * inv, a->ar[2] * inv};
     acc[M_S0] += W;
@@ -190,6 +206,36 @@ PPCR_HD float residual_hl(float y, float hi, float lo)
 #endif
 }
 
+PPCR_HD float f_rcp(float x)
+{
+#if defined(__CUDA_ARCH__)
+    return __frcp_rn(x);
+#else
+    return 1.0f / x;
+#endif
+}
+
+// t-distribution: unnormalised posterior u = (1 + r^2/v)^(-(v+d)/2) and u * expected weight, without log / exp.
+// u <= 1 and the nearest neighbour keeps the row sum away from zero, so the max-subtraction of the reference's
+// log-sum-exp (which only guards against overflow / total underflow) has nothing to do here.
+PPCR_HD void t_terms(const WeightCfg& wc, float r2w, float* u_out, float* ue_out)
+{
+    const float s = f_rcp(r2w * wc.f_inv_dof + 1.0f);
+    float u;
+    if (wc.pow_int >= 0) {
+        const float s2 = s * s, s4 = s2 * s2, s8 = s4 * s4;
+        u = (wc.pow_int & 1) ? s : 1.0f;
+        if (wc.pow_int & 2) u *= s2;
+        if (wc.pow_int & 4) u *= s4;
+        if (wc.pow_int & 8) u *= s8;
+        if (wc.pow_half) u *= sqrtf(s);
+    } else {
+        u = exp2f(wc.f_h * log2f(s));
+    }
+    *u_out = u;
+    *ue_out = u * (wc.f_c * s);
+}
+
 // same_pose: pose_w == pose_e (first evaluation of an outer iteration), the weight residual is the cost residual
 PPCR_HD void rowf_add(RowAccF* a, const WeightCfg& wc, float yx, float yy, float yz, const PointHL& pe, const PointHL& pw,
                       bool same_pose)
@@ -205,26 +251,24 @@ PPCR_HD void rowf_add(RowAccF* a, const WeightCfg& wc, float yx, float yy, float
         const float wz = residual_hl(yz, pw.hi[2], pw.lo[2]);
         r2w = wx * wx + wy * wy + wz * wz;
     }
-    float lp, ex;
+    float p, pw_;
     if (wc.is_normal) {
-        lp = -0.5f * r2w;
-        ex = 1.f;
+        const float lp = -0.5f * r2w;
+        if (lp > a->m) {  // new row maximum: rescale what has been accumulated so far
+            const float sc = expf(a->m - lp);
+            a->a0 *= sc;
+            a->a1 *= sc;
+            a->ar[0] *= sc;
+            a->ar[1] *= sc;
+            a->ar[2] *= sc;
+            a->ac *= sc;
+            a->m = lp;
+        }
+        p = expf(lp - a->m);
+        pw_ = p;
     } else {
-        lp = wc.f_t_exponent * log1pf(r2w * wc.f_inv_dof);
-        ex = wc.f_dof_plus_d / (wc.f_dof + r2w);
+        t_terms(wc, r2w, &p, &pw_);
     }
-    if (lp > a->m) {  // new row maximum: rescale what has been accumulated so far
-        const float sc = expf(a->m - lp);
-        a->a0 *= sc;
-        a->a1 *= sc;
-        a->ar[0] *= sc;
-        a->ar[1] *= sc;
-        a->ar[2] *= sc;
-        a->ac *= sc;
-        a->m = lp;
-    }
-    const float p = expf(lp - a->m);
-    const float pw_ = p * ex;
     a->a0 += p;
     a->a1 += pw_;
     a->ar[0] += pw_ * rx;
@@ -252,15 +296,10 @@ PPCR_HD float rowf_finished_weight(const RowAccF* a, const WeightCfg& wc, float 
     const float wy = residual_hl(yy, pw.hi[1], pw.lo[1]);
     const float wz = residual_hl(yz, pw.hi[2], pw.lo[2]);
     const float r2w = wx * wx + wy * wy + wz * wz;
-    float lp, ex;
-    if (wc.is_normal) {
-        lp = -0.5f * r2w;
-        ex = 1.f;
-    } else {
-        lp = wc.f_t_exponent * log1pf(r2w * wc.f_inv_dof);
-        ex = wc.f_dof_plus_d / (wc.f_dof + r2w);
-    }
-    return expf(lp - a->m) / a->a0 * ex;
+    if (wc.is_normal) return expf(-0.5f * r2w - a->m) / a->a0;
+    float u, ue;
+    t_terms(wc, r2w, &u, &ue);
+    return ue / a->a0;
 }
 
 PPCR_HD void apply_pose(const Pose& p, double sx, double sy, double sz, double* out)

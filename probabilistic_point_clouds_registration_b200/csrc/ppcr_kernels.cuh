@@ -17,8 +17,8 @@
 //   nodes       TreeNode[]         linear octree over tgt_sorted (ppcr_tree.h), 32-byte records, 8 children adjacent
 //   src         float4[n_src]      the moving source cloud (filtered), Morton-sorted once so that the 32 queries of a
 //                                  warp walk the same part of the tree; .w = original index
-//   nbr_x/y/z   float[m][n_pad]    slot-major neighbour coordinates: entry (k, i) is the k-th nearest target of
-//   nbr_idx     int[m][n_pad]      source i, so one warp reads 32 consecutive floats per slot (fully coalesced)
+//   nbr         float4[m][n_pad]   slot-major neighbour records (x, y, z, original index): entry (k, i) is the k-th
+//                                  nearest target of source i, so one warp reads 512 contiguous bytes per slot
 //   nbr_cnt     int[n_pad]
 //   partials    double[blocks][24] per-block moment sums, reduced in a fixed order by the controller
 // No tensor cores: nothing on this path is a dense contraction; the kernels are HBM/L2-bound streaming passes.
@@ -36,6 +36,9 @@ namespace ppcr {
 
 constexpr int kSearchThreads = 128;  // one query per thread
 constexpr int kEvalThreads = 256;
+#ifndef PPCR_EVAL_MIN_BLOCKS
+#define PPCR_EVAL_MIN_BLOCKS 2  // resident blocks per SM the register allocation of k_evalctl is held to
+#endif
 constexpr int kMailDoubles = 32;  // 24 moments + K + sequence stamp, padded
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -50,10 +53,7 @@ struct PairDev {
     int n_pad;
     int m;          // result capacity = min(max_neighbours, n_tgt)
     float r2f;      // float(radius * radius): strict membership bound (FLANN)
-    float* nbr_x;
-    float* nbr_y;
-    float* nbr_z;
-    int* nbr_idx;   // original target index
+    float4* nbr;    // [m][n_pad] slot-major neighbour records: x, y, z of the target point, .w = its original index
     float* nbr_d2;  // optional (stage API only), may be null
     float* nbr_kth; // d2 of the m-th neighbour found by the last search (+inf when fewer were found): warm start
     int* nbr_cnt;
@@ -312,10 +312,7 @@ __device__ __forceinline__ void search_store(const PairDev& P, int i, int e, uns
     const int idx = key_index(key);
     const float4 p = __ldg(P.tgt_raw + idx);
     const size_t o = static_cast<size_t>(e) * P.n_pad + i;
-    P.nbr_x[o] = p.x;
-    P.nbr_y[o] = p.y;
-    P.nbr_z[o] = p.z;
-    P.nbr_idx[o] = idx;
+    P.nbr[o] = make_float4(p.x, p.y, p.z, __int_as_float(idx));
     if (P.nbr_d2) P.nbr_d2[o] = key_d2(key);
 }
 
@@ -420,18 +417,22 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p)
 
 // The scalar LM / outer-loop state machine (ppcr_lm.h), one thread.  Kept out of line so that its register appetite
 // (a 7x7 Cholesky and the moment expansion, all float64) does not set the register count of the streaming part.
-__device__ __noinline__ void run_controller(const PairDev& P, const double* sums, int max_ticks)
+// It works on shared-memory copies of the pair state and configuration: the state machine is a long chain of
+// dependent reads and writes of those fields, and every one of them would otherwise be a global-memory round trip.
+__device__ __noinline__ void run_controller(PairState* st, const Config* cfg, const double* sums, double* history,
+                                            IterStats* stats, int max_hist, int max_ticks)
 {
-    PairState* st = P.state;
     double S[kNSum];
     for (int k = 0; k < kNSum; ++k) S[k] = sums[k];
     st->evals += 1;
-    controller_tick(st, P.cfg, S, P.history, P.stats, P.max_hist);
+    controller_tick(st, cfg, S, history, stats, max_hist);
     if (st->ticks >= max_ticks && st->phase != PH_DONE) {  // never spin forever on the device
         st->error = 1;
         st->phase = PH_DONE;
     }
 }
+
+static_assert(sizeof(PairState) % 8 == 0 && sizeof(Config) % 8 == 0, "copied as 64-bit words");
 
 struct LoopCtl {   // one per engine
     int active;      // any pair still running (read back by the host-stepped driver)
@@ -442,7 +443,7 @@ struct LoopCtl {   // one per engine
 // publishes its partial sums last -- the fixed-order reduction, the cross-rank exchange (sharded mode), the LM /
 // outer-loop controller and the loop condition of the tick graph.  One launch per LM iteration.
 template <bool kFast>
-__global__ void __launch_bounds__(kEvalThreads, 2) k_evalctl(const PairDev* __restrict__ pairs, int n_pairs,
+__global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(const PairDev* __restrict__ pairs, int n_pairs,
                                                           LoopCtl* __restrict__ loop, cudaGraphConditionalHandle cond,
                                                           int use_cond, int max_ticks)
 {
@@ -492,21 +493,17 @@ __global__ void __launch_bounds__(kEvalThreads, 2) k_evalctl(const PairDev* __re
             }
             RowAccF row;
             rowf_begin(&row);
-            constexpr int kU = 8;  // loads of kU correspondences are issued before their arithmetic
+            constexpr int kU = 5;  // records of kU correspondences are in flight before their arithmetic
+            const float4* rec = P.nbr + i;
             for (int k0 = 0; k0 < cnt; k0 += kU) {
-                float yx[kU], yy[kU], yz[kU];
-#pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    if (k0 + u < cnt) {
-                        const size_t o = static_cast<size_t>(k0 + u) * n_pad + i;
-                        yx[u] = __ldg(P.nbr_x + o);
-                        yy[u] = __ldg(P.nbr_y + o);
-                        yz[u] = __ldg(P.nbr_z + o);
-                    }
-                }
+                float4 y[kU];
 #pragma unroll
                 for (int u = 0; u < kU; ++u)
-                    if (k0 + u < cnt) rowf_add(&row, wc, yx[u], yy[u], yz[u], he, hw, same);
+                    if (k0 + u < cnt) y[u] = __ldg(rec + static_cast<size_t>(u) * n_pad);
+                rec += static_cast<size_t>(kU) * n_pad;
+#pragma unroll
+                for (int u = 0; u < kU; ++u)
+                    if (k0 + u < cnt) rowf_add(&row, wc, y[u].x, y[u].y, y[u].z, he, hw, same);
             }
             rowf_end(&row, sx, sy, sz, acc);
         }
@@ -523,8 +520,8 @@ __global__ void __launch_bounds__(kEvalThreads, 2) k_evalctl(const PairDev* __re
             row_begin(&row);
             for (int k = 0; k < cnt; ++k) {
                 const size_t o = static_cast<size_t>(k) * n_pad + i;
-                const float yx = __ldg(P.nbr_x + o), yy = __ldg(P.nbr_y + o), yz = __ldg(P.nbr_z + o);
-                row_add<false>(&row, wc, yx, yy, yz, pte, ptw);
+                const float4 y = __ldg(P.nbr + o);
+                row_add<false>(&row, wc, y.x, y.y, y.z, pte, ptw);
             }
             row_end(&row, sx, sy, sz, acc);
         }
@@ -639,7 +636,22 @@ __global__ void __launch_bounds__(kEvalThreads, 2) k_evalctl(const PairDev* __re
         __syncthreads();
     }
 
-    if (threadIdx.x == 0 && st->phase != PH_DONE) run_controller(P, s_sum, max_ticks);
+    {
+        __shared__ PairState s_state;
+        __shared__ Config s_cfg;
+        constexpr int kStateWords = sizeof(PairState) / 8, kCfgWords = sizeof(Config) / 8;
+        for (int k = threadIdx.x; k < kStateWords; k += kEvalThreads)
+            reinterpret_cast<unsigned long long*>(&s_state)[k] = __ldcg(reinterpret_cast<const unsigned long long*>(st) + k);
+        for (int k = threadIdx.x; k < kCfgWords; k += kEvalThreads)
+            reinterpret_cast<unsigned long long*>(&s_cfg)[k] = reinterpret_cast<const unsigned long long*>(P.cfg)[k];
+        __syncthreads();
+        if (threadIdx.x == 0 && s_state.phase != PH_DONE)
+            run_controller(&s_state, &s_cfg, s_sum, P.history, P.stats, P.max_hist, max_ticks);
+        __syncthreads();
+        for (int k = threadIdx.x; k < kStateWords; k += kEvalThreads)
+            reinterpret_cast<unsigned long long*>(st)[k] = reinterpret_cast<const unsigned long long*>(&s_state)[k];
+        __syncthreads();
+    }
     } else if (blockIdx.x != 0) {
         return;  // a finished pair: one block keeps the tick protocol going
     }
@@ -678,22 +690,22 @@ __global__ void k_dump_weights(const PairDev* __restrict__ pairs, double* __rest
         rowf_begin(&row);
         for (int k = 0; k < cnt; ++k) {
             const size_t o = static_cast<size_t>(k) * n_pad + i;
-            rowf_add(&row, P.wcfg, P.nbr_x[o], P.nbr_y[o], P.nbr_z[o], hw, hw, true);
+            rowf_add(&row, P.wcfg, P.nbr[o].x, P.nbr[o].y, P.nbr[o].z, hw, hw, true);
         }
         for (int k = 0; k < cnt; ++k) {
             const size_t o = static_cast<size_t>(k) * n_pad + i;
-            out[o] = rowf_finished_weight(&row, P.wcfg, P.nbr_x[o], P.nbr_y[o], P.nbr_z[o], hw);
+            out[o] = rowf_finished_weight(&row, P.wcfg, P.nbr[o].x, P.nbr[o].y, P.nbr[o].z, hw);
         }
     } else {
         RowAcc row;
         row_begin(&row);
         for (int k = 0; k < cnt; ++k) {
             const size_t o = static_cast<size_t>(k) * n_pad + i;
-            row_add<false>(&row, P.wcfg, P.nbr_x[o], P.nbr_y[o], P.nbr_z[o], ptw, ptw);
+            row_add<false>(&row, P.wcfg, P.nbr[o].x, P.nbr[o].y, P.nbr[o].z, ptw, ptw);
         }
         for (int k = 0; k < cnt; ++k) {
             const size_t o = static_cast<size_t>(k) * n_pad + i;
-            out[o] = finished_weight<false>(&row, P.wcfg, P.nbr_x[o], P.nbr_y[o], P.nbr_z[o], ptw);
+            out[o] = finished_weight<false>(&row, P.wcfg, P.nbr[o].x, P.nbr[o].y, P.nbr[o].z, ptw);
         }
     }
 }

@@ -19,7 +19,8 @@ src, tgt = bench.make_pair(workload, 0)
 params = capi.make_params(n_iter=n_iter, **bench.WORKLOADS[workload]["params"])
 names = {0: "search (cold bound)", 4: "search (moved + warm bound)", 1: "weights+normal eq+controller", 2: "cloud move",
          3: "target tree build"}
-with capi.Registration(src, tgt, params) as reg:
+leaf = int(os.environ.get("PPCR_LEAF", "0"))
+with capi.Registration(src, tgt, params, capi.make_options(leaf_capacity=leaf)) as reg:
     reg.align()
     print(f"{workload}: {len(reg.iteration_stats())} outer iterations")
     for which in (0, 4, 1, 2, 3):
