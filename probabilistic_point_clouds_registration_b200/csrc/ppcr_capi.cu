@@ -1322,13 +1322,13 @@ ppcr_status ppcr_weights_normal_eq(const float* src, int64_t n_src, const float*
         CK(cudaGetLastError());
         double S[kNSum];
         reduce_partials_like_controller(E, 0, S);
-        double H[kNP * kNP], g[kNP], cost;
-        expand_moments(S, pose_e, H, g, &cost);  // the controller's expansion, same source
+        Expanded ev;
+        expand_moments(S, pose_e, &ev);  // the controller's expansion, same source
         int o = 0;
         for (int r = 0; r < kNP; ++r)
-            for (int c = r; c < kNP; ++c) normal_eq[o++] = H[r * kNP + c];
-        for (int r = 0; r < kNP; ++r) normal_eq[o++] = g[r];
-        normal_eq[o] = cost;
+            for (int c = r; c < kNP; ++c) normal_eq[o++] = ev.H[r * kNP + c];
+        for (int r = 0; r < kNP; ++r) normal_eq[o++] = ev.g[r];
+        normal_eq[o] = ev.cost;
     });
 }
 

@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(const PairDev* __rest
     if (threadIdx.x < 12) s_T[threadIdx.x] = st->dT[threadIdx.x];
     const int m = P.m;
     const int n_chunks = (P.n_src + kSearchChunk - 1) / kSearchChunk;
-    int stack[kTreeStack];
+    int stack[2 * kTreeStack];
     int cnt_total = 0;
     for (;;) {
         __syncthreads();
@@ -419,16 +419,102 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p)
 // (a 7x7 Cholesky and the moment expansion, all float64) does not set the register count of the streaming part.
 // It works on shared-memory copies of the pair state and configuration: the state machine is a long chain of
 // dependent reads and writes of those fields, and every one of them would otherwise be a global-memory round trip.
-__device__ __noinline__ void run_controller(PairState* st, const Config* cfg, const double* sums, double* history,
-                                            IterStats* stats, int max_hist, int max_ticks)
+//
+// Cooperative form of ppcr_lm.h::controller_tick for the first warp of the controller block: lane 0 runs the scalar
+// decisions, the 7x7 Cholesky factorisation runs one row per lane (same operation order per entry as the serial
+// solve_damped, hence the same bits).  The moment expansion has already been done by the whole block (ev).
+struct CtrlShared {
+    Expanded ev;
+    double N[kExpandN];
+    QuatFrame frame;
+    double L[kNP][kNP];
+    double D[kNP], y[kNP];
+    int flag;
+};
+
+__device__ __noinline__ int ctrl_begin(PairState* st, const Config* cfg, const Expanded* ev)
 {
-    double S[kNSum];
-    for (int k = 0; k < kNSum; ++k) S[k] = sums[k];
     st->evals += 1;
-    controller_tick(st, cfg, S, history, stats, max_hist);
-    if (st->ticks >= max_ticks && st->phase != PH_DONE) {  // never spin forever on the device
-        st->error = 1;
-        st->phase = PH_DONE;
+    return controller_begin(st, cfg, *ev) ? 1 : 0;
+}
+__device__ __noinline__ int ctrl_prepare(PairState* st, const Config* cfg, double* D) { return step_prepare(st, cfg, D) ? 1 : 0; }
+__device__ __noinline__ int ctrl_complete(PairState* st, const Config* cfg, int valid, const double* y)
+{
+    return step_complete(st, cfg, valid != 0, y);
+}
+__device__ __noinline__ void ctrl_finish(PairState* st, const Config* cfg, double* history, IterStats* stats, int max_hist)
+{
+    outer_finish(st, cfg, history, stats, max_hist);
+}
+
+// (Hs + diag(D)^2) y = gs, rows of the factor spread over lanes 0..6; returns validity in every lane
+__device__ __forceinline__ int warp_solve_damped(const PairState* st, CtrlShared* sh, int lane)
+{
+    if (lane < kNP)
+        for (int c = 0; c < kNP; ++c) sh->L[lane][c] = st->Hs[lane * kNP + c] + (lane == c ? sh->D[lane] * sh->D[lane] : 0.0);
+    if (lane == 0) sh->flag = 1;
+    __syncwarp();
+    for (int c = 0; c < kNP; ++c) {
+        if (lane == c) {
+            double d = sh->L[c][c];
+            for (int k = 0; k < c; ++k) d -= sh->L[c][k] * sh->L[c][k];
+            if (!(d > 0.0)) sh->flag = 0;
+            else sh->L[c][c] = sqrt(d);
+        }
+        __syncwarp();
+        if (!sh->flag) break;
+        if (lane > c && lane < kNP) {
+            double s = sh->L[lane][c];
+            for (int k = 0; k < c; ++k) s -= sh->L[lane][k] * sh->L[c][k];
+            sh->L[lane][c] = s / sh->L[c][c];
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && sh->flag) {
+        double z[kNP];
+        for (int r = 0; r < kNP; ++r) {
+            double s = st->gs[r];
+            for (int k = 0; k < r; ++k) s -= sh->L[r][k] * z[k];
+            z[r] = s / sh->L[r][r];
+        }
+        for (int r = kNP - 1; r >= 0; --r) {
+            double s = z[r];
+            for (int k = r + 1; k < kNP; ++k) s -= sh->L[k][r] * sh->y[k];
+            sh->y[r] = s / sh->L[r][r];
+        }
+    }
+    __syncwarp();
+    return sh->flag;
+}
+
+__device__ __forceinline__ void warp_controller(PairState* st, const Config* cfg, CtrlShared* sh, double* history,
+                                                IterStats* stats, int max_hist, int max_ticks, int lane)
+{
+    int go = 0;
+    if (lane == 0) go = ctrl_begin(st, cfg, &sh->ev);
+    go = __shfl_sync(kFull, go, 0);
+    while (go) {
+        int ok = 0;
+        if (lane == 0) ok = ctrl_prepare(st, cfg, sh->D);
+        ok = __shfl_sync(kFull, ok, 0);  // also orders lane 0's writes of D before the other lanes' reads
+        if (!ok) {
+            go = 0;
+            break;
+        }
+        __syncwarp();
+        const int valid = warp_solve_damped(st, sh, lane);
+        int r = 0;
+        if (lane == 0) r = ctrl_complete(st, cfg, valid, sh->y);
+        r = __shfl_sync(kFull, r, 0);
+        if (r == 0) break;
+        if (r == 2) go = 0;
+    }
+    if (lane == 0) {
+        if (!go) ctrl_finish(st, cfg, history, stats, max_hist);
+        if (st->ticks >= max_ticks && st->phase != PH_DONE) {  // never spin forever on the device
+            st->error = 1;
+            st->phase = PH_DONE;
+        }
     }
 }
 
@@ -644,9 +730,19 @@ __global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(
             reinterpret_cast<unsigned long long*>(&s_state)[k] = __ldcg(reinterpret_cast<const unsigned long long*>(st) + k);
         for (int k = threadIdx.x; k < kCfgWords; k += kEvalThreads)
             reinterpret_cast<unsigned long long*>(&s_cfg)[k] = reinterpret_cast<const unsigned long long*>(P.cfg)[k];
+        __shared__ CtrlShared s_ctrl;
         __syncthreads();
-        if (threadIdx.x == 0 && s_state.phase != PH_DONE)
-            run_controller(&s_state, &s_cfg, s_sum, P.history, P.stats, P.max_hist, max_ticks);
+        if (s_state.phase != PH_DONE) {  // block-uniform
+            // moment expansion around the pose the residuals were taken at: 36 entries of N, then 27 output tasks
+            if (threadIdx.x == 0) quat_frame(evaluated_at(&s_state), &s_ctrl.frame);
+            __syncthreads();
+            if (threadIdx.x < kExpandN) s_ctrl.N[threadIdx.x] = expand_N_entry(s_ctrl.frame, threadIdx.x);
+            __syncthreads();
+            if (threadIdx.x < kExpandTasks) expand_task(s_sum, s_ctrl.N, threadIdx.x, &s_ctrl.ev);
+            __syncthreads();
+            if (threadIdx.x < 32)
+                warp_controller(&s_state, &s_cfg, &s_ctrl, P.history, P.stats, P.max_hist, max_ticks, threadIdx.x);
+        }
         __syncthreads();
         for (int k = threadIdx.x; k < kStateWords; k += kEvalThreads)
             reinterpret_cast<unsigned long long*>(st)[k] = reinterpret_cast<const unsigned long long*>(&s_state)[k];

@@ -148,72 +148,101 @@ PPCR_HD void matmul4(const double* A, const double* B, double* C)
     for (int k = 0; k < 16; ++k) C[k] = tmp[k];
 }
 
-// Moments -> dense J^T W J (H, 7x7 row-major), J^T W r (g) and cost at the pose x the residuals were taken at.
-PPCR_HD void expand_moments(const double* S, const double* x, double* H, double* g, double* cost)
+// ---- moments -> dense J^T W J (H, 7x7 row-major), J^T W r (g) and cost at the pose x the residuals were taken at ----
+//
+// Split into independent pieces so that the controller block can spread them over its threads (36 entries of N, then
+// 27 output tasks) while the CPU build runs the same pieces in a loop: both produce the same bits.
+
+struct Expanded {
+    double H[kNP * kNP];
+    double g[kNP];
+    double cost;
+};
+
+struct QuatFrame {  // u = q / |q| and 1 / |q|
+    double u[4];
+    double inv_n;
+};
+
+PPCR_HD void quat_frame(const double* x, QuatFrame* f)
 {
     const double n = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
-    const double u[4] = {x[0] / n, x[1] / n, x[2] / n, x[3] / n};
-    const double a = u[0];
-    const double b[3] = {u[1], u[2], u[3]};
-    double Pn[4][4];
-    for (int r = 0; r < 4; ++r)
-        for (int c = 0; c < 4; ++c) Pn[r][c] = ((r == c ? 1.0 : 0.0) - u[r] * u[c]) / n;
-    // N_c = M(e_c) * Pn, where M(p) = [ 2 b x p | -2a[p]x + 2((b.p) I + b p^T - 2 p b^T) ]
-    double N[3][3][4];
-    for (int c = 0; c < 3; ++c) {
-        double e[3] = {0.0, 0.0, 0.0};
-        e[c] = 1.0;
-        double M[3][4];
-        M[0][0] = 2.0 * (b[1] * e[2] - b[2] * e[1]);
-        M[1][0] = 2.0 * (b[2] * e[0] - b[0] * e[2]);
-        M[2][0] = 2.0 * (b[0] * e[1] - b[1] * e[0]);
-        const double skew[3][3] = {{0.0, -e[2], e[1]}, {e[2], 0.0, -e[0]}, {-e[1], e[0], 0.0}};
-        for (int r = 0; r < 3; ++r)
-            for (int k = 0; k < 3; ++k)
-                M[r][k + 1] = -2.0 * a * skew[r][k] + 2.0 * ((r == k ? b[c] : 0.0) + b[r] * e[k] - 2.0 * e[r] * b[k]);
-        for (int r = 0; r < 3; ++r)
-            for (int k = 0; k < 4; ++k) {
-                double s = 0.0;
-                for (int l = 0; l < 4; ++l) s += M[r][l] * Pn[l][k];
-                N[c][r][k] = s;
-            }
+    f->inv_n = 1.0 / n;
+    for (int k = 0; k < 4; ++k) f->u[k] = x[k] * f->inv_n;
+}
+
+constexpr int kExpandN = 36;      // entries of N[c][r][k], index (c * 3 + r) * 4 + k
+constexpr int kExpandTasks = 27;  // 10 H_qq pairs, 12 H_qt entries, 4 g_q entries, 1 task for H_tt / g_t / cost
+
+// N_c = M(e_c) * Pn with M(p) = [ 2 b x p | -2a[p]x + 2((b.p) I + b p^T - 2 p b^T) ], Pn = (I - u u^T) / |q|
+PPCR_HD double expand_N_entry(const QuatFrame& f, int idx)
+{
+    const int c = idx / 12, r = (idx / 4) % 3, k = idx % 4;
+    const double a = f.u[0];
+    const double b[3] = {f.u[1], f.u[2], f.u[3]};
+    double e[3] = {0.0, 0.0, 0.0};
+    e[c] = 1.0;
+    double M[4];
+    const int r1 = (r + 1) % 3, r2 = (r + 2) % 3;
+    M[0] = 2.0 * (b[r1] * e[r2] - b[r2] * e[r1]);  // 2 (b x e)_r
+    for (int kk = 0; kk < 3; ++kk) {
+        // skew(e)[r][kk]: +e[j] / -e[j] on the off-diagonals
+        double sk = 0.0;
+        if (kk == r1) sk = -e[r2];
+        else if (kk == r2) sk = e[r1];
+        M[kk + 1] = -2.0 * a * sk + 2.0 * ((r == kk ? b[c] : 0.0) + b[r] * e[kk] - 2.0 * e[r] * b[kk]);
     }
-    double S2[3][3];
-    S2[0][0] = S[M_S2 + 0]; S2[0][1] = S[M_S2 + 1]; S2[0][2] = S[M_S2 + 2];
-    S2[1][0] = S[M_S2 + 1]; S2[1][1] = S[M_S2 + 3]; S2[1][2] = S[M_S2 + 4];
-    S2[2][0] = S[M_S2 + 2]; S2[2][1] = S[M_S2 + 4]; S2[2][2] = S[M_S2 + 5];
-    for (int k = 0; k < kNP * kNP; ++k) H[k] = 0.0;
-    // H_qq = sum_{c,d} S2[c][d] N_c^T N_d
-    for (int p = 0; p < 4; ++p)
-        for (int q = p; q < 4; ++q) {
-            double s = 0.0;
-            for (int c = 0; c < 3; ++c)
-                for (int d = 0; d < 3; ++d) {
-                    double nn = 0.0;
-                    for (int r = 0; r < 3; ++r) nn += N[c][r][p] * N[d][r][q];
-                    s += S2[c][d] * nn;
-                }
-            H[p * kNP + q] = s;
-            H[q * kNP + p] = s;
+    double s = 0.0;
+    for (int l = 0; l < 4; ++l) s += M[l] * (((l == k ? 1.0 : 0.0) - f.u[l] * f.u[k]) * f.inv_n);
+    return s;
+}
+
+PPCR_HD void expand_task(const double* S, const double* N, int task, Expanded* out)
+{
+    if (task < 10) {  // H_qq(p, q) = sum_{c,d} S2[c][d] N_c[:,p] . N_d[:,q]
+        int p = 0, q = task;
+        while (q >= 4 - p) {
+            q -= 4 - p;
+            ++p;
         }
-    // H_qt = sum_c S1[c] N_c^T ; H_tt = S0 I
-    for (int p = 0; p < 4; ++p)
-        for (int r = 0; r < 3; ++r) {
-            double s = 0.0;
-            for (int c = 0; c < 3; ++c) s += S[M_S1 + c] * N[c][r][p];
-            H[p * kNP + 4 + r] = s;
-            H[(4 + r) * kNP + p] = s;
-        }
-    for (int r = 0; r < 3; ++r) H[(4 + r) * kNP + 4 + r] = S[M_S0];
-    // g = J^T W r with J = -[A | I]:  g_q = -sum_c N_c^T C[c,:]^T,  g_t = -S_rho
-    for (int p = 0; p < 4; ++p) {
+        q += p;
+        const int s2i[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
         double s = 0.0;
         for (int c = 0; c < 3; ++c)
-            for (int r = 0; r < 3; ++r) s += N[c][r][p] * S[M_C + 3 * c + r];
-        g[p] = -s;
+            for (int d = 0; d < 3; ++d) {
+                double nn = 0.0;
+                for (int r = 0; r < 3; ++r) nn += N[(c * 3 + r) * 4 + p] * N[(d * 3 + r) * 4 + q];
+                s += S[M_S2 + s2i[c][d]] * nn;
+            }
+        out->H[p * kNP + q] = s;
+        out->H[q * kNP + p] = s;
+    } else if (task < 22) {  // H_qt(p, r) = sum_c S1[c] N_c[r][p]
+        const int p = (task - 10) / 3, r = (task - 10) % 3;
+        double s = 0.0;
+        for (int c = 0; c < 3; ++c) s += S[M_S1 + c] * N[(c * 3 + r) * 4 + p];
+        out->H[p * kNP + 4 + r] = s;
+        out->H[(4 + r) * kNP + p] = s;
+    } else if (task < 26) {  // g_q(p) = -sum_{c,r} N_c[r][p] C[c][r]
+        const int p = task - 22;
+        double s = 0.0;
+        for (int c = 0; c < 3; ++c)
+            for (int r = 0; r < 3; ++r) s += N[(c * 3 + r) * 4 + p] * S[M_C + 3 * c + r];
+        out->g[p] = -s;
+    } else {  // H_tt = S0 I, g_t = -S_rho, cost
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) out->H[(4 + r) * kNP + 4 + c] = (r == c) ? S[M_S0] : 0.0;
+        for (int r = 0; r < 3; ++r) out->g[4 + r] = -S[M_SR + r];
+        out->cost = S[M_COST];
     }
-    for (int r = 0; r < 3; ++r) g[4 + r] = -S[M_SR + r];
-    *cost = S[M_COST];
+}
+
+PPCR_HD void expand_moments(const double* S, const double* x, Expanded* out)
+{
+    QuatFrame f;
+    quat_frame(x, &f);
+    double N[kExpandN];
+    for (int k = 0; k < kExpandN; ++k) N[k] = expand_N_entry(f, k);
+    for (int t = 0; t < kExpandTasks; ++t) expand_task(S, N, t, out);
 }
 
 // Solve (Hs + diag(D)^2) y = gs by Cholesky; false when the matrix is not numerically positive definite.
@@ -247,12 +276,12 @@ PPCR_HD bool solve_damped(const double* Hs, const double* gs, const double* D, d
     return true;
 }
 
-// Loads a fresh evaluation (at pose x_at) into the state: column-scaled Hs/gs, x_cost, gradient max-norm.
-PPCR_HD void load_evaluation(PairState* s, const double* S, const double* x_at, bool first)
+// Loads a fresh evaluation into the state: column-scaled Hs/gs, x_cost, gradient max-norm.
+PPCR_HD void load_evaluation(PairState* s, const Expanded& ev, bool first)
 {
-    double H[kNP * kNP], g[kNP], cost;
-    expand_moments(S, x_at, H, g, &cost);
-    s->x_cost = cost;
+    const double* H = ev.H;
+    const double* g = ev.g;
+    s->x_cost = ev.cost;
     double gm = 0.0;
     for (int p = 0; p < kNP; ++p) gm = fmax(gm, fabs(g[p]));
     s->grad_max = gm;  // max-norm of the UNSCALED gradient
@@ -272,62 +301,78 @@ PPCR_HD double vec_norm7(const double* v)
     return sqrt(n);
 }
 
-// FinalizeIteration + ComputeTrustRegionStep, looping over invalid steps.  Returns true when a candidate is
-// ready in s->cand / s->pose_e (the caller runs the eval kernel next), false when the minimiser stopped.
+// FinalizeIteration + ComputeTrustRegionStep of the restated Ceres minimiser, cut at the linear solve so that the
+// controller block can run the 7x7 Cholesky on several threads:
+//   step_prepare  -> false: the minimiser stopped (s->termination says why); true: D holds the damping diagonal
+//   [solve (Hs + diag(D)^2) y = gs]
+//   step_complete -> 0: candidate ready in s->cand / s->pose_e (evaluate it next), 1: invalid step, prepare again,
+//                    2: the minimiser stopped
+PPCR_HD bool step_prepare(PairState* s, const Config* cfg, double* D)
+{
+    const double kMinRadius = 1e-32, kMinDiag = 1e-6, kMaxDiag = 1e32, kGradTol = 1e-10;
+    if (s->step_ok) {
+        ++s->successful;
+        if (s->x_cost < s->minimum_cost) {
+            s->minimum_cost = s->x_cost;
+            for (int p = 0; p < kNP; ++p) s->best_x[p] = s->x[p];
+        }
+    }
+    // the IterationCallback refreshes the weights at the current iterate: the next eval does it on the fly
+    pose_from_x(s->x, &s->pose_w);
+    if (s->iteration >= cfg->max_lm_iterations) { s->termination = TERM_MAX_ITER; return false; }
+    if (s->step_ok && s->grad_max <= kGradTol) { s->termination = TERM_GRADIENT_TOL; return false; }
+    if (s->radius < kMinRadius) { s->termination = TERM_MIN_RADIUS; return false; }
+    ++s->iteration;
+    if (!s->reuse_diag) {
+        for (int p = 0; p < kNP; ++p) s->diag[p] = fmin(fmax(s->Hs[p * kNP + p], kMinDiag), kMaxDiag);
+    }
+    const double inv_radius = 1.0 / s->radius;
+    for (int p = 0; p < kNP; ++p) D[p] = sqrt(s->diag[p] * inv_radius);
+    return true;
+}
+
+PPCR_HD int step_complete(PairState* s, const Config* cfg, bool valid, const double* y)
+{
+    (void)cfg;
+    const int kMaxInvalid = 5;
+    s->reuse_diag = 1;
+    for (int p = 0; p < kNP && valid; ++p) valid = isfinite(y[p]);
+    if (valid) {
+        double lin = 0.0, quad = 0.0;
+        for (int r = 0; r < kNP; ++r) s->step[r] = -y[r];
+        for (int r = 0; r < kNP; ++r) {
+            lin += s->step[r] * s->gs[r];
+            double t = 0.0;
+            for (int c = 0; c < kNP; ++c) t += s->Hs[r * kNP + c] * s->step[c];
+            quad += s->step[r] * t;
+        }
+        s->model_change = -(lin + 0.5 * quad);
+        valid = s->model_change > 0.0;
+    }
+    if (!valid) {
+        if (++s->invalid >= kMaxInvalid) { s->termination = TERM_INVALID_STEPS; return 2; }
+        s->radius /= s->decrease_factor;
+        s->decrease_factor *= 2.0;
+        s->step_ok = 0;
+        s->min_iter_cost = fmin(s->min_iter_cost, s->x_cost);
+        return 1;
+    }
+    s->invalid = 0;
+    for (int p = 0; p < kNP; ++p) s->cand[p] = s->x[p] + s->step[p] * s->scale[p];
+    pose_from_x(s->cand, &s->pose_e);
+    return 0;
+}
+
+// the serial driver of the two halves (CPU build, and the reference the cooperative device driver must match)
 PPCR_HD bool finalize_and_step(PairState* s, const Config* cfg)
 {
-    const double kMaxRadius = 1e16, kMinRadius = 1e-32, kMinDiag = 1e-6, kMaxDiag = 1e32, kGradTol = 1e-10;
-    (void)kMaxRadius;
-    const int kMaxInvalid = 5;
     for (;;) {
-        if (s->step_ok) {
-            ++s->successful;
-            if (s->x_cost < s->minimum_cost) {
-                s->minimum_cost = s->x_cost;
-                for (int p = 0; p < kNP; ++p) s->best_x[p] = s->x[p];
-            }
-        }
-        // the IterationCallback refreshes the weights at the current iterate: the next eval does it on the fly
-        pose_from_x(s->x, &s->pose_w);
-        if (s->iteration >= cfg->max_lm_iterations) { s->termination = TERM_MAX_ITER; return false; }
-        if (s->step_ok && s->grad_max <= kGradTol) { s->termination = TERM_GRADIENT_TOL; return false; }
-        if (s->radius < kMinRadius) { s->termination = TERM_MIN_RADIUS; return false; }
-        ++s->iteration;
-
-        if (!s->reuse_diag) {
-            for (int p = 0; p < kNP; ++p) s->diag[p] = fmin(fmax(s->Hs[p * kNP + p], kMinDiag), kMaxDiag);
-        }
         double D[kNP], y[kNP];
-        for (int p = 0; p < kNP; ++p) D[p] = sqrt(s->diag[p] / s->radius);
-        bool valid = solve_damped(s->Hs, s->gs, D, y);
-        s->reuse_diag = 1;
-        for (int p = 0; p < kNP && valid; ++p) valid = isfinite(y[p]);
-        if (valid) {
-            double lin = 0.0, quad = 0.0;
-            for (int r = 0; r < kNP; ++r) {
-                s->step[r] = -y[r];
-            }
-            for (int r = 0; r < kNP; ++r) {
-                lin += s->step[r] * s->gs[r];
-                double t = 0.0;
-                for (int c = 0; c < kNP; ++c) t += s->Hs[r * kNP + c] * s->step[c];
-                quad += s->step[r] * t;
-            }
-            s->model_change = -(lin + 0.5 * quad);
-            valid = s->model_change > 0.0;
-        }
-        if (!valid) {
-            if (++s->invalid >= kMaxInvalid) { s->termination = TERM_INVALID_STEPS; return false; }
-            s->radius /= s->decrease_factor;
-            s->decrease_factor *= 2.0;
-            s->step_ok = 0;
-            s->min_iter_cost = fmin(s->min_iter_cost, s->x_cost);
-            continue;
-        }
-        s->invalid = 0;
-        for (int p = 0; p < kNP; ++p) s->cand[p] = s->x[p] + s->step[p] * s->scale[p];
-        pose_from_x(s->cand, &s->pose_e);
-        return true;
+        if (!step_prepare(s, cfg, D)) return false;
+        const bool valid = solve_damped(s->Hs, s->gs, D, y);
+        const int r = step_complete(s, cfg, valid, y);
+        if (r == 0) return true;
+        if (r == 2) return false;
     }
 }
 
@@ -355,16 +400,18 @@ PPCR_HD void lm_reset(PairState* s, const Config* cfg)
     s->K = 0;  // the search kernel accumulates the association size here
 }
 
-// After the first eval of an outer iteration (residuals and weights at x0).  true = LM continues.
-PPCR_HD bool lm_begin(PairState* s, const Config* cfg, const double* S)
+// After the first eval of an outer iteration (residuals and weights at x0).  true = LM continues with a
+// trust-region step (step_prepare / solve / step_complete).
+PPCR_HD bool lm_begin_eval(PairState* s, const Config* cfg, const Expanded& ev)
 {
+    (void)cfg;
     if (s->K == 0) {  // a Ceres problem without residual blocks: zero costs, pose untouched
         s->termination = TERM_NO_RESIDUALS;
         s->initial_cost = 0.0;
         s->min_iter_cost = 0.0;
         return false;
     }
-    load_evaluation(s, S, s->x, true);
+    load_evaluation(s, ev, true);
     s->x_norm = vec_norm7(s->x);
     s->initial_cost = s->x_cost;
     s->min_iter_cost = s->x_cost;
@@ -373,15 +420,16 @@ PPCR_HD bool lm_begin(PairState* s, const Config* cfg, const double* S)
     s->ev_acc_cand = 0.0;
     s->ev_nonmono = 0;
     s->step_ok = 1;
-    return finalize_and_step(s, cfg);
+    return true;
 }
 
-// After an eval at the candidate (weights refreshed at the current iterate).  true = LM continues.
-PPCR_HD bool lm_continue(PairState* s, const Config* cfg, const double* S)
+// After an eval at the candidate (weights refreshed at the current iterate).  true = LM continues with a
+// trust-region step.
+PPCR_HD bool lm_continue_eval(PairState* s, const Config* cfg, const Expanded& ev)
 {
     const double kParamTol = 1e-8, kMinRelDecrease = 1e-3, kMaxRadius = 1e16;
     const int kMaxNonmono = 5;
-    const double cand_cost = S[M_COST];
+    const double cand_cost = ev.cost;
     double step_norm = 0.0;
     for (int p = 0; p < kNP; ++p) step_norm += (s->x[p] - s->cand[p]) * (s->x[p] - s->cand[p]);
     step_norm = sqrt(step_norm);
@@ -394,7 +442,7 @@ PPCR_HD bool lm_continue(PairState* s, const Config* cfg, const double* S)
     if (quality > kMinRelDecrease) {
         for (int p = 0; p < kNP; ++p) s->x[p] = s->cand[p];
         s->x_norm = vec_norm7(s->x);
-        load_evaluation(s, S, s->x, false);  // the same pass already produced the Jacobian at the candidate
+        load_evaluation(s, ev, false);  // the same pass already produced the Jacobian at the candidate
         s->step_ok = 1;
         const double t = 2.0 * quality - 1.0;
         s->radius = fmin(kMaxRadius, s->radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
@@ -428,7 +476,7 @@ PPCR_HD bool lm_continue(PairState* s, const Config* cfg, const double* S)
         s->reuse_diag = 1;
         s->min_iter_cost = fmin(s->min_iter_cost, cand_cost);
     }
-    return finalize_and_step(s, cfg);
+    return true;
 }
 
 // hasConverged(), src/prob_point_cloud_registration.cc:138-158 (mutating).
@@ -476,20 +524,34 @@ PPCR_HD void outer_finish(PairState* s, const Config* cfg, double* history, Iter
     if (s->phase == PH_SEARCH) lm_reset(s, cfg);
 }
 
-// One controller invocation after an eval; drives the phases.
-PPCR_HD void controller_tick(PairState* s, const Config* cfg, const double* S, double* history, IterStats* stats,
-                             int32_t max_hist)
+// Pose the evaluation that has just finished took its residuals at (the moments are expanded around it).
+PPCR_HD const double* evaluated_at(const PairState* s) { return s->phase == PH_SEARCH ? s->x : s->cand; }
+
+// First half of a controller invocation: digest the evaluation.  true = a trust-region step follows.
+PPCR_HD bool controller_begin(PairState* s, const Config* cfg, const Expanded& ev)
 {
-    if (s->phase == PH_DONE) return;
     ++s->ticks;
     bool go;
     if (s->phase == PH_SEARCH) {
         s->apply_dT = 0;  // the search that fed this evaluation has moved the cloud
-        go = lm_begin(s, cfg, S);
+        go = lm_begin_eval(s, cfg, ev);
         s->phase = PH_LM;
     } else {
-        go = lm_continue(s, cfg, S);
+        go = lm_continue_eval(s, cfg, ev);
     }
+    return go;
+}
+
+// One controller invocation after an eval, serial form (CPU build; the device runs the same pieces with the moment
+// expansion and the linear solve spread over threads -- k_evalctl).
+PPCR_HD void controller_tick(PairState* s, const Config* cfg, const double* S, double* history, IterStats* stats,
+                             int32_t max_hist)
+{
+    if (s->phase == PH_DONE) return;
+    Expanded ev;
+    expand_moments(S, evaluated_at(s), &ev);
+    bool go = controller_begin(s, cfg, ev);
+    if (go) go = finalize_and_step(s, cfg);
     if (!go) outer_finish(s, cfg, history, stats, max_hist);
 }
 

@@ -253,34 +253,39 @@ struct TopListDyn {
 
 // ---- traversal -----------------------------------------------------------------------------------------------
 
-PPCR_HD float box_lower_bound(float qx, float qy, float qz, float cx, float cy, float cz, float hi)
+// squared distance from q to the interval [c - hi, c + hi] along one axis
+PPCR_HD float axis_gap2(float q, float c, float hi)
 {
-    // squared distance from q to the cube |p - c| <= hi per axis, shaved so that float rounding can only make it
-    // smaller than the exact float32 distance to any point binned into the cube
-    float dx = fabsf(qx - cx) - hi, dy = fabsf(qy - cy) - hi, dz = fabsf(qz - cz) - hi;
-    dx = dx > 0.f ? dx : 0.f;
-    dy = dy > 0.f ? dy : 0.f;
-    dz = dz > 0.f ? dz : 0.f;
-    return (dx * dx + dy * dy + dz * dz) * 0.99999f;
+    float d = fabsf(q - c) - hi;
+    d = d > 0.f ? d : 0.f;
+    return d * d;
 }
+
+// The pruning threshold a (not shaved) box lower bound is compared with: slightly ABOVE the bound, so that float
+// rounding in the lower bound can only keep a subtree that exact arithmetic would prune, never the reverse.
+PPCR_HD float prune_threshold(float bound_d2) { return bound_d2 * 1.00002f; }
 
 // Leaves the (at most m) nearest targets with d2 < r2f in L.  pts = Morton-sorted target, .w = original index.
 // bound0 <= r2f is a caller-supplied squared distance within which at least m targets are KNOWN to lie (r2f when
 // nothing is known): points farther than it cannot be among the m nearest, so subtrees beyond it are never opened.
-// `stack` must hold kTreeStack ints.
+// `stack` must hold 2 * kTreeStack ints: (node, lower bound of its box) pairs.
 template <class List>
 PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, const float4* __restrict__ pts,
                          float qx, float qy, float qz, float r2f, float bound0, List& L, int* stack)
 {
     const unsigned long long r2key = static_cast<unsigned long long>(float_bits(r2f)) << 32;  // keys of d2 >= r2f are > this
     float bound_d2 = bound0 < r2f ? bound0 : r2f;  // no unseen point farther than this can enter the list
+    float thr = prune_threshold(bound_d2);
     int sp = 0;
-    stack[sp++] = 0;
+    stack[0] = 0;
+    stack[1] = 0;  // float bits of 0.0f
+    sp = 1;
     while (sp > 0) {
-        const int ni = stack[--sp];
-        const TreeNode n = nodes[ni];
+        --sp;
+        // the bound may have shrunk since this node was pushed: re-test with the lower bound stored beside it
+        if (bits_float(static_cast<uint32_t>(stack[2 * sp + 1])) > thr) continue;
+        const TreeNode n = nodes[stack[2 * sp]];
         if (n.end <= n.begin) continue;
-        if (box_lower_bound(qx, qy, qz, n.cx, n.cy, n.cz, n.half + g.slack) > bound_d2) continue;
         if (n.child < 0) {
             // leaf: run ahead to the next candidate that enters the list, then insert.  Written as two nested loops so
             // that the threads of a warp meet again at the (expensive) insertion instead of serialising it.
@@ -304,23 +309,33 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
                 if (w != kKeyInf) {
                     const float wd = key_d2(w);
                     bound_d2 = wd < bound_d2 ? wd : bound_d2;
+                    thr = prune_threshold(bound_d2);
                 }
             }
             continue;
         }
-        // children, pushed far-to-near so that the octant holding q is opened first
+        // Children, pushed far-to-near so that the octant holding q is opened first.  The lower bound of a child box
+        // is a sum of three per-axis gaps, each of which takes one of two values (the child's half on q's side of
+        // the centre plane, or the other one): six gaps serve all eight children.
         const int oct = (qx >= n.cx ? 1 : 0) | (qy >= n.cy ? 2 : 0) | (qz >= n.cz ? 4 : 0);
         const float ch = n.half * 0.5f;
         const float hi = ch + g.slack;
+        const float gx_lo = axis_gap2(qx, n.cx - ch, hi), gx_hi = axis_gap2(qx, n.cx + ch, hi);
+        const float gy_lo = axis_gap2(qy, n.cy - ch, hi), gy_hi = axis_gap2(qy, n.cy + ch, hi);
+        const float gz_lo = axis_gap2(qz, n.cz - ch, hi), gz_hi = axis_gap2(qz, n.cz + ch, hi);
+        const float nx = (oct & 1) ? gx_hi : gx_lo, fx = (oct & 1) ? gx_lo : gx_hi;  // near / far side per axis
+        const float ny = (oct & 2) ? gy_hi : gy_lo, fy = (oct & 2) ? gy_lo : gy_hi;
+        const float nz = (oct & 4) ? gz_hi : gz_lo, fz = (oct & 4) ? gz_lo : gz_hi;
+        const int mask = n.mask;
 #pragma unroll
         for (int k = 7; k >= 0; --k) {
             const int c = oct ^ k;
-            if (!((n.mask >> c) & 1)) continue;
-            const float ccx = n.cx + ((c & 1) ? ch : -ch);
-            const float ccy = n.cy + ((c & 2) ? ch : -ch);
-            const float ccz = n.cz + ((c & 4) ? ch : -ch);
-            if (box_lower_bound(qx, qy, qz, ccx, ccy, ccz, hi) > bound_d2) continue;
-            stack[sp++] = n.child + c;
+            const float lb = ((k & 1) ? fx : nx) + ((k & 2) ? fy : ny) + ((k & 4) ? fz : nz);
+            if (((mask >> c) & 1) && !(lb > thr)) {
+                stack[2 * sp] = n.child + c;
+                stack[2 * sp + 1] = static_cast<int>(float_bits(lb));
+                ++sp;
+            }
         }
     }
 }

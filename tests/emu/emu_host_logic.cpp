@@ -175,13 +175,13 @@ void emu_normal_eq(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, 
     const WeightCfg wc = make_weight_cfg(dof);
     double S[kNSum];
     if (fast_weights) eval<true>(src, tgt, vi, vc, m, st, wc, S); else eval<false>(src, tgt, vi, vc, m, st, wc, S);
-    double H[kNP * kNP], g[kNP], cost;
-    expand_moments(S, pose_e, H, g, &cost);
+    Expanded ev;
+    expand_moments(S, pose_e, &ev);
     int o = 0;
     for (int r = 0; r < kNP; ++r)
-        for (int c = r; c < kNP; ++c) normal_eq36[o++] = H[r * kNP + c];
-    for (int r = 0; r < kNP; ++r) normal_eq36[o++] = g[r];
-    normal_eq36[o] = cost;
+        for (int c = r; c < kNP; ++c) normal_eq36[o++] = ev.H[r * kNP + c];
+    for (int r = 0; r < kNP; ++r) normal_eq36[o++] = ev.g[r];
+    normal_eq36[o] = ev.cost;
     if (moments24) std::memcpy(moments24, S, sizeof(S));
 }
 
@@ -249,7 +249,7 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
     }
     if (out_n_nodes) *out_n_nodes = n_nodes;
     int64_t total = 0;
-    int stack[kTreeStack];
+    int stack[2 * kTreeStack];
     std::vector<unsigned long long> buf(static_cast<size_t>(std::max(m, 1)));
     for (int64_t i = 0; i < n_src; ++i) {
         const float* q = src_xyzw + 4 * i;

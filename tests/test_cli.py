@@ -112,7 +112,9 @@ def test_cli_end_to_end_matches_oracle(cli, oracle, tmp_path):
     assert len(rows) == len(hist) and all(len(rw) == 12 for rw in rows)
     np.testing.assert_allclose(float(rows[0][2]), ref.stats[0]["initial_cost"], rtol=1e-4)
     m = re.findall(r"MSE w.r.t. ground truth: ([0-9.eE+-]+)", r.stdout)
-    assert len(m) >= 2 and float(m[-1]) < 0.05 and float(m[-1]) < float(rows[0][11])
+    want_mse = oracle.calculate_mse(synth.apply_T_like_pcl(src, ref.transformation), gt)   # calculateMSE, CLI:186
+    assert len(m) >= 2 and abs(float(m[-1]) - want_mse) < 1e-3 and float(m[-1]) < float(m[0])
+    assert abs(float(rows[-1][11]) - want_mse) < 1e-3
 
 
 @pytest.mark.gpu
