@@ -10,12 +10,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cfloat>
 #include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -104,9 +106,26 @@ struct DevBuf {
     }
 };
 
+// PPCR_TRACE=1: wall-clock trace of the set-up phases on stderr (each mark synchronises the stream first)
+struct Trace {
+    bool on;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point t0;
+    explicit Trace(cudaStream_t s) : on(getenv("PPCR_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what)
+    {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ppcr trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 static int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 static int g_sm_count = 0;
+constexpr size_t kEvalSmem = static_cast<size_t>(kNSum) * kEvalThreads * sizeof(double);  // per-thread moment columns
 constexpr int kDefaultLeafCap = 32;
 
 // kernel-launch bookkeeping for ppcr_get_stage_times: every launch site outside the tick adds to the engine the
@@ -164,7 +183,7 @@ struct Engine {
     std::vector<Pair> pairs;
     DevBuf<PairDev> d_pairs;
     DevBuf<LoopCtl> d_loop;
-    int* h_active = nullptr;  // pinned
+    int* h_active = nullptr;  // pinned, shared by the handles of a host thread (pinned_flag)
     int eval_blocks_per_sm = PPCR_EVAL_MIN_BLOCKS, search_blocks_per_sm = 8;
     int list_cap = 0;  // register capacity of the search kernel's top-m list; 0 = local-memory list (m > 32)
     // launch geometry (capacity based, so a captured graph stays valid while the slots are refilled)
@@ -202,7 +221,6 @@ struct Engine {
         d_pairs.release();
         d_loop.release();
         flush.release();
-        if (h_active) cudaFreeHost(h_active);
         if (stream) cudaStreamSynchronize(stream);  // the frees above are stream-ordered
         if (own_stream && stream) cudaStreamDestroy(stream);
         if (g_alloc_stream == stream) g_alloc_stream = nullptr;
@@ -217,29 +235,58 @@ struct ppcr_handle {
 // device selection
 // ------------------------------------------------------------------------------------------------------------
 
+// Per-device one-time set-up (architecture check, kernel attributes, memory pool); a handle per scan pair must not pay
+// for device queries again.
+struct DeviceInfo {
+    bool ready = false;
+    int sm_count = 0;
+};
+static DeviceInfo g_devices[64];
+static std::mutex g_devices_mutex;
+
 static void select_device(int device)
 {
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0) {
-        cudaGetLastError();
-        throw StatusError{PPCR_ERR_NO_DEVICE, "no CUDA device is visible; libppcr_cuda has no CPU fallback"};
+    if (device < 0 || device >= 64) throw StatusError{PPCR_ERR_NO_DEVICE, "device ordinal out of range"};
+    {
+        std::lock_guard<std::mutex> lock(g_devices_mutex);
+        DeviceInfo& info = g_devices[device];
+        if (!info.ready) {
+            int count = 0;
+            cudaError_t e = cudaGetDeviceCount(&count);
+            if (e != cudaSuccess || count == 0) {
+                cudaGetLastError();
+                throw StatusError{PPCR_ERR_NO_DEVICE, "no CUDA device is visible; libppcr_cuda has no CPU fallback"};
+            }
+            if (device >= count) throw StatusError{PPCR_ERR_NO_DEVICE, "device ordinal out of range"};
+            CK(cudaSetDevice(device));
+            int major = 0, sms = 0;
+            CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+            if (major != 10) {
+                cudaDeviceProp prop;
+                CK(cudaGetDeviceProperties(&prop, device));
+                throw StatusError{PPCR_ERR_NO_DEVICE, std::string("libppcr_cuda is built for sm_100a only; device is ") + prop.name};
+            }
+            CK(cudaFuncSetAttribute(k_evalctl<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kEvalSmem)));
+            CK(cudaFuncSetAttribute(k_evalctl<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kEvalSmem)));
+            cudaMemPool_t pool;
+            CK(cudaDeviceGetDefaultMemPool(&pool, device));
+            unsigned long long keep = ~0ull;
+            CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            info.sm_count = sms;
+            info.ready = true;
+        }
+        g_sm_count = info.sm_count;
     }
-    if (device < 0 || device >= count) throw StatusError{PPCR_ERR_NO_DEVICE, "device ordinal out of range"};
     CK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
-        throw StatusError{PPCR_ERR_NO_DEVICE, std::string("libppcr_cuda is built for sm_100a only; device is ") + prop.name};
-    g_sm_count = prop.multiProcessorCount;
-    static bool pool_ready[64] = {};
-    if (device < 64 && !pool_ready[device]) {
-        cudaMemPool_t pool;
-        CK(cudaDeviceGetDefaultMemPool(&pool, device));
-        unsigned long long keep = ~0ull;
-        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        pool_ready[device] = true;
-    }
+}
+
+// one small pinned word per host thread for the "still running?" read-back of the host-stepped driver
+static int* pinned_flag()
+{
+    static thread_local int* p = nullptr;
+    if (!p) CK(cudaMallocHost(&p, 4 * sizeof(int)));
+    return p;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -448,11 +495,13 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     if (n_src < 0 || n_tgt < 0 || (n_src > 0 && !src) || (n_tgt > 0 && !tgt)) throw StatusError{PPCR_ERR_INVALID, "null cloud"};
     if (n_src > INT_MAX / 2 || n_tgt > INT_MAX / 2) throw StatusError{PPCR_ERR_UNSUPPORTED, "clouds above 2^30 points are not supported"};
     cudaStream_t st = E.stream;
+    Trace tr(st);
     const ppcr_params& prm = E.params;
     upload_cloud(P.src, src, n_src, on_device, st);
     upload_cloud(P.tgt_raw, tgt, n_tgt, on_device, st);
     P.n_src = n_src;
     P.n_tgt = n_tgt;
+    tr.mark("upload clouds");
     if (prm.source_filter_size > 0 && n_src > 0) {
         int64_t k = voxel_filter_device(P.src.p, n_src, prm.source_filter_size, P.tmp_cloud, P, st);
         if (k >= 0) {
@@ -480,9 +529,11 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
         CK(cudaGetLastError());
         note_launches(1);
     }
+    tr.mark("voxel filters + tag");
     const int leaf_cap = E.opts.leaf_capacity > 0 ? E.opts.leaf_capacity : kDefaultLeafCap;
     if (P.n_tgt > 0) {
         build_target_tree(E, P, leaf_cap);
+        tr.mark("target tree");
     } else {
         // an empty target: a root with no points, every search returns nothing
         Bbox bb{};
@@ -498,6 +549,7 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     }
     sort_source(E, P);
     D.src = P.src.p;
+    tr.mark("source sort");
     const size_t plane = static_cast<size_t>(D.m) * D.n_pad;
     P.nbr.reserve(plane);
     P.nbr_cnt.reserve(D.n_pad);
@@ -544,6 +596,7 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     D.world = 1;
     D.spin_limit = 4000000000ll;  // ~2 s of SM clocks
     CK(cudaStreamSynchronize(st));  // host temporaries (hs, c) must outlive the copies
+    tr.mark("buffers + state");
 }
 
 static void engine_init(Engine& E, const ppcr_params& params, const ppcr_options* options)
@@ -564,7 +617,7 @@ static void engine_init(Engine& E, const ppcr_params& params, const ppcr_options
     g_alloc_stream = E.stream;
     E.d_loop.reserve(1);
     CK(cudaMemsetAsync(E.d_loop.p, 0, sizeof(LoopCtl), E.stream));
-    CK(cudaMallocHost(&E.h_active, 4 * sizeof(int)));
+    E.h_active = pinned_flag();
     if (E.opts.ticks_per_sync <= 0) E.opts.ticks_per_sync = 4;
     const char* env = getenv("PPCR_DRIVER");
     if (env && E.opts.driver == 0) E.opts.driver = atoi(env);
@@ -653,9 +706,9 @@ static void launch_evalctl(Engine& E, bool use_cond)
     const int np = static_cast<int>(E.pairs.size());
     dim3 grid(E.max_eval_blocks, np);
     if (!E.opts.exact_weights)
-        k_evalctl<true><<<grid, kEvalThreads, 0, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, use_cond ? 1 : 0, E.max_ticks);
+        k_evalctl<true><<<grid, kEvalThreads, kEvalSmem, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, use_cond ? 1 : 0, E.max_ticks);
     else
-        k_evalctl<false><<<grid, kEvalThreads, 0, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, use_cond ? 1 : 0, E.max_ticks);
+        k_evalctl<false><<<grid, kEvalThreads, kEvalSmem, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, use_cond ? 1 : 0, E.max_ticks);
 }
 
 static int launches_per_tick(const Engine& E) { return E.skip_search ? 1 : 2; }
@@ -761,11 +814,14 @@ static void run_to_completion(Engine& E)
     E.times.total_launches += 1;
     const bool rec = E.opts.record_stage_times != 0;
     bool use_graph = (E.opts.driver == 2) || (E.opts.driver == 0 && !rec && E.world == 1);
+    Trace tr(E.stream);
     if (use_graph) use_graph = build_graph(E);
+    tr.mark("graph build");
     if (use_graph) {
         CK(cudaGraphLaunch(E.graph_exec, E.stream));
         launch_final_transform(E);
         CK(cudaStreamSynchronize(E.stream));
+        tr.mark("graph run");
     } else {
         long long guard = 0;
         for (;;) {

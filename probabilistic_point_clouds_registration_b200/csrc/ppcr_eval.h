@@ -131,36 +131,41 @@ PPCR_HD void row_add(RowAcc* a, const WeightCfg& wc, double yx, double yy, doubl
 }
 
 // fold a finished row into the 24 moments; (sx,sy,sz) is the source point in double
-PPCR_HD void row_end(const RowAcc* a, double sx, double sy, double sz, double* acc)
+// STRIDE: distance between consecutive moments in `acc` (1 = a plain array; the eval kernel keeps one column per
+// thread in shared memory, STRIDE = block size, so that the 24 accumulators do not occupy 48 registers)
+template <int STRIDE>
+PPCR_HD void row_end_s(const RowAcc* a, double sx, double sy, double sz, double* acc)
 {
     const double inv = a->a0 > 0.0 ? 1.0 / a->a0 : 0.0;  // every posterior underflowed: the row carries no weight
     const double W = a->a1 * inv;
     const double rho[3] = {a->ar[0] * inv, a->ar[1] * inv, a->ar[2] * inv};
-    acc[M_S0] += W;
-    acc[M_S1 + 0] += W * sx;
-    acc[M_S1 + 1] += W * sy;
-    acc[M_S1 + 2] += W * sz;
-    acc[M_S2 + 0] += W * sx * sx;
-    acc[M_S2 + 1] += W * sx * sy;
-    acc[M_S2 + 2] += W * sx * sz;
-    acc[M_S2 + 3] += W * sy * sy;
-    acc[M_S2 + 4] += W * sy * sz;
-    acc[M_S2 + 5] += W * sz * sz;
-    acc[M_SR + 0] += rho[0];
-    acc[M_SR + 1] += rho[1];
-    acc[M_SR + 2] += rho[2];
-    acc[M_C + 0] += sx * rho[0];
-    acc[M_C + 1] += sx * rho[1];
-    acc[M_C + 2] += sx * rho[2];
-    acc[M_C + 3] += sy * rho[0];
-    acc[M_C + 4] += sy * rho[1];
-    acc[M_C + 5] += sy * rho[2];
-    acc[M_C + 6] += sz * rho[0];
-    acc[M_C + 7] += sz * rho[1];
-    acc[M_C + 8] += sz * rho[2];
-    acc[M_COST] += 0.5 * a->ac * inv;
-    acc[M_ROWS] += 1.0;
+    acc[(M_S0) * STRIDE] += W;
+    acc[(M_S1 + 0) * STRIDE] += W * sx;
+    acc[(M_S1 + 1) * STRIDE] += W * sy;
+    acc[(M_S1 + 2) * STRIDE] += W * sz;
+    acc[(M_S2 + 0) * STRIDE] += W * sx * sx;
+    acc[(M_S2 + 1) * STRIDE] += W * sx * sy;
+    acc[(M_S2 + 2) * STRIDE] += W * sx * sz;
+    acc[(M_S2 + 3) * STRIDE] += W * sy * sy;
+    acc[(M_S2 + 4) * STRIDE] += W * sy * sz;
+    acc[(M_S2 + 5) * STRIDE] += W * sz * sz;
+    acc[(M_SR + 0) * STRIDE] += rho[0];
+    acc[(M_SR + 1) * STRIDE] += rho[1];
+    acc[(M_SR + 2) * STRIDE] += rho[2];
+    acc[(M_C + 0) * STRIDE] += sx * rho[0];
+    acc[(M_C + 1) * STRIDE] += sx * rho[1];
+    acc[(M_C + 2) * STRIDE] += sx * rho[2];
+    acc[(M_C + 3) * STRIDE] += sy * rho[0];
+    acc[(M_C + 4) * STRIDE] += sy * rho[1];
+    acc[(M_C + 5) * STRIDE] += sy * rho[2];
+    acc[(M_C + 6) * STRIDE] += sz * rho[0];
+    acc[(M_C + 7) * STRIDE] += sz * rho[1];
+    acc[(M_C + 8) * STRIDE] += sz * rho[2];
+    acc[(M_COST) * STRIDE] += 0.5 * a->ac * inv;
+    acc[(M_ROWS) * STRIDE] += 1.0;
 }
+
+PPCR_HD void row_end(const RowAcc* a, double sx, double sy, double sz, double* acc) { row_end_s<1>(a, sx, sy, sz, acc); }
 
 // ---- fast path ------------------------------------------------------------------------------------------------
 //
@@ -277,7 +282,8 @@ PPCR_HD void rowf_add(RowAccF* a, const WeightCfg& wc, float yx, float yy, float
     a->ac += pw_ * r2e;
 }
 
-PPCR_HD void rowf_end(const RowAccF* a, double sx, double sy, double sz, double* acc)
+template <int STRIDE>
+PPCR_HD void rowf_end_s(const RowAccF* a, double sx, double sy, double sz, double* acc)
 {
     RowAcc d;
     d.m = a->m;
@@ -287,8 +293,9 @@ PPCR_HD void rowf_end(const RowAccF* a, double sx, double sy, double sz, double*
     d.ar[1] = a->ar[1];
     d.ar[2] = a->ar[2];
     d.ac = a->ac;
-    row_end(&d, sx, sy, sz, acc);
+    row_end_s<STRIDE>(&d, sx, sy, sz, acc);
 }
+PPCR_HD void rowf_end(const RowAccF* a, double sx, double sy, double sz, double* acc) { rowf_end_s<1>(a, sx, sy, sz, acc); }
 
 PPCR_HD float rowf_finished_weight(const RowAccF* a, const WeightCfg& wc, float yx, float yy, float yz, const PointHL& pw)
 {

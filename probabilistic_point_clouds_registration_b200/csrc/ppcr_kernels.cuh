@@ -36,8 +36,11 @@ namespace ppcr {
 
 constexpr int kSearchThreads = 128;  // one query per thread
 constexpr int kEvalThreads = 256;
+#ifndef PPCR_EVAL_BATCH
+#define PPCR_EVAL_BATCH 5
+#endif
 #ifndef PPCR_EVAL_MIN_BLOCKS
-#define PPCR_EVAL_MIN_BLOCKS 2  // resident blocks per SM the register allocation of k_evalctl is held to
+#define PPCR_EVAL_MIN_BLOCKS 4  // resident blocks per SM the register allocation of k_evalctl is held to
 #endif
 constexpr int kMailDoubles = 32;  // 24 moments + K + sequence stamp, padded
 constexpr unsigned kFull = 0xffffffffu;
@@ -552,9 +555,12 @@ __global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(
     const Pose& pe = s_pe;
     const Pose& pw = s_pw;
     const WeightCfg wc = P.wcfg;
-    double acc[kNSum];
+    // the 24 float64 accumulators of a thread live in shared memory (one column per thread, conflict-free): they are
+    // touched once per row, and keeping them out of the register file leaves room to have a whole row in flight
+    extern __shared__ double s_acc[];
+    double* acc = s_acc + threadIdx.x;
 #pragma unroll
-    for (int k = 0; k < kNSum; ++k) acc[k] = 0.0;
+    for (int k = 0; k < kNSum; ++k) acc[k * kEvalThreads] = 0.0;
     const int stride = P.n_eval_blocks * kEvalThreads;
     const size_t n_pad = P.n_pad;
     if constexpr (kFast) {
@@ -579,7 +585,7 @@ __global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(
             }
             RowAccF row;
             rowf_begin(&row);
-            constexpr int kU = 5;  // records of kU correspondences are in flight before their arithmetic
+            constexpr int kU = PPCR_EVAL_BATCH;  // records of kU correspondences are in flight before their arithmetic
             const float4* rec = P.nbr + i;
             for (int k0 = 0; k0 < cnt; k0 += kU) {
                 float4 y[kU];
@@ -591,7 +597,7 @@ __global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(
                 for (int u = 0; u < kU; ++u)
                     if (k0 + u < cnt) rowf_add(&row, wc, y[u].x, y[u].y, y[u].z, he, hw, same);
             }
-            rowf_end(&row, sx, sy, sz, acc);
+            rowf_end_s<kEvalThreads>(&row, sx, sy, sz, acc);
         }
     } else {
         for (int i = blockIdx.x * kEvalThreads + threadIdx.x; i < P.n_src; i += stride) {
@@ -609,14 +615,14 @@ __global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(
                 const float4 y = __ldg(P.nbr + o);
                 row_add<false>(&row, wc, y.x, y.y, y.z, pte, ptw);
             }
-            row_end(&row, sx, sy, sz, acc);
+            row_end_s<kEvalThreads>(&row, sx, sy, sz, acc);
         }
     }
     // fixed-shape reduction: xor-shuffle tree inside the warp, then warps in index order
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < kNSum; ++k) {
-        double v = acc[k];
+        double v = acc[k * kEvalThreads];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
         if (lane == 0) s_red[warp][k] = v;
     }
