@@ -121,7 +121,8 @@ ppcr_status ppcr_filtered_source(ppcr_handle* h, float* out_xyzw, int64_t* n_ino
 ppcr_status ppcr_filtered_target(ppcr_handle* h, float* out_xyzw, int64_t* n_inout);
 
 /* Current data association of the handle (the CSR pattern of :69-83), for parity tests:
- * idx is [n_src][max_neighbours] in source order, rows sorted by (d2, index); count[n_src]. */
+ * idx is [n_src][max_neighbours] in source order, each row sorted by target index (the column order of the
+ * reference's CSR after setFromTriplets, :82-83), padded with -1; count[n_src]. */
 ppcr_status ppcr_association(ppcr_handle* h, int32_t* idx, int32_t* count, int64_t n_src, int32_t max_neighbours);
 
 ppcr_status ppcr_get_stage_times(ppcr_handle* h, ppcr_stage_times* out);

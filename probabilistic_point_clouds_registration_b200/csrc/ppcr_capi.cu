@@ -185,7 +185,7 @@ struct Engine {
     DevBuf<LoopCtl> d_loop;
     int* h_active = nullptr;  // pinned, shared by the handles of a host thread (pinned_flag)
     int eval_blocks_per_sm = PPCR_EVAL_MIN_BLOCKS, search_blocks_per_sm = 8;
-    int list_cap = 0;  // register capacity of the search kernel's top-m list; 0 = local-memory list (m > 32)
+    size_t search_smem = 0;  // the search kernel's per-block heap columns
     // launch geometry (capacity based, so a captured graph stays valid while the slots are refilled)
     int max_tiles = 1, max_eval_blocks = 1, max_tr_blocks = 1;
     bool skip_search = false;
@@ -640,9 +640,14 @@ static void engine_commit(Engine& E)
     E.d_pairs.reserve(np);
     CK(cudaMemcpyAsync(E.d_pairs.p, host.data(), sizeof(PairDev) * np, cudaMemcpyHostToDevice, E.stream));
     CK(cudaStreamSynchronize(E.stream));
-    const int cap_m = E.params.max_neighbours;
-    E.list_cap = cap_m <= 4 ? 4 : cap_m <= 8 ? 8 : cap_m <= 12 ? 12 : cap_m <= 16 ? 16 : cap_m <= 20 ? 20
-               : cap_m <= 24 ? 24 : cap_m <= 32 ? 32 : 0;
+    E.search_smem = static_cast<size_t>(E.params.max_neighbours) * kSearchThreads * sizeof(unsigned long long);
+    if (E.search_smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.search_smem)));
+    {   // persistent grid: exactly as many blocks as the device keeps resident
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search, kSearchThreads, E.search_smem));
+        E.search_blocks_per_sm = std::max(1, per_sm);
+    }
     const int tiles = std::max(1, std::min(ceil_div(max_src, kSearchChunk), E.search_blocks_per_sm * std::max(g_sm_count, 1)));
     const int trb = std::max(1, std::min(ceil_div(max_src, 256), 8 * std::max(g_sm_count, 1)));
     if (tiles > E.max_tiles || max_eval > E.max_eval_blocks || trb > E.max_tr_blocks) {
@@ -688,16 +693,7 @@ static void launch_search(Engine& E)
 {
     const int np = static_cast<int>(E.pairs.size());
     dim3 grid(E.max_tiles, np);
-    switch (E.list_cap) {
-        case 4: k_search<4><<<grid, kSearchThreads, 0, E.stream>>>(E.d_pairs.p); break;
-        case 8: k_search<8><<<grid, kSearchThreads, 0, E.stream>>>(E.d_pairs.p); break;
-        case 12: k_search<12><<<grid, kSearchThreads, 0, E.stream>>>(E.d_pairs.p); break;
-        case 16: k_search<16><<<grid, kSearchThreads, 0, E.stream>>>(E.d_pairs.p); break;
-        case 20: k_search<20><<<grid, kSearchThreads, 0, E.stream>>>(E.d_pairs.p); break;
-        case 24: k_search<24><<<grid, kSearchThreads, 0, E.stream>>>(E.d_pairs.p); break;
-        case 32: k_search<32><<<grid, kSearchThreads, 0, E.stream>>>(E.d_pairs.p); break;
-        default: k_search<0><<<grid, kSearchThreads, 0, E.stream>>>(E.d_pairs.p); break;
-    }
+    k_search<<<grid, kSearchThreads, E.search_smem, E.stream>>>(E.d_pairs.p);
 }
 
 // weights + moments + (in its last block) reduction, controller and loop condition
@@ -912,14 +908,21 @@ static void download_association(Engine& E, int p, int32_t* idx, float* d2, int3
     CK(cudaStreamSynchronize(E.stream));
     for (size_t k = 0; k < h_rec.size(); ++k) memcpy(&h_idx[k], &h_rec[k].w, 4);
     const std::vector<int> order = source_order(E, p);
+    // rows sit on the device in heap order: hand them out sorted by (d2, index) when distances were recorded
+    // (FLANN's result order), by target index otherwise (the column order of the reference's CSR, :82-83)
+    std::vector<std::pair<float, int>> row;
     for (int64_t j = 0; j < n_src; ++j) {  // device row j is the caller's point order[j]
         const int64_t i = order[j];
-        const int c = h_cnt[j];
+        const int c = std::min(h_cnt[j], D.m);
         count[i] = c;
+        row.clear();
+        for (int k = 0; k < c; ++k)
+            row.push_back({d2 ? h_d2[static_cast<size_t>(k) * D.n_pad + j] : 0.f, h_idx[static_cast<size_t>(k) * D.n_pad + j]});
+        std::sort(row.begin(), row.end());
         for (int k = 0; k < max_nn; ++k) {
-            const bool have = k < c && k < D.m;
-            idx[i * max_nn + k] = have ? h_idx[static_cast<size_t>(k) * D.n_pad + j] : -1;
-            if (d2) d2[i * max_nn + k] = have ? h_d2[static_cast<size_t>(k) * D.n_pad + j] : 0.f;
+            const bool have = k < c;
+            idx[i * max_nn + k] = have ? row[k].second : -1;
+            if (d2) d2[i * max_nn + k] = have ? row[k].first : 0.f;
         }
     }
 }

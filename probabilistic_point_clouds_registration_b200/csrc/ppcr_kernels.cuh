@@ -329,10 +329,13 @@ constexpr int kSearchChunk = kSearchThreads;  // queries handed out per grab of 
 // follows a pose update -- and the warm start of the pruning bound: the m targets found last time lie within
 // sqrt(d_m) + |dx| of the moved query, so nothing farther than that can be among the m nearest now.
 //
-// CAP > 0: list of CAP registers (m <= CAP).  CAP == 0: any m, list in local memory.
-template <int CAP>
+// The m best candidates of a query live in a binary max-heap in shared memory (one column per thread, m * 8 bytes of
+// dynamic shared memory per thread): replacing the root and sifting down costs ~log2(m) steps, about half the
+// instructions of a sorted register list at m = 10..20, and works for any m.  Rows are stored in heap order; nothing
+// downstream depends on the order inside a row (the host sorts rows it hands out).
 __global__ void __launch_bounds__(kSearchThreads) k_search(const PairDev* __restrict__ pairs)
 {
+    extern __shared__ unsigned long long s_heap[];
     const PairDev& P = pairs[blockIdx.y];
     PairState* st = P.state;
     if (st->phase != PH_SEARCH) return;
@@ -370,33 +373,15 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(const PairDev* __rest
         }
         int cnt = 0;
         float kth = __int_as_float(0x7f800000);
-        if constexpr (CAP > 0) {
-            TopList<CAP> L;
-            L.init(m);
-            tree_search(P.tree, P.nodes, P.tgt_sorted, q.x, q.y, q.z, P.r2f, bound0, L, stack);
-#pragma unroll
-            for (int s = 0; s < CAP; ++s) {
-                const int e = m - 1 - s;  // ascending rank of slot s
-                if (e >= 0 && L.k[s] != kKeyInf) {
-                    search_store(P, i, e, L.k[s]);
-                    ++cnt;
-                }
-            }
-            if (L.k[0] != kKeyInf) kth = key_d2(L.k[0]);
-        } else {
-            unsigned long long buf[128];
-            TopListDyn L;
-            L.k = buf;
-            L.init(m);
-            tree_search(P.tree, P.nodes, P.tgt_sorted, q.x, q.y, q.z, P.r2f, bound0, L, stack);
-            for (int s = 0; s < m; ++s) {
-                if (buf[s] != kKeyInf) {
-                    search_store(P, i, m - 1 - s, buf[s]);
-                    ++cnt;
-                }
-            }
-            if (buf[0] != kKeyInf) kth = key_d2(buf[0]);
+        HeapList<kSearchThreads> L;
+        L.k = s_heap + threadIdx.x;
+        L.init(m);
+        tree_search(P.tree, P.nodes, P.tgt_sorted, q.x, q.y, q.z, P.r2f, bound0, L, stack);
+        for (int s = 0; s < m; ++s) {
+            const unsigned long long key = L.k[s * kSearchThreads];
+            if (key != kKeyInf) search_store(P, i, cnt++, key);
         }
+        if (L.k[0] != kKeyInf) kth = key_d2(L.k[0]);
         P.nbr_cnt[i] = cnt;
         P.nbr_kth[i] = kth;
         cnt_total += cnt;

@@ -251,6 +251,42 @@ struct TopListDyn {
     }
 };
 
+// binary max-heap of the m best keys in addressable memory, element i at k[i * STRIDE] (the search kernel keeps one
+// column per thread in shared memory, STRIDE = block size).  worst() is the root; entries come out unordered.
+template <int STRIDE>
+struct HeapList {
+    unsigned long long* k;
+    int m;
+    PPCR_HD void init(int m_)
+    {
+        m = m_;
+        for (int i = 0; i < m; ++i) k[i * STRIDE] = kKeyInf;
+    }
+    PPCR_HD unsigned long long worst() const { return k[0]; }
+    // pre: x < k[0].  Replaces the root and sifts down.
+    PPCR_HD void insert(unsigned long long x)
+    {
+        int i = 0;
+        for (;;) {
+            const int l = 2 * i + 1;
+            if (l >= m) break;
+            unsigned long long vc = k[l * STRIDE];
+            int c = l;
+            if (l + 1 < m) {
+                const unsigned long long vr = k[(l + 1) * STRIDE];
+                if (vr > vc) {
+                    vc = vr;
+                    c = l + 1;
+                }
+            }
+            if (vc <= x) break;
+            k[i * STRIDE] = vc;
+            i = c;
+        }
+        k[i * STRIDE] = x;
+    }
+};
+
 // ---- traversal -----------------------------------------------------------------------------------------------
 
 // squared distance from q to the interval [c - hi, c + hi] along one axis

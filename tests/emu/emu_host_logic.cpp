@@ -188,7 +188,7 @@ void emu_normal_eq(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, 
 
 // The product's octree (csrc/ppcr_tree.h): serial build with the same split routine the build kernel calls, then the
 // same traversal the search kernel runs, one query at a time.  Rows come back sorted ascending by (d2, index).
-// list_kind: 0 = register list sized like the kernel's dispatch, 1 = the addressable list used for m > 32.
+// list_kind: 0 = sorted register list, 1 = sorted addressable list, 2 = max-heap (what the search kernel uses).
 int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, int64_t n_tgt, double radius,
                         int max_nn, int leaf_cap, int list_kind, const float* bounds, int* out_idx, float* out_d2,
                         int* out_cnt, int* out_n_nodes)
@@ -280,6 +280,13 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
                 default: EMU_RUN(32) break;
             }
 #undef EMU_RUN
+        } else if (list_kind == 2) {  // the search kernel's list: a max-heap (one column per thread on the device)
+            HeapList<1> L;
+            L.k = buf.data();
+            L.init(m);
+            tree_search(g, nodes.data(), pts.data(), q[0], q[1], q[2], r2f, bound0, L, stack);
+            for (int s2 = 0; s2 < m; ++s2)
+                if (buf[s2] != kKeyInf) found.push_back(buf[s2]);
         } else {
             TopListDyn L;
             L.k = buf.data();

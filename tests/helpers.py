@@ -71,7 +71,7 @@ def rows_as_sets(idx, cnt):
     return [frozenset(idx[i, :cnt[i]].tolist()) for i in range(len(cnt))]
 
 
-def emu_tree_search(lib, src, tgt, radius, m, leaf_cap=32, list_kind=0, bounds=None):
+def emu_tree_search(lib, src, tgt, radius, m, leaf_cap=32, list_kind=2, bounds=None):
     """The product's octree build + traversal (csrc/ppcr_tree.h) compiled for the CPU.  bounds: optional per-query
     squared distance within which m targets are known to lie (the warm start of the search kernel)."""
     src = np.ascontiguousarray(src, dtype=np.float32)

@@ -32,10 +32,12 @@ def test_result_independent_of_tree_shape(emu, oracle, leaf):
     assert (n_nodes == 1) == (leaf == 100000)
 
 
-def test_lidar_with_outliers_and_both_list_kinds(emu, oracle):
+def test_lidar_with_outliers_and_all_list_kinds(emu, oracle):
     src, tgt, _ = synth.lidar_pair(7, 32, 600, outlier_frac=0.2)
-    _check(emu, oracle, src, tgt, 3.0, 20)
+    _check(emu, oracle, src, tgt, 3.0, 20, list_kind=2)
+    _check(emu, oracle, src, tgt, 3.0, 20, list_kind=0)
     _check(emu, oracle, src, tgt, 0.5, 10, list_kind=1)
+    _check(emu, oracle, src, tgt, 3.0, 50, list_kind=2)
 
 
 @pytest.mark.parametrize("m", [3, 5, 20])
