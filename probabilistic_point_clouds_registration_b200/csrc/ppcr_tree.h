@@ -118,6 +118,15 @@ PPCR_HD unsigned long long make_key(float d2, int idx)
 PPCR_HD float key_d2(unsigned long long k) { return bits_float(static_cast<uint32_t>((k - 1ull) >> 32)); }
 PPCR_HD int key_index(unsigned long long k) { return static_cast<int>(static_cast<uint32_t>(k - 1ull)); }
 
+PPCR_HD int lowest_bit(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs(static_cast<int>(v)) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+
 // ---- Morton keys ---------------------------------------------------------------------------------------------
 
 PPCR_HD unsigned long long spread3(uint32_t v)  // 16 bits -> every third bit
@@ -323,29 +332,35 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
         const TreeNode n = nodes[stack[2 * sp]];
         if (n.end <= n.begin) continue;
         if (n.child < 0) {
-            // leaf: run ahead to the next candidate that enters the list, then insert.  Written as two nested loops so
-            // that the threads of a warp meet again at the (expensive) insertion instead of serialising it.
-            int j = n.begin;
-            for (;;) {
-                unsigned long long key = kKeyInf;
-                while (j < n.end) {
-                    const float4 p = pts[j++];
+            // Leaf, 32 points at a time, in two passes so that the threads of a warp stay together: first a plain
+            // distance test of every point against the current bound (a bit per survivor, nothing else), then the
+            // survivors -- re-read from L1 -- go through the list one after the other.  The expensive, divergent part
+            // (the heap update) is thereby reached by all threads at the same time instead of point by point.
+            for (int j0 = n.begin; j0 < n.end; j0 += 32) {
+                const int cnt = n.end - j0 < 32 ? n.end - j0 : 32;
+                uint32_t pass = 0;
+                for (int t = 0; t < cnt; ++t) {
+                    const float4 p = pts[j0 + t];
                     const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
-                    if (d2 <= bound_d2) {
+                    if (d2 <= bound_d2) pass |= 1u << t;
+                }
+                while (pass) {
+                    const int t = lowest_bit(pass);
+                    pass &= pass - 1;
+                    const float4 p = pts[j0 + t];
+                    const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+                    if (d2 <= bound_d2) {  // the bound may have shrunk since the first pass
                         const unsigned long long k2 = make_key(d2, static_cast<int>(float_bits(p.w)));
                         if (k2 <= r2key && k2 < L.worst()) {  // k2 <= r2key  <=>  d2 < r2f (keys carry +1)
-                            key = k2;
-                            break;
+                            L.insert(k2);
+                            const unsigned long long w = L.worst();
+                            if (w != kKeyInf) {
+                                const float wd = key_d2(w);
+                                bound_d2 = wd < bound_d2 ? wd : bound_d2;
+                                thr = prune_threshold(bound_d2);
+                            }
                         }
                     }
-                }
-                if (key == kKeyInf) break;
-                L.insert(key);
-                const unsigned long long w = L.worst();
-                if (w != kKeyInf) {
-                    const float wd = key_d2(w);
-                    bound_d2 = wd < bound_d2 ? wd : bound_d2;
-                    thr = prune_threshold(bound_d2);
                 }
             }
             continue;
