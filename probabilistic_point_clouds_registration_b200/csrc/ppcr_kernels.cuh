@@ -296,6 +296,12 @@ __global__ void k_tree_split_level(TreeGeom g, const unsigned long long* __restr
     }
 }
 
+__global__ void k_tree_finalize(TreeNode* __restrict__ nodes, const TreeCounters* __restrict__ tc, int cap)
+{
+    const int n = min(tc->n_nodes, cap);
+    for (int ni = blockIdx.x * blockDim.x + threadIdx.x; ni < n; ni += gridDim.x * blockDim.x) tree_mark_leaf_children(nodes, ni);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // radius search: one thread per query walks the octree with a register-resident sorted top-m list
 // ------------------------------------------------------------------------------------------------------------

@@ -48,7 +48,7 @@ struct TreeNode {       // 32 bytes
     float half;         // half edge (not inflated)
     int begin, end;     // range in the Morton-sorted target
     int child;          // first of 8 consecutive children, -1 = leaf
-    int mask;           // bits 0..7: non-empty children; bits 8..15: level
+    int mask;           // bits 0..7: non-empty children; bits 8..15: level; bits 16..23: children that are leaves
 };
 
 // ---- bit-exact float helpers ---------------------------------------------------------------------------------
@@ -260,6 +260,18 @@ struct TopListDyn {
     }
 };
 
+// After the build: every inner node learns which of its children are leaves (bits 16..23 of mask), so that the
+// traversal can sort children into "open later" and "scan later" without loading them.
+PPCR_HD void tree_mark_leaf_children(TreeNode* nodes, int ni)
+{
+    const int child = nodes[ni].child;
+    if (child < 0) return;
+    int bits = 0;
+    for (int c = 0; c < 8; ++c)
+        if (nodes[child + c].child < 0) bits |= 1 << (16 + c);
+    nodes[ni].mask = (nodes[ni].mask & 0xffff) | bits;
+}
+
 // binary max-heap of the m best keys in addressable memory, element i at k[i * STRIDE] (the search kernel keeps one
 // column per thread in shared memory, STRIDE = block size).  worst() is the root; entries come out unordered.
 template <int STRIDE>
@@ -321,21 +333,74 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
     const unsigned long long r2key = static_cast<unsigned long long>(float_bits(r2f)) << 32;  // keys of d2 >= r2f are > this
     float bound_d2 = bound0 < r2f ? bound0 : r2f;  // no unseen point farther than this can enter the list
     float thr = prune_threshold(bound_d2);
-    int sp = 0;
-    stack[0] = 0;
-    stack[1] = 0;  // float bits of 0.0f
-    sp = 1;
-    while (sp > 0) {
-        --sp;
-        // the bound may have shrunk since this node was pushed: re-test with the lower bound stored beside it
-        if (bits_float(static_cast<uint32_t>(stack[2 * sp + 1])) > thr) continue;
-        const TreeNode n = nodes[stack[2 * sp]];
-        if (n.end <= n.begin) continue;
-        if (n.child < 0) {
-            // Leaf, 32 points at a time, in two passes so that the threads of a warp stay together: first a plain
-            // distance test of every point against the current bound (a bit per survivor, nothing else), then the
-            // survivors -- re-read from L1 -- go through the list one after the other.  The expensive, divergent part
-            // (the heap update) is thereby reached by all threads at the same time instead of point by point.
+    // Two kinds of work alternate, each done by all threads of a warp at the same time: opening inner nodes (their
+    // leaf children go to a short pending list, the inner ones back on the stack) and scanning pending leaves.
+    constexpr int kPend = 16;
+    int pend[2 * kPend];
+    int sp = 0, np = 0;
+    {
+        const TreeNode root = nodes[0];
+        if (root.end <= root.begin) return;
+        if (root.child < 0) {
+            pend[0] = 0;
+            pend[1] = 0;  // float bits of 0.0f
+            np = 1;
+        } else {
+            stack[0] = 0;
+            stack[1] = 0;
+            sp = 1;
+        }
+    }
+    for (;;) {
+        // ---- open inner nodes until the stack is empty or the pending list could overflow ----
+        while (sp > 0 && np <= kPend - 8) {
+            --sp;
+            // the bound may have shrunk since this node was pushed: re-test with the lower bound stored beside it
+            if (bits_float(static_cast<uint32_t>(stack[2 * sp + 1])) > thr) continue;
+            const TreeNode n = nodes[stack[2 * sp]];
+            // Children far-to-near, so that the octant holding q is opened / scanned first.  The lower bound of a
+            // child box is a sum of three per-axis gaps, each of which takes one of two values (the child's half on
+            // q's side of the centre plane, or the other one): six gaps serve all eight children.
+            const int oct = (qx >= n.cx ? 1 : 0) | (qy >= n.cy ? 2 : 0) | (qz >= n.cz ? 4 : 0);
+            const float ch = n.half * 0.5f;
+            const float hi = ch + g.slack;
+            const float gx_lo = axis_gap2(qx, n.cx - ch, hi), gx_hi = axis_gap2(qx, n.cx + ch, hi);
+            const float gy_lo = axis_gap2(qy, n.cy - ch, hi), gy_hi = axis_gap2(qy, n.cy + ch, hi);
+            const float gz_lo = axis_gap2(qz, n.cz - ch, hi), gz_hi = axis_gap2(qz, n.cz + ch, hi);
+            const float nx = (oct & 1) ? gx_hi : gx_lo, fx = (oct & 1) ? gx_lo : gx_hi;  // near / far side per axis
+            const float ny = (oct & 2) ? gy_hi : gy_lo, fy = (oct & 2) ? gy_lo : gy_hi;
+            const float nz = (oct & 4) ? gz_hi : gz_lo, fz = (oct & 4) ? gz_lo : gz_hi;
+            const int mask = n.mask;
+#pragma unroll
+            for (int k = 7; k >= 0; --k) {
+                const int c = oct ^ k;
+                const float lb = ((k & 1) ? fx : nx) + ((k & 2) ? fy : ny) + ((k & 4) ? fz : nz);
+                if (((mask >> c) & 1) && !(lb > thr)) {
+                    if ((mask >> (16 + c)) & 1) {  // a leaf
+                        pend[2 * np] = n.child + c;
+                        pend[2 * np + 1] = static_cast<int>(float_bits(lb));
+                        ++np;
+                    } else {
+                        stack[2 * sp] = n.child + c;
+                        stack[2 * sp + 1] = static_cast<int>(float_bits(lb));
+                        ++sp;
+                    }
+                }
+            }
+        }
+        if (np == 0) {
+            if (sp == 0) break;
+            continue;
+        }
+        // ---- scan the pending leaves, nearest (appended last) first ----
+        while (np > 0) {
+            --np;
+            if (bits_float(static_cast<uint32_t>(pend[2 * np + 1])) > thr) continue;
+            const TreeNode n = nodes[pend[2 * np]];
+            // 32 points at a time, in two passes so that the threads of a warp stay together: first a plain distance
+            // test of every point against the current bound (a bit per survivor, nothing else), then the survivors --
+            // re-read from L1 -- go through the list one after the other.  The expensive, divergent part (the heap
+            // update) is thereby reached by all threads at the same time instead of point by point.
             for (int j0 = n.begin; j0 < n.end; j0 += 32) {
                 const int cnt = n.end - j0 < 32 ? n.end - j0 : 32;
                 uint32_t pass = 0;
@@ -362,30 +427,6 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
                         }
                     }
                 }
-            }
-            continue;
-        }
-        // Children, pushed far-to-near so that the octant holding q is opened first.  The lower bound of a child box
-        // is a sum of three per-axis gaps, each of which takes one of two values (the child's half on q's side of
-        // the centre plane, or the other one): six gaps serve all eight children.
-        const int oct = (qx >= n.cx ? 1 : 0) | (qy >= n.cy ? 2 : 0) | (qz >= n.cz ? 4 : 0);
-        const float ch = n.half * 0.5f;
-        const float hi = ch + g.slack;
-        const float gx_lo = axis_gap2(qx, n.cx - ch, hi), gx_hi = axis_gap2(qx, n.cx + ch, hi);
-        const float gy_lo = axis_gap2(qy, n.cy - ch, hi), gy_hi = axis_gap2(qy, n.cy + ch, hi);
-        const float gz_lo = axis_gap2(qz, n.cz - ch, hi), gz_hi = axis_gap2(qz, n.cz + ch, hi);
-        const float nx = (oct & 1) ? gx_hi : gx_lo, fx = (oct & 1) ? gx_lo : gx_hi;  // near / far side per axis
-        const float ny = (oct & 2) ? gy_hi : gy_lo, fy = (oct & 2) ? gy_lo : gy_hi;
-        const float nz = (oct & 4) ? gz_hi : gz_lo, fz = (oct & 4) ? gz_lo : gz_hi;
-        const int mask = n.mask;
-#pragma unroll
-        for (int k = 7; k >= 0; --k) {
-            const int c = oct ^ k;
-            const float lb = ((k & 1) ? fx : nx) + ((k & 2) ? fy : ny) + ((k & 4) ? fz : nz);
-            if (((mask >> c) & 1) && !(lb > thr)) {
-                stack[2 * sp] = n.child + c;
-                stack[2 * sp + 1] = static_cast<int>(float_bits(lb));
-                ++sp;
             }
         }
     }
