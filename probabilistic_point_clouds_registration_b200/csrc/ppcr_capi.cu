@@ -141,7 +141,7 @@ static inline void note_launches(int n) { *g_launch_sink += n; }
 struct Pair {
     DevBuf<float4> src, tgt_raw, tgt_sorted, tmp_cloud;
     DevBuf<int> nbr_cnt, scan_sums;
-    DevBuf<float4> nbr;
+    DevBuf<int> nbr_pos, inv_perm;
     DevBuf<TreeNode> nodes;
     DevBuf<TreeCounters> tree_counters;
     DevBuf<unsigned long long> sort_keys[2];
@@ -162,7 +162,7 @@ struct Pair {
     {
         src.release(); tgt_raw.release(); tgt_sorted.release(); tmp_cloud.release();
         nodes.release(); tree_counters.release(); sort_keys[0].release(); sort_keys[1].release();
-        sort_vals[0].release(); sort_vals[1].release(); sort_tmp.release(); nbr.release(); nbr_cnt.release();
+        sort_vals[0].release(); sort_vals[1].release(); sort_tmp.release(); nbr_pos.release(); inv_perm.release(); nbr_cnt.release();
         scan_sums.release(); nbr_d2.release(); nbr_kth.release();
         partials.release(); history.release(); mailbox.release(); state.release(); cfg.release(); stats.release();
         scratch_u.release(); scratch_ull.release();
@@ -379,7 +379,8 @@ static void build_target_tree(Engine& E, Pair& P, int leaf_cap)
     const TreeGeom g = make_tree_geom(bb, leaf_cap, n);
     morton_sort(P, P.tgt_raw.p, n, g, st);
     P.tgt_sorted.reserve(n);
-    k_tree_gather<<<ceil_div(n, 256), 256, 0, st>>>(P.tgt_raw.p, P.sort_vals[1].p, n, 0, P.tgt_sorted.p);
+    P.inv_perm.reserve(n);
+    k_tree_gather<<<ceil_div(n, 256), 256, 0, st>>>(P.tgt_raw.p, P.sort_vals[1].p, n, 0, P.tgt_sorted.p, P.inv_perm.p);
     CK(cudaGetLastError());
     P.nodes.reserve(static_cast<size_t>(g.n_nodes_cap) + 8);
     P.tree_counters.reserve(1);
@@ -398,6 +399,7 @@ static void build_target_tree(Engine& E, Pair& P, int leaf_cap)
     P.dev.nodes = P.nodes.p;
     P.dev.tgt_sorted = P.tgt_sorted.p;
     P.dev.tgt_raw = P.tgt_raw.p;
+    P.dev.inv_perm = P.inv_perm.p;
 }
 
 // Sorts the (tagged) source cloud along the target tree's Morton curve: the queries of one warp then open the same
@@ -409,7 +411,7 @@ static void sort_source(Engine& E, Pair& P)
     if (n <= 1) return;
     morton_sort(P, P.src.p, n, P.dev.tree, st);
     P.tmp_cloud.reserve(n);
-    k_tree_gather<<<ceil_div(n, 256), 256, 0, st>>>(P.src.p, P.sort_vals[1].p, n, 1, P.tmp_cloud.p);
+    k_tree_gather<<<ceil_div(n, 256), 256, 0, st>>>(P.src.p, P.sort_vals[1].p, n, 1, P.tmp_cloud.p, nullptr);
     CK(cudaGetLastError());
     note_launches(1);
     std::swap(P.src, P.tmp_cloud);
@@ -547,18 +549,20 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
         D.nodes = P.nodes.p;
         D.tgt_sorted = P.tgt_sorted.p;
         D.tgt_raw = P.tgt_raw.p;
+        P.inv_perm.reserve(1);
+        D.inv_perm = P.inv_perm.p;
     }
     sort_source(E, P);
     D.src = P.src.p;
     tr.mark("source sort");
     const size_t plane = static_cast<size_t>(D.m) * D.n_pad;
-    P.nbr.reserve(plane);
+    P.nbr_pos.reserve(plane);
     P.nbr_cnt.reserve(D.n_pad);
     P.nbr_kth.reserve(D.n_pad);
     D.nbr_kth = P.nbr_kth.p;
     CK(cudaMemsetAsync(P.nbr_kth.p, 0x7f, static_cast<size_t>(D.n_pad) * sizeof(float), st));  // "nothing known yet"
     if (P.want_d2) P.nbr_d2.reserve(plane);
-    D.nbr = P.nbr.p;
+    D.nbr_pos = P.nbr_pos.p;
     D.nbr_d2 = P.want_d2 ? P.nbr_d2.p : nullptr;
     D.nbr_cnt = P.nbr_cnt.p;
     CK(cudaMemsetAsync(P.nbr_cnt.p, 0, static_cast<size_t>(D.n_pad) * sizeof(int), st));
@@ -643,10 +647,13 @@ static void engine_commit(Engine& E)
     CK(cudaStreamSynchronize(E.stream));
     E.search_smem = static_cast<size_t>(E.params.max_neighbours) * kSearchThreads * sizeof(unsigned long long);
     if (E.search_smem > 48 * 1024)
-        CK(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.search_smem)));
+    {
+        CK(cudaFuncSetAttribute(k_search<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.search_smem)));
+        CK(cudaFuncSetAttribute(k_search<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.search_smem)));
+    }
     {   // persistent grid: exactly as many blocks as the device keeps resident
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search, kSearchThreads, E.search_smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search<1>, kSearchThreads, E.search_smem));
         E.search_blocks_per_sm = std::max(1, per_sm);
     }
     const int tiles = std::max(1, std::min(ceil_div(max_src, kSearchChunk), E.search_blocks_per_sm * std::max(g_sm_count, 1)));
@@ -694,18 +701,21 @@ static void launch_search(Engine& E)
 {
     const int np = static_cast<int>(E.pairs.size());
     dim3 grid(E.max_tiles, np);
-    k_search<<<grid, kSearchThreads, E.search_smem, E.stream>>>(E.d_pairs.p);
+    static const int variant = getenv("PPCR_SEARCH_VARIANT") ? atoi(getenv("PPCR_SEARCH_VARIANT")) : 0;  // tuning only
+    if (variant & 1) k_search<1><<<grid, kSearchThreads, E.search_smem, E.stream>>>(E.d_pairs.p);
+    else k_search<0><<<grid, kSearchThreads, E.search_smem, E.stream>>>(E.d_pairs.p);
 }
 
 // weights + moments + (in its last block) reduction, controller and loop condition
-static void launch_evalctl(Engine& E, bool use_cond)
+static void launch_evalctl(Engine& E, bool use_cond, int probe = 0)
 {
     const int np = static_cast<int>(E.pairs.size());
     dim3 grid(E.max_eval_blocks, np);
+    const int flags = (use_cond ? 1 : 0) | probe;
     if (!E.opts.exact_weights)
-        k_evalctl<true><<<grid, kEvalThreads, kEvalSmem, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, use_cond ? 1 : 0, E.max_ticks);
+        k_evalctl<true><<<grid, kEvalThreads, kEvalSmem, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, flags, E.max_ticks);
     else
-        k_evalctl<false><<<grid, kEvalThreads, kEvalSmem, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, use_cond ? 1 : 0, E.max_ticks);
+        k_evalctl<false><<<grid, kEvalThreads, kEvalSmem, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, flags, E.max_ticks);
 }
 
 static int launches_per_tick(const Engine& E) { return E.skip_search ? 1 : 2; }
@@ -896,10 +906,12 @@ static void download_association(Engine& E, int p, int32_t* idx, float* d2, int3
     Pair& P = E.pairs[p];
     const PairDev& D = P.dev;
     if (n_src != D.n_src) throw StatusError{PPCR_ERR_INVALID, "n_src does not match the handle's (filtered) source size"};
-    std::vector<float4> h_rec(static_cast<size_t>(D.m) * D.n_pad);
-    std::vector<int> h_idx(h_rec.size()), h_cnt(D.n_pad);
+    std::vector<int> h_idx(static_cast<size_t>(D.m) * D.n_pad), h_cnt(D.n_pad);
+    std::vector<float4> h_tbl(static_cast<size_t>(std::max(D.n_tgt, 1)));
     std::vector<float> h_d2;
-    CK(cudaMemcpyAsync(h_rec.data(), D.nbr, h_rec.size() * sizeof(float4), cudaMemcpyDeviceToHost, E.stream));
+    CK(cudaMemcpyAsync(h_idx.data(), D.nbr_pos, h_idx.size() * sizeof(int), cudaMemcpyDeviceToHost, E.stream));
+    if (D.n_tgt > 0)
+        CK(cudaMemcpyAsync(h_tbl.data(), D.tgt_sorted, static_cast<size_t>(D.n_tgt) * sizeof(float4), cudaMemcpyDeviceToHost, E.stream));
     CK(cudaMemcpyAsync(h_cnt.data(), D.nbr_cnt, h_cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, E.stream));
     if (d2) {
         if (!D.nbr_d2) throw StatusError{PPCR_ERR_INVALID, "distances were not recorded"};
@@ -907,8 +919,12 @@ static void download_association(Engine& E, int p, int32_t* idx, float* d2, int3
         CK(cudaMemcpyAsync(h_d2.data(), D.nbr_d2, h_d2.size() * sizeof(float), cudaMemcpyDeviceToHost, E.stream));
     }
     CK(cudaStreamSynchronize(E.stream));
-    for (size_t k = 0; k < h_rec.size(); ++k) memcpy(&h_idx[k], &h_rec[k].w, 4);
     const std::vector<int> order = source_order(E, p);
+    auto original_index = [&](int pos) {  // the device stores positions in the Morton-sorted target
+        int idx_out = -1;
+        if (pos >= 0 && pos < D.n_tgt) memcpy(&idx_out, &h_tbl[static_cast<size_t>(pos)].w, 4);
+        return idx_out;
+    };
     // rows sit on the device in heap order: hand them out sorted by (d2, index) when distances were recorded
     // (FLANN's result order), by target index otherwise (the column order of the reference's CSR, :82-83)
     std::vector<std::pair<float, int>> row;
@@ -918,7 +934,7 @@ static void download_association(Engine& E, int p, int32_t* idx, float* d2, int3
         count[i] = c;
         row.clear();
         for (int k = 0; k < c; ++k)
-            row.push_back({d2 ? h_d2[static_cast<size_t>(k) * D.n_pad + j] : 0.f, h_idx[static_cast<size_t>(k) * D.n_pad + j]});
+            row.push_back({d2 ? h_d2[static_cast<size_t>(k) * D.n_pad + j] : 0.f, original_index(h_idx[static_cast<size_t>(k) * D.n_pad + j])});
         std::sort(row.begin(), row.end());
         for (int k = 0; k < max_nn; ++k) {
             const bool have = k < c;
@@ -935,8 +951,15 @@ static void upload_association(Engine& E, int p, const float* tgt_xyzw, int64_t 
     Pair& P = E.pairs[p];
     const PairDev& D = P.dev;
     const size_t plane = static_cast<size_t>(D.m) * D.n_pad;
-    std::vector<float4> hr(plane, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<int> hr(plane, 0);
     std::vector<int> hc(D.n_pad, 0);
+    if (n_tgt != D.n_tgt) throw StatusError{PPCR_ERR_INVALID, "n_tgt does not match the handle's (filtered) target size"};
+    std::vector<int> h_inv(static_cast<size_t>(std::max(D.n_tgt, 1)), 0);
+    if (D.n_tgt > 0) {
+        CK(cudaMemcpyAsync(h_inv.data(), D.inv_perm, static_cast<size_t>(D.n_tgt) * sizeof(int), cudaMemcpyDeviceToHost, E.stream));
+        CK(cudaStreamSynchronize(E.stream));
+    }
+    (void)tgt_xyzw;
     int64_t K = 0;
     const std::vector<int> order = source_order(E, p);
     for (int64_t row = 0; row < D.n_src; ++row) {  // device row `row` is the caller's point order[row]
@@ -948,14 +971,10 @@ static void upload_association(Engine& E, int p, const float* tgt_xyzw, int64_t 
         for (int k = 0; k < c; ++k) {
             const int j = idx[i * max_nn + k];
             if (j < 0 || j >= n_tgt) throw StatusError{PPCR_ERR_INVALID, "association index out of range"};
-            const size_t o = static_cast<size_t>(k) * D.n_pad + row;
-            hr[o].x = tgt_xyzw[4 * static_cast<size_t>(j)];
-            hr[o].y = tgt_xyzw[4 * static_cast<size_t>(j) + 1];
-            hr[o].z = tgt_xyzw[4 * static_cast<size_t>(j) + 2];
-            memcpy(&hr[o].w, &j, 4);
+            hr[static_cast<size_t>(k) * D.n_pad + row] = h_inv[static_cast<size_t>(j)];
         }
     }
-    CK(cudaMemcpyAsync(D.nbr, hr.data(), plane * sizeof(float4), cudaMemcpyHostToDevice, E.stream));
+    CK(cudaMemcpyAsync(D.nbr_pos, hr.data(), plane * sizeof(int), cudaMemcpyHostToDevice, E.stream));
     CK(cudaMemcpyAsync(D.nbr_cnt, hc.data(), hc.size() * sizeof(int), cudaMemcpyHostToDevice, E.stream));
     PairState s = download_state(E, p);
     s.K = K;
@@ -1238,6 +1257,8 @@ ppcr_status ppcr_time_kernel(ppcr_handle* h, int32_t which, int32_t reps, int32_
             switch (which) {
                 case 0: case 4: launch_search(E); break;
                 case 1: launch_evalctl(E, false); break;
+                case 5: launch_evalctl(E, false, 2); break;  // probes: streaming part only / everything but the LM state machine
+                case 6: launch_evalctl(E, false, 4); break;
                 case 2: k_transform_final<<<dim3(E.max_tr_blocks, 1), 256, 0, E.stream>>>(E.d_pairs.p); break;
                 default: build_target_tree(E, P, D.tree.leaf_cap); break;
             }
@@ -1262,10 +1283,13 @@ ppcr_status ppcr_time_kernel(ppcr_handle* h, int32_t which, int32_t reps, int32_
         if (algorithmic_bytes) {
             const double ns = D.n_src, nt = D.n_tgt;
             switch (which) {
-                // query (+ write-back when moving), target, count + k-th distance, 3 planes + index per correspondence
-                case 0: *algorithmic_bytes = 16.0 * ns + 16.0 * nt + 8.0 * ns + 16.0 * K; break;
-                case 4: *algorithmic_bytes = 32.0 * ns + 16.0 * nt + 12.0 * ns + 16.0 * K; break;
-                case 1: *algorithmic_bytes = 16.0 * ns + 4.0 * ns + 12.0 * K; break;              // source, count, 3 planes
+                // query float4 (+ its write-back when the cloud move is fused in), sorted target float4 +
+                // index map, count and k-th distance, one 4-byte index per correspondence
+                case 0: *algorithmic_bytes = 16.0 * ns + 20.0 * nt + 8.0 * ns + 4.0 * K; break;
+                case 4: *algorithmic_bytes = 32.0 * ns + 20.0 * nt + 12.0 * ns + 4.0 * K; break;
+                // source float4 + count; per correspondence a 4-byte index and the 16-byte target point it
+                // names (the points are gathered from the L2-resident sorted target, so DRAM traffic is far below this)
+                case 1: case 5: case 6: *algorithmic_bytes = 20.0 * ns + 20.0 * K; break;
                 case 2: *algorithmic_bytes = 32.0 * ns; break;
                 default: *algorithmic_bytes = 44.0 * nt; break;  // read 16, key+value 12, sorted write 16
             }

@@ -172,8 +172,28 @@ PPCR_HD void row_end(const RowAcc* a, double sx, double sy, double sz, double* a
 // The same row arithmetic with float32 transcendentals and float32 in-row sums.  The residuals keep (nearly) full
 // float32 relative precision although they are differences of ~10..100 m coordinates: the transformed source point
 // is held as an unevaluated float pair (hi + lo), and y - hi is exact or within one rounding, so
-// r = (y - hi) - lo carries ~1e-7 relative error instead of 1e-7 * |y| absolute.  Weights then agree with the
-// float64 formula to a few 1e-7 relative (the bar is 1e-5); everything that is summed ACROSS rows stays float64.
+// r = (y - hi) - lo carries ~1e-7 relative error instead of 1e-7 * |y| absolute.  The weight residual (taken at
+// pose_w) is r_w = r_e + (p_e - p_w): the pose difference is a per-row constant, computed in float64.  Weights then
+// agree with the float64 formula to a few 1e-7 relative (the bar is 1e-5); everything that is summed ACROSS rows
+// stays float64.
+//
+// The per-correspondence arithmetic is instantiated per weight model (WM_*) and per "pose_w == pose_e", both uniform
+// over a launch, so the inner loop carries no branch on either.
+
+enum WeightMode {
+    WM_T_H4 = 0,    // t, (v + d) / 2 == 4  (the reference's default dof = 5): u = s^4, two multiplications
+    WM_T_INT = 1,   // t, 2h an integer <= 31: repeated multiplication (+ a square root for the half)
+    WM_T_REAL = 2,  // t, any other dof: u = exp2(h * log2(s))
+    WM_GAUSS = 3,   // dof = +inf: softmax(-r^2 / 2) with a running maximum
+};
+
+PPCR_HD int weight_mode(const WeightCfg& wc)
+{
+    if (wc.is_normal) return WM_GAUSS;
+    if (wc.pow_int == 4 && !wc.pow_half) return WM_T_H4;
+    if (wc.pow_int >= 0) return WM_T_INT;
+    return WM_T_REAL;
+}
 
 struct PointHL {  // p = hi + lo, component-wise
     float hi[3], lo[3];
@@ -187,8 +207,14 @@ PPCR_HD void split_point(const double* p, PointHL* out)
     }
 }
 
+// d = p_e - p_w, so that  y - p_w = (y - p_e) + d
+PPCR_HD void pose_delta(const double* pe, const double* pw, float* d)
+{
+    for (int k = 0; k < 3; ++k) d[k] = static_cast<float>(pe[k] - pw[k]);
+}
+
 struct RowAccF {
-    float m;      // running max of the log-probabilities
+    float m;      // running max of the log-probabilities (Gaussian model only)
     float a0;     // sum exp(l - m)
     float a1;     // sum exp(l - m) e
     float ar[3];  // sum exp(l - m) e r
@@ -211,23 +237,39 @@ PPCR_HD float residual_hl(float y, float hi, float lo)
 #endif
 }
 
+// 1/x for x in [1, 2^60): one MUFU.RCP on the device (<= 1 ulp), a division on the host
 PPCR_HD float f_rcp(float x)
 {
 #if defined(__CUDA_ARCH__)
-    return __frcp_rn(x);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 #else
     return 1.0f / x;
+#endif
+}
+
+PPCR_HD float f_exp(float x)
+{
+#if defined(__CUDA_ARCH__)
+    return __expf(x);
+#else
+    return expf(x);
 #endif
 }
 
 // t-distribution: unnormalised posterior u = (1 + r^2/v)^(-(v+d)/2) and u * expected weight, without log / exp.
 // u <= 1 and the nearest neighbour keeps the row sum away from zero, so the max-subtraction of the reference's
 // log-sum-exp (which only guards against overflow / total underflow) has nothing to do here.
+template <int WM>
 PPCR_HD void t_terms(const WeightCfg& wc, float r2w, float* u_out, float* ue_out)
 {
     const float s = f_rcp(r2w * wc.f_inv_dof + 1.0f);
     float u;
-    if (wc.pow_int >= 0) {
+    if (WM == WM_T_H4) {
+        const float s2 = s * s;
+        u = s2 * s2;
+    } else if (WM == WM_T_INT) {
         const float s2 = s * s, s4 = s2 * s2, s8 = s4 * s4;
         u = (wc.pow_int & 1) ? s : 1.0f;
         if (wc.pow_int & 2) u *= s2;
@@ -235,32 +277,35 @@ PPCR_HD void t_terms(const WeightCfg& wc, float r2w, float* u_out, float* ue_out
         if (wc.pow_int & 8) u *= s8;
         if (wc.pow_half) u *= sqrtf(s);
     } else {
+#if defined(__CUDA_ARCH__)
+        u = exp2f(wc.f_h * __log2f(s));
+#else
         u = exp2f(wc.f_h * log2f(s));
+#endif
     }
     *u_out = u;
     *ue_out = u * (wc.f_c * s);
 }
 
-// same_pose: pose_w == pose_e (first evaluation of an outer iteration), the weight residual is the cost residual
-PPCR_HD void rowf_add(RowAccF* a, const WeightCfg& wc, float yx, float yy, float yz, const PointHL& pe, const PointHL& pw,
-                      bool same_pose)
+// One correspondence.  SAME: pose_w == pose_e (first evaluation of an outer iteration), the weight residual is the
+// cost residual; otherwise dw = p_e - p_w of this row (pose_delta).
+template <int WM, bool SAME>
+PPCR_HD void rowf_add_t(RowAccF* a, const WeightCfg& wc, float yx, float yy, float yz, const PointHL& pe, const float* dw)
 {
     const float rx = residual_hl(yx, pe.hi[0], pe.lo[0]);
     const float ry = residual_hl(yy, pe.hi[1], pe.lo[1]);
     const float rz = residual_hl(yz, pe.hi[2], pe.lo[2]);
     const float r2e = rx * rx + ry * ry + rz * rz;
     float r2w = r2e;
-    if (!same_pose) {
-        const float wx = residual_hl(yx, pw.hi[0], pw.lo[0]);
-        const float wy = residual_hl(yy, pw.hi[1], pw.lo[1]);
-        const float wz = residual_hl(yz, pw.hi[2], pw.lo[2]);
+    if (!SAME) {
+        const float wx = rx + dw[0], wy = ry + dw[1], wz = rz + dw[2];
         r2w = wx * wx + wy * wy + wz * wz;
     }
     float p, pw_;
-    if (wc.is_normal) {
+    if (WM == WM_GAUSS) {
         const float lp = -0.5f * r2w;
         if (lp > a->m) {  // new row maximum: rescale what has been accumulated so far
-            const float sc = expf(a->m - lp);
+            const float sc = f_exp(a->m - lp);
             a->a0 *= sc;
             a->a1 *= sc;
             a->ar[0] *= sc;
@@ -269,10 +314,10 @@ PPCR_HD void rowf_add(RowAccF* a, const WeightCfg& wc, float yx, float yy, float
             a->ac *= sc;
             a->m = lp;
         }
-        p = expf(lp - a->m);
+        p = f_exp(lp - a->m);
         pw_ = p;
     } else {
-        t_terms(wc, r2w, &p, &pw_);
+        t_terms<WM>(wc, r2w, &p, &pw_);
     }
     a->a0 += p;
     a->a1 += pw_;
@@ -282,30 +327,73 @@ PPCR_HD void rowf_add(RowAccF* a, const WeightCfg& wc, float yx, float yy, float
     a->ac += pw_ * r2e;
 }
 
+// run-time dispatch of the above (host emulation, parity dumps)
+PPCR_HD void rowf_add(RowAccF* a, const WeightCfg& wc, float yx, float yy, float yz, const PointHL& pe, const float* dw,
+                      bool same_pose)
+{
+    switch (weight_mode(wc) * 2 + (same_pose ? 1 : 0)) {
+        case WM_T_H4 * 2: rowf_add_t<WM_T_H4, false>(a, wc, yx, yy, yz, pe, dw); break;
+        case WM_T_H4 * 2 + 1: rowf_add_t<WM_T_H4, true>(a, wc, yx, yy, yz, pe, dw); break;
+        case WM_T_INT * 2: rowf_add_t<WM_T_INT, false>(a, wc, yx, yy, yz, pe, dw); break;
+        case WM_T_INT * 2 + 1: rowf_add_t<WM_T_INT, true>(a, wc, yx, yy, yz, pe, dw); break;
+        case WM_T_REAL * 2: rowf_add_t<WM_T_REAL, false>(a, wc, yx, yy, yz, pe, dw); break;
+        case WM_T_REAL * 2 + 1: rowf_add_t<WM_T_REAL, true>(a, wc, yx, yy, yz, pe, dw); break;
+        case WM_GAUSS * 2: rowf_add_t<WM_GAUSS, false>(a, wc, yx, yy, yz, pe, dw); break;
+        default: rowf_add_t<WM_GAUSS, true>(a, wc, yx, yy, yz, pe, dw); break;
+    }
+}
+
+// fold a finished float32 row into the 24 float64 moments: the row quotients are float32 (like the row sums), the
+// products with the source point and everything summed across rows are float64
 template <int STRIDE>
 PPCR_HD void rowf_end_s(const RowAccF* a, double sx, double sy, double sz, double* acc)
 {
-    RowAcc d;
-    d.m = a->m;
-    d.a0 = a->a0;
-    d.a1 = a->a1;
-    d.ar[0] = a->ar[0];
-    d.ar[1] = a->ar[1];
-    d.ar[2] = a->ar[2];
-    d.ac = a->ac;
-    row_end_s<STRIDE>(&d, sx, sy, sz, acc);
+    const float inv = a->a0 > 0.f ? 1.0f / a->a0 : 0.f;  // every posterior underflowed: the row carries no weight
+    const double W = static_cast<double>(a->a1 * inv);
+    const double rho[3] = {static_cast<double>(a->ar[0] * inv), static_cast<double>(a->ar[1] * inv),
+                           static_cast<double>(a->ar[2] * inv)};
+    const double Wx = W * sx, Wy = W * sy, Wz = W * sz;
+    acc[(M_S0) * STRIDE] += W;
+    acc[(M_S1 + 0) * STRIDE] += Wx;
+    acc[(M_S1 + 1) * STRIDE] += Wy;
+    acc[(M_S1 + 2) * STRIDE] += Wz;
+    acc[(M_S2 + 0) * STRIDE] += Wx * sx;
+    acc[(M_S2 + 1) * STRIDE] += Wx * sy;
+    acc[(M_S2 + 2) * STRIDE] += Wx * sz;
+    acc[(M_S2 + 3) * STRIDE] += Wy * sy;
+    acc[(M_S2 + 4) * STRIDE] += Wy * sz;
+    acc[(M_S2 + 5) * STRIDE] += Wz * sz;
+    acc[(M_SR + 0) * STRIDE] += rho[0];
+    acc[(M_SR + 1) * STRIDE] += rho[1];
+    acc[(M_SR + 2) * STRIDE] += rho[2];
+    acc[(M_C + 0) * STRIDE] += sx * rho[0];
+    acc[(M_C + 1) * STRIDE] += sx * rho[1];
+    acc[(M_C + 2) * STRIDE] += sx * rho[2];
+    acc[(M_C + 3) * STRIDE] += sy * rho[0];
+    acc[(M_C + 4) * STRIDE] += sy * rho[1];
+    acc[(M_C + 5) * STRIDE] += sy * rho[2];
+    acc[(M_C + 6) * STRIDE] += sz * rho[0];
+    acc[(M_C + 7) * STRIDE] += sz * rho[1];
+    acc[(M_C + 8) * STRIDE] += sz * rho[2];
+    acc[(M_COST) * STRIDE] += static_cast<double>(0.5f * a->ac * inv);
+    acc[(M_ROWS) * STRIDE] += 1.0;
 }
 PPCR_HD void rowf_end(const RowAccF* a, double sx, double sy, double sz, double* acc) { rowf_end_s<1>(a, sx, sy, sz, acc); }
 
+// weight of one correspondence once the row statistics are known (parity dumps only); pw = p_w as a float pair
 PPCR_HD float rowf_finished_weight(const RowAccF* a, const WeightCfg& wc, float yx, float yy, float yz, const PointHL& pw)
 {
     const float wx = residual_hl(yx, pw.hi[0], pw.lo[0]);
     const float wy = residual_hl(yy, pw.hi[1], pw.lo[1]);
     const float wz = residual_hl(yz, pw.hi[2], pw.lo[2]);
     const float r2w = wx * wx + wy * wy + wz * wz;
-    if (wc.is_normal) return expf(-0.5f * r2w - a->m) / a->a0;
+    if (wc.is_normal) return f_exp(-0.5f * r2w - a->m) / a->a0;
     float u, ue;
-    t_terms(wc, r2w, &u, &ue);
+    switch (weight_mode(wc)) {
+        case WM_T_H4: t_terms<WM_T_H4>(wc, r2w, &u, &ue); break;
+        case WM_T_INT: t_terms<WM_T_INT>(wc, r2w, &u, &ue); break;
+        default: t_terms<WM_T_REAL>(wc, r2w, &u, &ue); break;
+    }
     return ue / a->a0;
 }
 

@@ -17,8 +17,11 @@
 //   nodes       TreeNode[]         linear octree over tgt_sorted (ppcr_tree.h), 32-byte records, 8 children adjacent
 //   src         float4[n_src]      the moving source cloud (filtered), Morton-sorted once so that the 32 queries of a
 //                                  warp walk the same part of the tree; .w = original index
-//   nbr         float4[m][n_pad]   slot-major neighbour records (x, y, z, original index): entry (k, i) is the k-th
-//                                  nearest target of source i, so one warp reads 512 contiguous bytes per slot
+//   nbr_pos     int[m][n_pad]      slot-major association: entry (k, i) is the position IN tgt_sorted of a neighbour of
+//                                  source i (one warp reads 128 contiguous bytes per slot); the evaluation gathers the
+//                                  16-byte target points from tgt_sorted, which stays in L2 and -- neighbours of
+//                                  neighbouring queries being neighbours in Morton order -- mostly in L1
+//   inv_perm    int[n_tgt]         original target index -> position in tgt_sorted
 //   nbr_cnt     int[n_pad]
 //   partials    double[blocks][24] per-block moment sums, reduced in a fixed order by the controller
 // No tensor cores: nothing on this path is a dense contraction; the kernels are HBM/L2-bound streaming passes.
@@ -56,7 +59,8 @@ struct PairDev {
     int n_pad;
     int m;          // result capacity = min(max_neighbours, n_tgt)
     float r2f;      // float(radius * radius): strict membership bound (FLANN)
-    float4* nbr;    // [m][n_pad] slot-major neighbour records: x, y, z of the target point, .w = its original index
+    int* nbr_pos;   // [m][n_pad] slot-major association: positions in tgt_sorted
+    const int* inv_perm;  // [n_tgt] original index -> position in tgt_sorted
     float* nbr_d2;  // optional (stage API only), may be null
     float* nbr_kth; // d2 of the m-th neighbour found by the last search (+inf when fewer were found): warm start
     int* nbr_cnt;
@@ -233,7 +237,7 @@ __global__ void k_tree_keys(const float4* __restrict__ pts, int n, TreeGeom g, u
 // sorted[j] = pts[vals[j]] with .w = the original index.  keep_w: the input's own .w is carried instead (a cloud that
 // is already tagged, i.e. re-sorting the source)
 __global__ void k_tree_gather(const float4* __restrict__ pts, const unsigned* __restrict__ vals, int n, int keep_w,
-                              float4* __restrict__ sorted)
+                              float4* __restrict__ sorted, int* __restrict__ inv_perm)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -241,6 +245,7 @@ __global__ void k_tree_gather(const float4* __restrict__ pts, const unsigned* __
     float4 p = pts[i];
     if (!keep_w) p.w = __int_as_float(static_cast<int>(i));
     sorted[j] = p;
+    if (inv_perm) inv_perm[i] = j;
 }
 
 // tag every point with its own index in .w (the source keeps its caller-order identity through the Morton sort)
@@ -318,10 +323,8 @@ __device__ __forceinline__ float transform_row(const double* T, double x, double
 
 __device__ __forceinline__ void search_store(const PairDev& P, int i, int e, unsigned long long key)
 {
-    const int idx = key_index(key);
-    const float4 p = __ldg(P.tgt_raw + idx);
     const size_t o = static_cast<size_t>(e) * P.n_pad + i;
-    P.nbr[o] = make_float4(p.x, p.y, p.z, __int_as_float(idx));
+    P.nbr_pos[o] = __ldg(P.inv_perm + key_index(key));
     if (P.nbr_d2) P.nbr_d2[o] = key_d2(key);
 }
 
@@ -339,6 +342,7 @@ constexpr int kSearchChunk = kSearchThreads;  // queries handed out per grab of 
 // dynamic shared memory per thread): replacing the root and sifting down costs ~log2(m) steps, about half the
 // instructions of a sorted register list at m = 10..20, and works for any m.  Rows are stored in heap order; nothing
 // downstream depends on the order inside a row (the host sorts rows it hands out).
+template <int VAR>
 __global__ void __launch_bounds__(kSearchThreads) k_search(const PairDev* __restrict__ pairs)
 {
     extern __shared__ unsigned long long s_heap[];
@@ -379,15 +383,15 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(const PairDev* __rest
         }
         int cnt = 0;
         float kth = __int_as_float(0x7f800000);
-        HeapList<kSearchThreads> L;
+        HeapList<kSearchThreads, (VAR & 1) != 0> L;
         L.k = s_heap + threadIdx.x;
         L.init(m);
         tree_search(P.tree, P.nodes, P.tgt_sorted, q.x, q.y, q.z, P.r2f, bound0, L, stack);
-        for (int s = 0; s < m; ++s) {
+        for (int s = 0; s < L.n; ++s) {
             const unsigned long long key = L.k[s * kSearchThreads];
-            if (key != kKeyInf) search_store(P, i, cnt++, key);
+            if ((VAR & 1) || key != kKeyInf) search_store(P, i, cnt++, key);
         }
-        if (L.k[0] != kKeyInf) kth = key_d2(L.k[0]);
+        if (L.n == m && L.k[0] != kKeyInf) kth = key_d2(L.k[0]);
         P.nbr_cnt[i] = cnt;
         P.nbr_kth[i] = kth;
         cnt_total += cnt;
@@ -514,6 +518,63 @@ __device__ __forceinline__ void warp_controller(PairState* st, const Config* cfg
 
 static_assert(sizeof(PairState) % 8 == 0 && sizeof(Config) % 8 == 0, "copied as 64-bit words");
 
+// The float32 row loop of k_evalctl: one source row per thread, grid-stride.  The neighbour records of a row are
+// kU slots apart in the slot-major planes (each a coalesced 512-byte read per warp); full batches of kU records are
+// loaded without predicates before their arithmetic, the ragged tail of a row with.
+template <int WM, bool SAME>
+__device__ __forceinline__ void eval_rows_fast(const PairDev& P, const Pose& pe, const Pose& pw, const WeightCfg& wc, double* acc)
+{
+    constexpr int kU = PPCR_EVAL_BATCH;
+    const int stride = P.n_eval_blocks * kEvalThreads;
+    const size_t n_pad = P.n_pad;
+    for (int i = blockIdx.x * kEvalThreads + threadIdx.x; i < P.n_src; i += stride) {
+        const int cnt = P.nbr_cnt[i];
+        if (cnt == 0) continue;
+        const float4 sp = P.src[i];
+        const double sx = sp.x, sy = sp.y, sz = sp.z;
+        double pte[3];
+        apply_pose(pe, sx, sy, sz, pte);
+        PointHL he;
+        split_point(pte, &he);
+        float dw[3] = {0.f, 0.f, 0.f};
+        if (!SAME) {
+            double ptw[3];
+            apply_pose(pw, sx, sy, sz, ptw);
+            pose_delta(pte, ptw, dw);
+        }
+        RowAccF row;
+        rowf_begin(&row);
+        const int* rec = P.nbr_pos + i;
+        const float4* __restrict__ table = P.tgt_sorted;
+        int k0 = 0;
+        for (; k0 + kU <= cnt; k0 += kU) {
+            int pos[kU];
+            float4 y[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) pos[u] = __ldg(rec + static_cast<size_t>(u) * n_pad);
+            rec += static_cast<size_t>(kU) * n_pad;
+#pragma unroll
+            for (int u = 0; u < kU; ++u) y[u] = __ldg(table + pos[u]);
+#pragma unroll
+            for (int u = 0; u < kU; ++u) rowf_add_t<WM, SAME>(&row, wc, y[u].x, y[u].y, y[u].z, he, dw);
+        }
+        if (k0 < cnt) {
+            int pos[kU - 1];
+            float4 y[kU - 1];
+#pragma unroll
+            for (int u = 0; u < kU - 1; ++u)
+                if (k0 + u < cnt) pos[u] = __ldg(rec + static_cast<size_t>(u) * n_pad);
+#pragma unroll
+            for (int u = 0; u < kU - 1; ++u)
+                if (k0 + u < cnt) y[u] = __ldg(table + pos[u]);
+#pragma unroll
+            for (int u = 0; u < kU - 1; ++u)
+                if (k0 + u < cnt) rowf_add_t<WM, SAME>(&row, wc, y[u].x, y[u].y, y[u].z, he, dw);
+        }
+        rowf_end_s<kEvalThreads>(&row, sx, sy, sz, acc);
+    }
+}
+
 struct LoopCtl {   // one per engine
     int active;      // any pair still running (read back by the host-stepped driver)
     int pairs_done;  // pairs whose controller has finished this tick
@@ -560,35 +621,16 @@ __global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(
 #pragma unroll
         for (int k = 0; k < 12; ++k)
             same = same && (reinterpret_cast<const double*>(&s_pe)[k] == reinterpret_cast<const double*>(&s_pw)[k]);
-        for (int i = blockIdx.x * kEvalThreads + threadIdx.x; i < P.n_src; i += stride) {
-            const int cnt = P.nbr_cnt[i];
-            if (cnt == 0) continue;
-            const float4 sp = P.src[i];
-            const double sx = sp.x, sy = sp.y, sz = sp.z;
-            double pte[3], ptw[3];
-            apply_pose(pe, sx, sy, sz, pte);
-            PointHL he, hw;
-            split_point(pte, &he);
-            hw = he;
-            if (!same) {
-                apply_pose(pw, sx, sy, sz, ptw);
-                split_point(ptw, &hw);
-            }
-            RowAccF row;
-            rowf_begin(&row);
-            constexpr int kU = PPCR_EVAL_BATCH;  // records of kU correspondences are in flight before their arithmetic
-            const float4* rec = P.nbr + i;
-            for (int k0 = 0; k0 < cnt; k0 += kU) {
-                float4 y[kU];
-#pragma unroll
-                for (int u = 0; u < kU; ++u)
-                    if (k0 + u < cnt) y[u] = __ldg(rec + static_cast<size_t>(u) * n_pad);
-                rec += static_cast<size_t>(kU) * n_pad;
-#pragma unroll
-                for (int u = 0; u < kU; ++u)
-                    if (k0 + u < cnt) rowf_add(&row, wc, y[u].x, y[u].y, y[u].z, he, hw, same);
-            }
-            rowf_end_s<kEvalThreads>(&row, sx, sy, sz, acc);
+        // one instantiation of the row loop per (weight model, same pose): both are uniform over the launch
+        switch (weight_mode(wc) * 2 + (same ? 1 : 0)) {
+            case WM_T_H4 * 2: eval_rows_fast<WM_T_H4, false>(P, pe, pw, wc, acc); break;
+            case WM_T_H4 * 2 + 1: eval_rows_fast<WM_T_H4, true>(P, pe, pw, wc, acc); break;
+            case WM_T_INT * 2: eval_rows_fast<WM_T_INT, false>(P, pe, pw, wc, acc); break;
+            case WM_T_INT * 2 + 1: eval_rows_fast<WM_T_INT, true>(P, pe, pw, wc, acc); break;
+            case WM_T_REAL * 2: eval_rows_fast<WM_T_REAL, false>(P, pe, pw, wc, acc); break;
+            case WM_T_REAL * 2 + 1: eval_rows_fast<WM_T_REAL, true>(P, pe, pw, wc, acc); break;
+            case WM_GAUSS * 2: eval_rows_fast<WM_GAUSS, false>(P, pe, pw, wc, acc); break;
+            default: eval_rows_fast<WM_GAUSS, true>(P, pe, pw, wc, acc); break;
         }
     } else {
         for (int i = blockIdx.x * kEvalThreads + threadIdx.x; i < P.n_src; i += stride) {
@@ -603,7 +645,7 @@ __global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(
             row_begin(&row);
             for (int k = 0; k < cnt; ++k) {
                 const size_t o = static_cast<size_t>(k) * n_pad + i;
-                const float4 y = __ldg(P.nbr + o);
+                const float4 y = __ldg(P.tgt_sorted + __ldg(P.nbr_pos + o));
                 row_add<false>(&row, wc, y.x, y.y, y.z, pte, ptw);
             }
             row_end_s<kEvalThreads>(&row, sx, sy, sz, acc);
@@ -632,6 +674,7 @@ __global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(
     if (!s_flag) return;
     __threadfence();
     if (threadIdx.x == 0) st->eval_ticket = 0;
+    if (use_cond & 2) return;  // timing probe (ppcr_time_kernel): the streaming part alone
     {
         // group g folds blocks g, g + G, g + 2G, ... in order (loads issued eight at a time), then the groups in order
         double v = 0.0;
@@ -737,7 +780,7 @@ __global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(
             __syncthreads();
             if (threadIdx.x < kExpandTasks) expand_task(s_sum, s_ctrl.N, threadIdx.x, &s_ctrl.ev);
             __syncthreads();
-            if (threadIdx.x < 32)
+            if (threadIdx.x < 32 && !(use_cond & 4))  // & 4: timing probe without the LM state machine
                 warp_controller(&s_state, &s_cfg, &s_ctrl, P.history, P.stats, P.max_hist, max_ticks, threadIdx.x);
         }
         __syncthreads();
@@ -757,7 +800,7 @@ __global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(
             int active = 0;
             for (int p = 0; p < n_pairs; ++p) active |= (*reinterpret_cast<volatile int*>(&pairs[p].state->phase) != PH_DONE);
             loop->active = active;
-            if (use_cond) cudaGraphSetConditional(cond, active ? 1u : 0u);
+            if (use_cond & 1) cudaGraphSetConditional(cond, active ? 1u : 0u);
         }
     }
 }
@@ -783,22 +826,27 @@ __global__ void k_dump_weights(const PairDev* __restrict__ pairs, double* __rest
         rowf_begin(&row);
         for (int k = 0; k < cnt; ++k) {
             const size_t o = static_cast<size_t>(k) * n_pad + i;
-            rowf_add(&row, P.wcfg, P.nbr[o].x, P.nbr[o].y, P.nbr[o].z, hw, hw, true);
+            const float zero[3] = {0.f, 0.f, 0.f};
+            const float4 y = P.tgt_sorted[P.nbr_pos[o]];
+            rowf_add(&row, P.wcfg, y.x, y.y, y.z, hw, zero, true);
         }
         for (int k = 0; k < cnt; ++k) {
             const size_t o = static_cast<size_t>(k) * n_pad + i;
-            out[o] = rowf_finished_weight(&row, P.wcfg, P.nbr[o].x, P.nbr[o].y, P.nbr[o].z, hw);
+            const float4 y = P.tgt_sorted[P.nbr_pos[o]];
+            out[o] = rowf_finished_weight(&row, P.wcfg, y.x, y.y, y.z, hw);
         }
     } else {
         RowAcc row;
         row_begin(&row);
         for (int k = 0; k < cnt; ++k) {
             const size_t o = static_cast<size_t>(k) * n_pad + i;
-            row_add<false>(&row, P.wcfg, P.nbr[o].x, P.nbr[o].y, P.nbr[o].z, ptw, ptw);
+            const float4 y = P.tgt_sorted[P.nbr_pos[o]];
+            row_add<false>(&row, P.wcfg, y.x, y.y, y.z, ptw, ptw);
         }
         for (int k = 0; k < cnt; ++k) {
             const size_t o = static_cast<size_t>(k) * n_pad + i;
-            out[o] = finished_weight<false>(&row, P.wcfg, P.nbr[o].x, P.nbr[o].y, P.nbr[o].z, ptw);
+            const float4 y = P.tgt_sorted[P.nbr_pos[o]];
+            out[o] = finished_weight<false>(&row, P.wcfg, y.x, y.y, y.z, ptw);
         }
     }
 }

@@ -273,21 +273,28 @@ PPCR_HD void tree_mark_leaf_children(TreeNode* nodes, int ni)
 }
 
 // binary max-heap of the m best keys in addressable memory, element i at k[i * STRIDE] (the search kernel keeps one
-// column per thread in shared memory, STRIDE = block size).  worst() is the root; entries come out unordered.
-template <int STRIDE>
+// column per thread in shared memory, STRIDE = block size).  The first m candidates are only appended -- nothing can
+// be rejected before m are known, so no order is needed -- and the heap is built once, when the m-th arrives
+// (Floyd, ~m/2 short sift-downs); from then on a better candidate replaces the root and sifts down.  Entries
+// [0, n) are valid and come out unordered.
+template <int STRIDE, bool APPEND = true>
 struct HeapList {
     unsigned long long* k;
     int m;
+    int n;
     PPCR_HD void init(int m_)
     {
         m = m_;
-        for (int i = 0; i < m; ++i) k[i * STRIDE] = kKeyInf;
+        n = 0;
+        if (!APPEND) {
+            n = m;
+            for (int i = 0; i < m; ++i) k[i * STRIDE] = kKeyInf;
+        }
     }
-    PPCR_HD unsigned long long worst() const { return k[0]; }
-    // pre: x < k[0].  Replaces the root and sifts down.
-    PPCR_HD void insert(unsigned long long x)
+    PPCR_HD unsigned long long worst() const { return n == m ? k[0] : kKeyInf; }
+    // puts x into the hole at i and moves it down until both children are smaller
+    PPCR_HD void sift_down(int i, unsigned long long x)
     {
-        int i = 0;
         for (;;) {
             const int l = 2 * i + 1;
             if (l >= m) break;
@@ -306,9 +313,31 @@ struct HeapList {
         }
         k[i * STRIDE] = x;
     }
+    // pre: x < worst()
+    PPCR_HD void insert(unsigned long long x)
+    {
+        if (n < m) {
+            k[n * STRIDE] = x;
+            if (++n == m)
+                for (int i = m / 2 - 1; i >= 0; --i) sift_down(i, k[i * STRIDE]);
+        } else {
+            sift_down(0, x);
+        }
+    }
 };
 
 // ---- traversal -----------------------------------------------------------------------------------------------
+
+// work counters of the traversal, host builds with -DPPCR_TREE_STATS only (tools/tree_stats.py)
+#if defined(PPCR_TREE_STATS) && !defined(__CUDA_ARCH__)
+struct TreeStats {
+    long long opens, leaves, leaves_skipped, points, survivors, inserts, stack_skipped;
+};
+inline TreeStats g_tree_stats = {};
+#define PPCR_STAT(field, n) (g_tree_stats.field += (n))
+#else
+#define PPCR_STAT(field, n) ((void)0)
+#endif
 
 // squared distance from q to the interval [c - hi, c + hi] along one axis
 PPCR_HD float axis_gap2(float q, float c, float hi)
@@ -356,7 +385,11 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
         while (sp > 0 && np <= kPend - 8) {
             --sp;
             // the bound may have shrunk since this node was pushed: re-test with the lower bound stored beside it
-            if (bits_float(static_cast<uint32_t>(stack[2 * sp + 1])) > thr) continue;
+            if (bits_float(static_cast<uint32_t>(stack[2 * sp + 1])) > thr) {
+                PPCR_STAT(stack_skipped, 1);
+                continue;
+            }
+            PPCR_STAT(opens, 1);
             const TreeNode n = nodes[stack[2 * sp]];
             // Children far-to-near, so that the octant holding q is opened / scanned first.  The lower bound of a
             // child box is a sum of three per-axis gaps, each of which takes one of two values (the child's half on
@@ -395,8 +428,13 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
         // ---- scan the pending leaves, nearest (appended last) first ----
         while (np > 0) {
             --np;
-            if (bits_float(static_cast<uint32_t>(pend[2 * np + 1])) > thr) continue;
+            if (bits_float(static_cast<uint32_t>(pend[2 * np + 1])) > thr) {
+                PPCR_STAT(leaves_skipped, 1);
+                continue;
+            }
             const TreeNode n = nodes[pend[2 * np]];
+            PPCR_STAT(leaves, 1);
+            PPCR_STAT(points, n.end - n.begin);
             // 32 points at a time, in two passes so that the threads of a warp stay together: first a plain distance
             // test of every point against the current bound (a bit per survivor, nothing else), then the survivors --
             // re-read from L1 -- go through the list one after the other.  The expensive, divergent part (the heap
@@ -412,12 +450,14 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
                 while (pass) {
                     const int t = lowest_bit(pass);
                     pass &= pass - 1;
+                    PPCR_STAT(survivors, 1);
                     const float4 p = pts[j0 + t];
                     const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
                     if (d2 <= bound_d2) {  // the bound may have shrunk since the first pass
                         const unsigned long long k2 = make_key(d2, static_cast<int>(float_bits(p.w)));
                         if (k2 <= r2key && k2 < L.worst()) {  // k2 <= r2key  <=>  d2 < r2f (keys carry +1)
                             L.insert(k2);
+                            PPCR_STAT(inserts, 1);
                             const unsigned long long w = L.worst();
                             if (w != kKeyInf) {
                                 const float wd = key_d2(w);

@@ -82,14 +82,15 @@ void eval(const Cloud& src, const Cloud& tgt, const std::vector<int>& idx, const
         apply_pose(st.pose_e, sx, sy, sz, pe);
         apply_pose(st.pose_w, sx, sy, sz, pw);
         if (kFast) {  // the float32 row path of k_eval<true>
-            PointHL he, hw;
+            PointHL he;
             split_point(pe, &he);
-            split_point(pw, &hw);
+            float dw[3];
+            pose_delta(pe, pw, dw);
             RowAccF row;
             rowf_begin(&row);
             for (int k = 0; k < cnt[i]; ++k) {
                 const float* y = &tgt.p[4 * static_cast<size_t>(idx[i * m + k])];
-                rowf_add(&row, wc, y[0], y[1], y[2], he, hw, same);
+                rowf_add(&row, wc, y[0], y[1], y[2], he, dw, same);
             }
             rowf_end(&row, sx, sy, sz, S);
         } else {
@@ -286,8 +287,7 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
             L.k = buf.data();
             L.init(m);
             tree_search(g, nodes.data(), pts.data(), q[0], q[1], q[2], r2f, bound0, L, stack);
-            for (int s2 = 0; s2 < m; ++s2)
-                if (buf[s2] != kKeyInf) found.push_back(buf[s2]);
+            for (int s2 = 0; s2 < L.n; ++s2) found.push_back(buf[s2]);
         } else {
             TopListDyn L;
             L.k = buf.data();
@@ -305,5 +305,15 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
     }
     return total;
 }
+
+#if defined(PPCR_TREE_STATS)
+void emu_tree_stats(long long* out7, int reset)
+{
+    const long long v[7] = {g_tree_stats.opens, g_tree_stats.leaves, g_tree_stats.leaves_skipped, g_tree_stats.points,
+                            g_tree_stats.survivors, g_tree_stats.inserts, g_tree_stats.stack_skipped};
+    for (int k = 0; k < 7; ++k) out7[k] = v[k];
+    if (reset) g_tree_stats = TreeStats{};
+}
+#endif
 
 }  // extern "C"

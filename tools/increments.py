@@ -11,6 +11,8 @@ with capi.Registration(src, tgt, capi.make_params(**bench.WORKLOADS[w]["params"]
     reg.align()
     inc = reg.increment_history()
     st = reg.iteration_stats()
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+np.save(os.path.join(ROOT, "gpurun_out", f"increments_{w}.npy"), np.asarray(inc))
 R = np.linalg.norm(src[:, :3], axis=1)
 for k, T in enumerate(inc):
     ang = np.arccos(np.clip((np.trace(T[:3, :3]) - 1) / 2, -1, 1))

@@ -1,6 +1,6 @@
 """Per-source-line instruction counts of one kernel from an .ncu-rep (run here, no GPU needed).
 
-    python tools/ncu_lines.py rep.ncu-rep kernel_mangled_substring [top]
+    python tools/ncu_lines.py rep.ncu-rep kernel_mangled_substring [top] [inst|samples]
 
 Joins ncu's SASS page (address -> executed instructions, stall samples) with nvdisasm's line table of the built
 library (address -> file:line, inlining included), because `ncu --page source --csv` carries no metrics for the CUDA-C view.
@@ -19,6 +19,7 @@ LIB = os.path.join(ROOT, "probabilistic_point_clouds_registration_b200", "csrc",
 
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 50
+order = 2 if (len(sys.argv) > 4 and sys.argv[4].startswith("s")) else 0
 
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", LIB], cwd=tmp, capture_output=True)
@@ -85,5 +86,5 @@ def src_text(f, l):
 
 
 print(f"total warp instructions {total[0]:.0f}, thread instructions {total[1]:.0f} (avg {total[1] / max(total[0], 1):.1f} lanes), samples {total[2]:.0f}")
-for key, v in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:top]:
+for key, v in sorted(per_line.items(), key=lambda kv: -kv[1][order])[:top]:
     print(f"{100 * v[0] / total[0]:5.1f}% inst {100 * v[2] / max(total[2], 1):5.1f}% smp  lanes {v[1] / max(v[0], 1):4.1f}  {key[0]}:{key[1]:<4d} {src_text(*key)}")

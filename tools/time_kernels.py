@@ -18,11 +18,12 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 src, tgt = bench.make_pair(workload, 0)
 params = capi.make_params(n_iter=n_iter, **bench.WORKLOADS[workload]["params"])
 names = {0: "search (cold bound)", 4: "search (moved + warm bound)", 1: "weights+normal eq+controller", 2: "cloud move",
-         3: "target tree build"}
+         3: "target tree build", 5: "  weights+normal eq only (probe)", 6: "  ... + fold, no LM (probe)"}
 leaf = int(os.environ.get("PPCR_LEAF", "0"))
 with capi.Registration(src, tgt, params, capi.make_options(leaf_capacity=leaf)) as reg:
     reg.align()
     print(f"{workload}: {len(reg.iteration_stats())} outer iterations")
-    for which in (0, 4, 1, 2, 3):
+    for which in (0, 4, 1, 5, 6, 2, 3):
         ms, nbytes = reg.time_kernel(which, reps=reps, flush_l2=True)
-        print(f"  {names[which]:32s} {ms*1e3:9.1f} us  {nbytes/1e6:8.1f} MB algorithmic  {nbytes/ms/1e6:8.1f} GB/s")
+        hot, _ = reg.time_kernel(which, reps=reps, flush_l2=False)
+        print(f"  {names[which]:32s} {ms*1e3:9.1f} us  {nbytes/1e6:8.1f} MB algorithmic  {nbytes/ms/1e6:8.1f} GB/s   (L2 not flushed: {hot*1e3:.1f} us)")
