@@ -141,7 +141,7 @@ static inline void note_launches(int n) { *g_launch_sink += n; }
 struct Pair {
     DevBuf<float4> src, tgt_raw, tgt_sorted, tmp_cloud;
     DevBuf<int> nbr_cnt, scan_sums;
-    DevBuf<int> nbr_pos, inv_perm;
+    DevBuf<int> nbr_pos, inv_perm, group_ticket;
     DevBuf<TreeNode> nodes;
     DevBuf<TreeCounters> tree_counters;
     DevBuf<unsigned long long> sort_keys[2];
@@ -162,7 +162,7 @@ struct Pair {
     {
         src.release(); tgt_raw.release(); tgt_sorted.release(); tmp_cloud.release();
         nodes.release(); tree_counters.release(); sort_keys[0].release(); sort_keys[1].release();
-        sort_vals[0].release(); sort_vals[1].release(); sort_tmp.release(); nbr_pos.release(); inv_perm.release(); nbr_cnt.release();
+        sort_vals[0].release(); sort_vals[1].release(); sort_tmp.release(); nbr_pos.release(); inv_perm.release(); group_ticket.release(); nbr_cnt.release();
         scan_sums.release(); nbr_d2.release(); nbr_kth.release();
         partials.release(); history.release(); mailbox.release(); state.release(); cfg.release(); stats.release();
         scratch_u.release(); scratch_ull.release();
@@ -186,6 +186,7 @@ struct Engine {
     int* h_active = nullptr;  // pinned, shared by the handles of a host thread (pinned_flag)
     int eval_blocks_per_sm = PPCR_EVAL_MIN_BLOCKS, search_blocks_per_sm = 8;
     size_t search_smem = 0;  // the search kernel's per-block heap columns
+    size_t eval_smem = kEvalSmem;  // float64 path: moment columns; float32 path: the staged tiles (set in engine_commit)
     // launch geometry (capacity based, so a captured graph stays valid while the slots are refilled)
     int max_tiles = 1, max_eval_blocks = 1, max_tr_blocks = 1;
     bool skip_search = false;
@@ -522,8 +523,9 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     PairDev& D = P.dev;
     D.n_src = static_cast<int>(P.n_src);
     D.n_tgt = static_cast<int>(P.n_tgt);
-    D.n_pad = (D.n_src + 31) / 32 * 32;
-    if (D.n_pad == 0) D.n_pad = 32;
+    // rows are padded to whole tiles of the evaluation (bulk copies read whole tiles; the padding rows carry count 0)
+    D.n_pad = (D.n_src + kEvalFastThreads - 1) / kEvalFastThreads * kEvalFastThreads;
+    if (D.n_pad == 0) D.n_pad = kEvalFastThreads;
     D.m = static_cast<int>(std::min<int64_t>(prm.max_neighbours, std::max<int64_t>(P.n_tgt, 1)));
     D.r2f = static_cast<float>(prm.radius * prm.radius);
     D.src = P.src.p;
@@ -566,10 +568,19 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     D.nbr_d2 = P.want_d2 ? P.nbr_d2.p : nullptr;
     D.nbr_cnt = P.nbr_cnt.p;
     CK(cudaMemsetAsync(P.nbr_cnt.p, 0, static_cast<size_t>(D.n_pad) * sizeof(int), st));
-    D.n_eval_blocks = std::max(1, std::min(ceil_div(std::max(D.n_src, 1), kEvalThreads), E.eval_blocks_per_sm * std::max(g_sm_count, 1)));
-    P.partials.reserve(static_cast<size_t>(D.n_eval_blocks) * kNSum);
+    {
+        const bool fast = !E.opts.exact_weights;
+        const int per_sm = fast ? kEvalFastBlocks : E.eval_blocks_per_sm;
+        D.n_eval_blocks = std::max(1, std::min(ceil_div(std::max(D.n_src, 1), eval_threads(fast)), per_sm * std::max(g_sm_count, 1)));
+    }
+    D.n_eval_groups = ceil_div(D.n_eval_blocks, kFoldGroup);
+    P.partials.reserve(static_cast<size_t>(D.n_eval_blocks + D.n_eval_groups) * kNSum);
     D.partials = P.partials.p;
-    CK(cudaMemsetAsync(P.partials.p, 0, static_cast<size_t>(D.n_eval_blocks) * kNSum * sizeof(double), st));
+    D.group_partials = P.partials.p + static_cast<size_t>(D.n_eval_blocks) * kNSum;
+    CK(cudaMemsetAsync(P.partials.p, 0, static_cast<size_t>(D.n_eval_blocks + D.n_eval_groups) * kNSum * sizeof(double), st));
+    P.group_ticket.reserve(D.n_eval_groups);
+    D.group_ticket = P.group_ticket.p;
+    CK(cudaMemsetAsync(P.group_ticket.p, 0, static_cast<size_t>(D.n_eval_groups) * sizeof(int), st));
     D.max_hist = std::max(1, prm.n_iter);
     P.history.reserve(static_cast<size_t>(D.max_hist) * 32);  // accumulated poses, then the increments
     P.stats.reserve(D.max_hist);
@@ -646,6 +657,12 @@ static void engine_commit(Engine& E)
     CK(cudaMemcpyAsync(E.d_pairs.p, host.data(), sizeof(PairDev) * np, cudaMemcpyHostToDevice, E.stream));
     CK(cudaStreamSynchronize(E.stream));
     E.search_smem = static_cast<size_t>(E.params.max_neighbours) * kSearchThreads * sizeof(unsigned long long);
+    if (!E.opts.exact_weights) {
+        E.eval_smem = eval_fast_smem(max_m);
+        CK(cudaFuncSetAttribute(k_evalctl<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.eval_smem)));
+    } else {
+        E.eval_smem = kEvalSmem;
+    }
     if (E.search_smem > 48 * 1024)
     {
         CK(cudaFuncSetAttribute(k_search<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.search_smem)));
@@ -713,9 +730,9 @@ static void launch_evalctl(Engine& E, bool use_cond, int probe = 0)
     dim3 grid(E.max_eval_blocks, np);
     const int flags = (use_cond ? 1 : 0) | probe;
     if (!E.opts.exact_weights)
-        k_evalctl<true><<<grid, kEvalThreads, kEvalSmem, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, flags, E.max_ticks);
+        k_evalctl<true><<<grid, kEvalFastThreads, E.eval_smem, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, flags, E.max_ticks);
     else
-        k_evalctl<false><<<grid, kEvalThreads, kEvalSmem, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, flags, E.max_ticks);
+        k_evalctl<false><<<grid, kEvalThreads, E.eval_smem, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, flags, E.max_ticks);
 }
 
 static int launches_per_tick(const Engine& E) { return E.skip_search ? 1 : 2; }
@@ -989,12 +1006,16 @@ static void reduce_partials_like_controller(Engine& E, int p, double* S)
     std::vector<double> part(static_cast<size_t>(D.n_eval_blocks) * kNSum);
     CK(cudaMemcpyAsync(part.data(), D.partials, part.size() * sizeof(double), cudaMemcpyDeviceToHost, E.stream));
     CK(cudaStreamSynchronize(E.stream));
-    const int W = kCtrlGroups;
     for (int k = 0; k < kNSum; ++k) {
         double total = 0.0;
-        for (int w = 0; w < W; ++w) {
+        for (int q = 0; q < kFoldChains; ++q) {
             double v = 0.0;
-            for (int b = w; b < D.n_eval_blocks; b += W) v += part[static_cast<size_t>(b) * kNSum + k];
+            for (int g = q; g < D.n_eval_groups; g += kFoldChains) {
+                double gp = 0.0;  // level 1: the group's blocks in order
+                for (int b = g * kFoldGroup; b < std::min(D.n_eval_blocks, (g + 1) * kFoldGroup); ++b)
+                    gp += part[static_cast<size_t>(b) * kNSum + k];
+                v += gp;
+            }
             total += v;
         }
         S[k] = total;

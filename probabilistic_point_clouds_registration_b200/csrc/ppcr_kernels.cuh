@@ -38,13 +38,18 @@
 namespace ppcr {
 
 constexpr int kSearchThreads = 128;  // one query per thread
-constexpr int kEvalThreads = 256;
+constexpr int kEvalThreads = 256;      // float64 ("exact") evaluation: one row per thread, grid-stride, moments in shared memory
+constexpr int kEvalFastThreads = 128;  // float32-row evaluation: tiles of 128 rows staged by bulk copies, moments in registers
+constexpr int kEvalFastBlocks = 4;     // resident blocks per SM the fast evaluation is held to (128 registers per thread)
+constexpr int kEvalStages = 3;         // staged tiles per block
 #ifndef PPCR_EVAL_BATCH
 #define PPCR_EVAL_BATCH 5
 #endif
 #ifndef PPCR_EVAL_MIN_BLOCKS
 #define PPCR_EVAL_MIN_BLOCKS 4  // resident blocks per SM the register allocation of k_evalctl is held to
 #endif
+constexpr int kFoldGroup = 16;    // blocks per first-level group of the moment reduction
+constexpr int kFoldChains = 4;    // interleaved chains of the second level
 constexpr int kMailDoubles = 32;  // 24 moments + K + sequence stamp, padded
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -64,8 +69,11 @@ struct PairDev {
     float* nbr_d2;  // optional (stage API only), may be null
     float* nbr_kth; // d2 of the m-th neighbour found by the last search (+inf when fewer were found): warm start
     int* nbr_cnt;
-    double* partials;
+    double* partials;        // [n_eval_blocks][24] per-block moment sums
+    double* group_partials;  // [n_eval_groups][24] sums of kFoldGroup consecutive blocks
+    int* group_ticket;       // [n_eval_groups] blocks of the group that have published
     int n_eval_blocks;
+    int n_eval_groups;
     int max_hist;
     PairState* state;
     const Config* cfg;
@@ -321,11 +329,18 @@ __device__ __forceinline__ float transform_row(const double* T, double x, double
     return __double2float_rn(acc);
 }
 
-__device__ __forceinline__ void search_store(const PairDev& P, int i, int e, unsigned long long key)
+struct SearchOut {  // where a query's results go (copied out of the PairDev once per block)
+    int* __restrict__ nbr_pos;
+    float* __restrict__ nbr_d2;
+    const int* __restrict__ inv_perm;
+    size_t n_pad;
+};
+
+__device__ __forceinline__ void search_store(const SearchOut& O, int i, int e, unsigned long long key)
 {
-    const size_t o = static_cast<size_t>(e) * P.n_pad + i;
-    P.nbr_pos[o] = __ldg(P.inv_perm + key_index(key));
-    if (P.nbr_d2) P.nbr_d2[o] = key_d2(key);
+    const size_t o = static_cast<size_t>(e) * O.n_pad + i;
+    O.nbr_pos[o] = __ldg(O.inv_perm + key_index(key));
+    if (O.nbr_d2) O.nbr_d2[o] = key_d2(key);
 }
 
 constexpr int kSearchChunk = kSearchThreads;  // queries handed out per grab of the work cursor
@@ -353,8 +368,18 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(const PairDev* __rest
     __shared__ int s_chunk;
     const bool moving = st->apply_dT != 0;
     if (threadIdx.x < 12) s_T[threadIdx.x] = st->dT[threadIdx.x];
+    // the geometry and the pointers the walk uses, held in registers (P lives in global memory)
     const int m = P.m;
-    const int n_chunks = (P.n_src + kSearchChunk - 1) / kSearchChunk;
+    const int n_src = P.n_src;
+    const float r2f = P.r2f;
+    const TreeGeom geom = P.tree;
+    const TreeNode* __restrict__ nodes = P.nodes;
+    const float4* __restrict__ tgt_sorted = P.tgt_sorted;
+    const SearchOut out{P.nbr_pos, P.nbr_d2, P.inv_perm, static_cast<size_t>(P.n_pad)};
+    float4* __restrict__ src = P.src;
+    float* __restrict__ nbr_kth = P.nbr_kth;
+    int* __restrict__ nbr_cnt = P.nbr_cnt;
+    const int n_chunks = (n_src + kSearchChunk - 1) / kSearchChunk;
     int stack[2 * kTreeStack];
     int cnt_total = 0;
     for (;;) {
@@ -364,36 +389,36 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(const PairDev* __rest
         const int chunk = s_chunk;
         if (chunk >= n_chunks) break;
         const int i = chunk * kSearchChunk + threadIdx.x;
-        if (i >= P.n_src) continue;
-        float4 q = P.src[i];
-        float bound0 = P.r2f;
+        if (i >= n_src) continue;
+        float4 q = src[i];
+        float bound0 = r2f;
         if (moving) {
             const double x = q.x, y = q.y, z = q.z;
             const float nx = transform_row(s_T, x, y, z), ny = transform_row(s_T + 4, x, y, z),
                         nz = transform_row(s_T + 8, x, y, z);
-            const float prev = P.nbr_kth[i];  // d2 of the m-th neighbour of the last search, +inf if it found fewer
+            const float prev = nbr_kth[i];  // d2 of the m-th neighbour of the last search, +inf if it found fewer
             const float ddx = nx - q.x, ddy = ny - q.y, ddz = nz - q.z;
             const float move = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz) * 1.000001f;
             const float reach = sqrtf(prev) * 1.000001f + move;
-            bound0 = fminf(P.r2f, reach * reach * 1.00001f);  // inf stays inf -> r2f
+            bound0 = fminf(r2f, reach * reach * 1.00001f);  // inf stays inf -> r2f
             q.x = nx;
             q.y = ny;
             q.z = nz;
-            P.src[i] = q;
+            src[i] = q;
         }
         int cnt = 0;
         float kth = __int_as_float(0x7f800000);
         HeapList<kSearchThreads, (VAR & 1) != 0> L;
         L.k = s_heap + threadIdx.x;
         L.init(m);
-        tree_search(P.tree, P.nodes, P.tgt_sorted, q.x, q.y, q.z, P.r2f, bound0, L, stack);
+        tree_search(geom, nodes, tgt_sorted, q.x, q.y, q.z, r2f, bound0, L, stack);
         for (int s = 0; s < L.n; ++s) {
             const unsigned long long key = L.k[s * kSearchThreads];
-            if ((VAR & 1) || key != kKeyInf) search_store(P, i, cnt++, key);
+            if ((VAR & 1) || key != kKeyInf) search_store(out, i, cnt++, key);
         }
         if (L.n == m && L.k[0] != kKeyInf) kth = key_d2(L.k[0]);
-        P.nbr_cnt[i] = cnt;
-        P.nbr_kth[i] = kth;
+        nbr_cnt[i] = cnt;
+        nbr_kth[i] = kth;
         cnt_total += cnt;
     }
     // association size: warp sum, one atomic per warp
@@ -406,7 +431,42 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(const PairDev* __rest
 // weights + normal-equation moments
 // ------------------------------------------------------------------------------------------------------------
 
-constexpr int kCtrlGroups = kEvalThreads / 32;  // partial sums are folded in kCtrlGroups interleaved chains
+PPCR_HD constexpr int eval_threads(bool fast) { return fast ? kEvalFastThreads : kEvalThreads; }
+
+// one staged tile of the fast evaluation: [m][128] positions, [128] counts, [128] source points
+PPCR_HD constexpr size_t eval_stage_bytes(int m) { return static_cast<size_t>(kEvalFastThreads) * (4u * static_cast<size_t>(m) + 20u); }
+PPCR_HD constexpr size_t eval_fast_smem(int m) { return kEvalStages * eval_stage_bytes(m) + 16u * kEvalStages; }
+
+// ---- asynchronous bulk copies (TMA, 1-D) completing on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
 
 __device__ __forceinline__ double ld_volatile_f64(const double* p)
 {
@@ -518,60 +578,96 @@ __device__ __forceinline__ void warp_controller(PairState* st, const Config* cfg
 
 static_assert(sizeof(PairState) % 8 == 0 && sizeof(Config) % 8 == 0, "copied as 64-bit words");
 
-// The float32 row loop of k_evalctl: one source row per thread, grid-stride.  The neighbour records of a row are
-// kU slots apart in the slot-major planes (each a coalesced 512-byte read per warp); full batches of kU records are
-// loaded without predicates before their arithmetic, the ragged tail of a row with.
+// The float32 row loop of k_evalctl.  A block walks tiles of 128 consecutive rows (tile = blockIdx.x, += gridDim.x).
+// What a tile needs from the planes -- m slot segments of positions (512 contiguous bytes each), the counts, the source
+// points -- is brought into shared memory by 1-D bulk copies (TMA) that complete on an mbarrier, kEvalStages tiles
+// ahead of the arithmetic: the latency of the planes never sits on a thread's critical path, and no register is spent
+// on prefetching.  The 16-byte target points are then gathered from the Morton-sorted target (L2 / L1 resident: the
+// neighbours of neighbouring rows are neighbours in that order), kU at a time.  The 24 float64 moments of a thread
+// stay in registers.
+struct EvalStage {
+    unsigned char* base;   // this block's staging area
+    uint32_t bar0;         // shared-space address of the first mbarrier
+    size_t stage_bytes;
+    int m;
+};
+
+// called by the whole first warp: lane 0 arms the barrier, then the lanes issue the m + 2 copies between them
+__device__ __forceinline__ void eval_issue_tile(const PairDev& P, const EvalStage& S, int stage, int tile)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t bar = S.bar0 + 8u * stage;
+    const uint32_t dst = smem_u32(S.base + stage * S.stage_bytes);
+    const size_t row0 = static_cast<size_t>(tile) * kEvalFastThreads;
+    constexpr uint32_t seg = kEvalFastThreads * 4u;
+    if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive_expect_tx(bar, seg * static_cast<uint32_t>(S.m) + seg + kEvalFastThreads * 16u);
+    }
+    __syncwarp();
+    for (int k = lane; k < S.m; k += 32) bulk_g2s(dst + seg * k, P.nbr_pos + static_cast<size_t>(k) * P.n_pad + row0, seg, bar);
+    if (lane == (S.m & 31)) bulk_g2s(dst + seg * S.m, P.nbr_cnt + row0, seg, bar);
+    if (lane == ((S.m + 1) & 31)) bulk_g2s(dst + seg * S.m + seg, P.src + row0, kEvalFastThreads * 16u, bar);
+}
+
 template <int WM, bool SAME>
-__device__ __forceinline__ void eval_rows_fast(const PairDev& P, const Pose& pe, const Pose& pw, const WeightCfg& wc, double* acc)
+__device__ __forceinline__ void eval_rows_fast(const PairDev& P, const EvalStage& S, const Pose& pe, const Pose& pw,
+                                               const WeightCfg& wc, double* __restrict__ racc)
 {
     constexpr int kU = PPCR_EVAL_BATCH;
-    const int stride = P.n_eval_blocks * kEvalThreads;
-    const size_t n_pad = P.n_pad;
-    for (int i = blockIdx.x * kEvalThreads + threadIdx.x; i < P.n_src; i += stride) {
-        const int cnt = P.nbr_cnt[i];
-        if (cnt == 0) continue;
-        const float4 sp = P.src[i];
-        const double sx = sp.x, sy = sp.y, sz = sp.z;
-        double pte[3];
-        apply_pose(pe, sx, sy, sz, pte);
-        PointHL he;
-        split_point(pte, &he);
-        float dw[3] = {0.f, 0.f, 0.f};
-        if (!SAME) {
-            double ptw[3];
-            apply_pose(pw, sx, sy, sz, ptw);
-            pose_delta(pte, ptw, dw);
+    const int n_tiles = (P.n_src + kEvalFastThreads - 1) / kEvalFastThreads;
+    const int tile_step = P.n_eval_blocks;
+    const float4* __restrict__ table = P.tgt_sorted;
+    const int n_src = P.n_src;
+    int j = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += tile_step, ++j) {
+        const int stage = j % kEvalStages;
+        const uint32_t parity = static_cast<uint32_t>(j / kEvalStages) & 1u;
+        while (!mbar_try_wait(S.bar0 + 8u * stage, parity)) {
         }
-        RowAccF row;
-        rowf_begin(&row);
-        const int* rec = P.nbr_pos + i;
-        const float4* __restrict__ table = P.tgt_sorted;
-        int k0 = 0;
-        for (; k0 + kU <= cnt; k0 += kU) {
-            int pos[kU];
-            float4 y[kU];
+        const unsigned char* sb = S.base + stage * S.stage_bytes;
+        const int* s_pos = reinterpret_cast<const int*>(sb) + threadIdx.x;
+        int cnt = reinterpret_cast<const int*>(sb + static_cast<size_t>(kEvalFastThreads) * 4u * S.m)[threadIdx.x];
+        if (tile * kEvalFastThreads + static_cast<int>(threadIdx.x) >= n_src) cnt = 0;
+        if (cnt > 0) {
+            const float4 sp = reinterpret_cast<const float4*>(sb + static_cast<size_t>(kEvalFastThreads) * 4u * (S.m + 1))[threadIdx.x];
+            const double sx = sp.x, sy = sp.y, sz = sp.z;
+            double pte[3];
+            apply_pose(pe, sx, sy, sz, pte);
+            PointHL he;
+            split_point(pte, &he);
+            float dw[3] = {0.f, 0.f, 0.f};
+            if (!SAME) {
+                double ptw[3];
+                apply_pose(pw, sx, sy, sz, ptw);
+                pose_delta(pte, ptw, dw);
+            }
+            RowAccF row;
+            rowf_begin(&row);
+            int k0 = 0;
+            for (; k0 + kU <= cnt; k0 += kU) {
+                float4 y[kU];
 #pragma unroll
-            for (int u = 0; u < kU; ++u) pos[u] = __ldg(rec + static_cast<size_t>(u) * n_pad);
-            rec += static_cast<size_t>(kU) * n_pad;
+                for (int u = 0; u < kU; ++u) y[u] = __ldg(table + s_pos[(k0 + u) * kEvalFastThreads]);
 #pragma unroll
-            for (int u = 0; u < kU; ++u) y[u] = __ldg(table + pos[u]);
+                for (int u = 0; u < kU; ++u) rowf_add_t<WM, SAME>(&row, wc, y[u].x, y[u].y, y[u].z, he, dw);
+            }
+            if (k0 < cnt) {
+                float4 y[kU - 1];
 #pragma unroll
-            for (int u = 0; u < kU; ++u) rowf_add_t<WM, SAME>(&row, wc, y[u].x, y[u].y, y[u].z, he, dw);
+                for (int u = 0; u < kU - 1; ++u)
+                    if (k0 + u < cnt) y[u] = __ldg(table + s_pos[(k0 + u) * kEvalFastThreads]);
+#pragma unroll
+                for (int u = 0; u < kU - 1; ++u)
+                    if (k0 + u < cnt) rowf_add_t<WM, SAME>(&row, wc, y[u].x, y[u].y, y[u].z, he, dw);
+            }
+            rowf_end_s<1>(&row, sx, sy, sz, racc);
         }
-        if (k0 < cnt) {
-            int pos[kU - 1];
-            float4 y[kU - 1];
-#pragma unroll
-            for (int u = 0; u < kU - 1; ++u)
-                if (k0 + u < cnt) pos[u] = __ldg(rec + static_cast<size_t>(u) * n_pad);
-#pragma unroll
-            for (int u = 0; u < kU - 1; ++u)
-                if (k0 + u < cnt) y[u] = __ldg(table + pos[u]);
-#pragma unroll
-            for (int u = 0; u < kU - 1; ++u)
-                if (k0 + u < cnt) rowf_add_t<WM, SAME>(&row, wc, y[u].x, y[u].y, y[u].z, he, dw);
+        __syncthreads();  // every thread is done with this stage: refill it with the tile kEvalStages ahead
+        if (threadIdx.x < 32) {
+            const int next = tile + kEvalStages * tile_step;
+            if (next < n_tiles) eval_issue_tile(P, S, stage, next);
         }
-        rowf_end_s<kEvalThreads>(&row, sx, sy, sz, acc);
     }
 }
 
@@ -584,19 +680,42 @@ struct LoopCtl {   // one per engine
 // publishes its partial sums last -- the fixed-order reduction, the cross-rank exchange (sharded mode), the LM /
 // outer-loop controller and the loop condition of the tick graph.  One launch per LM iteration.
 template <bool kFast>
-__global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(const PairDev* __restrict__ pairs, int n_pairs,
-                                                          LoopCtl* __restrict__ loop, cudaGraphConditionalHandle cond,
-                                                          int use_cond, int max_ticks)
+__global__ void __launch_bounds__(eval_threads(kFast), kFast ? kEvalFastBlocks : PPCR_EVAL_MIN_BLOCKS)
+    k_evalctl(const PairDev* __restrict__ pairs, int n_pairs, LoopCtl* __restrict__ loop, cudaGraphConditionalHandle cond,
+              int use_cond, int max_ticks)
 {
+    constexpr int NT = eval_threads(kFast);
     const PairDev& P = pairs[blockIdx.y];
     PairState* st = P.state;
     __shared__ Pose s_pe, s_pw;
-    __shared__ double s_red[kEvalThreads / 32][kNSum];
+    __shared__ double s_red[NT / 32][kNSum];
+    static_assert(NT / 32 >= kFoldChains && NT >= kNSum * kFoldChains, "the reduction needs kFoldChains rows of s_red");
     __shared__ double s_sum[kMailDoubles];
     __shared__ int s_flag;
     const bool live = st->phase != PH_DONE;
     if (live) {
     if (static_cast<int>(blockIdx.x) >= P.n_eval_blocks) return;
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    EvalStage stg;
+    if constexpr (kFast) {
+        // staging area + one mbarrier per stage; the first kEvalStages tiles are requested before anything else
+        stg.m = P.m;
+        stg.stage_bytes = eval_stage_bytes(stg.m);
+        stg.base = s_dyn;
+        stg.bar0 = smem_u32(s_dyn + kEvalStages * stg.stage_bytes);
+        if (threadIdx.x < 32) {
+            if (threadIdx.x == 0) {
+                for (int k = 0; k < kEvalStages; ++k) mbar_init(stg.bar0 + 8u * k, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncwarp();
+            const int n_tiles = (P.n_src + kEvalFastThreads - 1) / kEvalFastThreads;
+            for (int k = 0; k < kEvalStages; ++k) {
+                const int tile = blockIdx.x + k * P.n_eval_blocks;
+                if (tile < n_tiles) eval_issue_tile(P, stg, k, tile);
+            }
+        }
+    }
     if (threadIdx.x < 12) {
         const double* pe = reinterpret_cast<const double*>(&st->pose_e);
         const double* pw = reinterpret_cast<const double*>(&st->pose_w);
@@ -607,14 +726,9 @@ __global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(
     const Pose& pe = s_pe;
     const Pose& pw = s_pw;
     const WeightCfg wc = P.wcfg;
-    // the 24 float64 accumulators of a thread live in shared memory (one column per thread, conflict-free): they are
-    // touched once per row, and keeping them out of the register file leaves room to have a whole row in flight
-    extern __shared__ double s_acc[];
-    double* acc = s_acc + threadIdx.x;
+    double racc[kNSum];  // fast path: the thread's 24 moments, in registers
 #pragma unroll
-    for (int k = 0; k < kNSum; ++k) acc[k * kEvalThreads] = 0.0;
-    const int stride = P.n_eval_blocks * kEvalThreads;
-    const size_t n_pad = P.n_pad;
+    for (int k = 0; k < kNSum; ++k) racc[k] = 0.0;
     if constexpr (kFast) {
         // pose_w == pose_e on the first evaluation of every outer iteration: one residual serves both uses
         bool same = true;
@@ -623,16 +737,22 @@ __global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(
             same = same && (reinterpret_cast<const double*>(&s_pe)[k] == reinterpret_cast<const double*>(&s_pw)[k]);
         // one instantiation of the row loop per (weight model, same pose): both are uniform over the launch
         switch (weight_mode(wc) * 2 + (same ? 1 : 0)) {
-            case WM_T_H4 * 2: eval_rows_fast<WM_T_H4, false>(P, pe, pw, wc, acc); break;
-            case WM_T_H4 * 2 + 1: eval_rows_fast<WM_T_H4, true>(P, pe, pw, wc, acc); break;
-            case WM_T_INT * 2: eval_rows_fast<WM_T_INT, false>(P, pe, pw, wc, acc); break;
-            case WM_T_INT * 2 + 1: eval_rows_fast<WM_T_INT, true>(P, pe, pw, wc, acc); break;
-            case WM_T_REAL * 2: eval_rows_fast<WM_T_REAL, false>(P, pe, pw, wc, acc); break;
-            case WM_T_REAL * 2 + 1: eval_rows_fast<WM_T_REAL, true>(P, pe, pw, wc, acc); break;
-            case WM_GAUSS * 2: eval_rows_fast<WM_GAUSS, false>(P, pe, pw, wc, acc); break;
-            default: eval_rows_fast<WM_GAUSS, true>(P, pe, pw, wc, acc); break;
+            case WM_T_H4 * 2: eval_rows_fast<WM_T_H4, false>(P, stg, pe, pw, wc, racc); break;
+            case WM_T_H4 * 2 + 1: eval_rows_fast<WM_T_H4, true>(P, stg, pe, pw, wc, racc); break;
+            case WM_T_INT * 2: eval_rows_fast<WM_T_INT, false>(P, stg, pe, pw, wc, racc); break;
+            case WM_T_INT * 2 + 1: eval_rows_fast<WM_T_INT, true>(P, stg, pe, pw, wc, racc); break;
+            case WM_T_REAL * 2: eval_rows_fast<WM_T_REAL, false>(P, stg, pe, pw, wc, racc); break;
+            case WM_T_REAL * 2 + 1: eval_rows_fast<WM_T_REAL, true>(P, stg, pe, pw, wc, racc); break;
+            case WM_GAUSS * 2: eval_rows_fast<WM_GAUSS, false>(P, stg, pe, pw, wc, racc); break;
+            default: eval_rows_fast<WM_GAUSS, true>(P, stg, pe, pw, wc, racc); break;
         }
     } else {
+        // float64 path: the 24 accumulators of a thread live in shared memory (one column per thread, conflict-free)
+        double* acc = reinterpret_cast<double*>(s_dyn) + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < kNSum; ++k) acc[k * kEvalThreads] = 0.0;
+        const int stride = P.n_eval_blocks * kEvalThreads;
+        const size_t n_pad = P.n_pad;
         for (int i = blockIdx.x * kEvalThreads + threadIdx.x; i < P.n_src; i += stride) {
             const int cnt = P.nbr_cnt[i];
             if (cnt == 0) continue;
@@ -650,12 +770,14 @@ __global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(
             }
             row_end_s<kEvalThreads>(&row, sx, sy, sz, acc);
         }
+#pragma unroll
+        for (int k = 0; k < kNSum; ++k) racc[k] = acc[k * kEvalThreads];
     }
     // fixed-shape reduction: xor-shuffle tree inside the warp, then warps in index order
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < kNSum; ++k) {
-        double v = acc[k * kEvalThreads];
+        double v = racc[k];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
         if (lane == 0) s_red[warp][k] = v;
     }
@@ -663,39 +785,68 @@ __global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(
     if (threadIdx.x < kNSum) {
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < kEvalThreads / 32; ++w) v += s_red[w][threadIdx.x];
+        for (int w = 0; w < NT / 32; ++w) v += s_red[w][threadIdx.x];
         P.partials[static_cast<size_t>(blockIdx.x) * kNSum + threadIdx.x] = v;
     }
-    // ---- last block standing runs the controller --------------------------------------------------------------
+    // ---- two-level, fixed-order reduction; the block that finishes it runs the controller ----------------------
+    // Level 1: the last block of every group of kFoldGroup consecutive blocks to publish adds the group's partial sums
+    // in block order.  Level 2: the last group to finish adds the group sums in kFoldChains interleaved chains.  Both
+    // orders are fixed, so the result does not depend on which blocks happen to be last; two short rounds of L2 reads
+    // replace one long serial pass over every block's partial sums.
+    const int group = blockIdx.x / kFoldGroup;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_flag = (atomicAdd(&st->eval_ticket, 1) == P.n_eval_blocks - 1);
+    if (threadIdx.x == 0) {
+        const int members = min(kFoldGroup, P.n_eval_blocks - group * kFoldGroup);
+        s_flag = (atomicAdd(&P.group_ticket[group], 1) == members - 1);
+    }
+    __syncthreads();
+    if (!s_flag) return;
+    __threadfence();
+    if (threadIdx.x < kNSum) {
+        const int b0 = group * kFoldGroup;
+        const int members = min(kFoldGroup, P.n_eval_blocks - b0);
+        const double* base = P.partials + static_cast<size_t>(b0) * kNSum + threadIdx.x;
+        double t[kFoldGroup];
+#pragma unroll
+        for (int u = 0; u < kFoldGroup; ++u) t[u] = u < members ? __ldcg(base + static_cast<size_t>(u) * kNSum) : 0.0;
+        double v = 0.0;
+#pragma unroll
+        for (int u = 0; u < kFoldGroup; ++u)
+            if (u < members) v += t[u];
+        P.group_partials[static_cast<size_t>(group) * kNSum + threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) P.group_ticket[group] = 0;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_flag = (atomicAdd(&st->eval_ticket, 1) == P.n_eval_groups - 1);
     __syncthreads();
     if (!s_flag) return;
     __threadfence();
     if (threadIdx.x == 0) st->eval_ticket = 0;
     if (use_cond & 2) return;  // timing probe (ppcr_time_kernel): the streaming part alone
     {
-        // group g folds blocks g, g + G, g + 2G, ... in order (loads issued eight at a time), then the groups in order
-        double v = 0.0;
-        if (lane < kNSum) {
-            const double* base = P.partials + lane;
-            int b = warp;
-            for (; b + 7 * kCtrlGroups < P.n_eval_blocks; b += 8 * kCtrlGroups) {
+        // chain q adds groups q, q + kFoldChains, ... in order (all loads of a chain issued together), then the chains in order
+        if (threadIdx.x < kNSum * kFoldChains) {
+            const int k = threadIdx.x % kNSum, q = threadIdx.x / kNSum;
+            const double* base = P.group_partials + k;
+            double v = 0.0;
+            int g = q;
+            for (; g + 7 * kFoldChains < P.n_eval_groups; g += 8 * kFoldChains) {
                 double t[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] = __ldcg(base + static_cast<size_t>(b + u * kCtrlGroups) * kNSum);
+                for (int u = 0; u < 8; ++u) t[u] = __ldcg(base + static_cast<size_t>(g + u * kFoldChains) * kNSum);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) v += t[u];
             }
-            for (; b < P.n_eval_blocks; b += kCtrlGroups) v += __ldcg(base + static_cast<size_t>(b) * kNSum);
-            s_red[warp][lane] = v;
+            for (; g < P.n_eval_groups; g += kFoldChains) v += __ldcg(base + static_cast<size_t>(g) * kNSum);
+            s_red[q][k] = v;
         }
         __syncthreads();
         if (threadIdx.x < kNSum) {
             double t = 0.0;
 #pragma unroll
-            for (int w = 0; w < kCtrlGroups; ++w) t += s_red[w][threadIdx.x];
+            for (int q = 0; q < kFoldChains; ++q) t += s_red[q][threadIdx.x];
             s_sum[threadIdx.x] = t;
         }
         __syncthreads();
@@ -766,9 +917,9 @@ __global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(
         __shared__ PairState s_state;
         __shared__ Config s_cfg;
         constexpr int kStateWords = sizeof(PairState) / 8, kCfgWords = sizeof(Config) / 8;
-        for (int k = threadIdx.x; k < kStateWords; k += kEvalThreads)
+        for (int k = threadIdx.x; k < kStateWords; k += NT)
             reinterpret_cast<unsigned long long*>(&s_state)[k] = __ldcg(reinterpret_cast<const unsigned long long*>(st) + k);
-        for (int k = threadIdx.x; k < kCfgWords; k += kEvalThreads)
+        for (int k = threadIdx.x; k < kCfgWords; k += NT)
             reinterpret_cast<unsigned long long*>(&s_cfg)[k] = reinterpret_cast<const unsigned long long*>(P.cfg)[k];
         __shared__ CtrlShared s_ctrl;
         __syncthreads();
@@ -784,7 +935,7 @@ __global__ void __launch_bounds__(kEvalThreads, PPCR_EVAL_MIN_BLOCKS) k_evalctl(
                 warp_controller(&s_state, &s_cfg, &s_ctrl, P.history, P.stats, P.max_hist, max_ticks, threadIdx.x);
         }
         __syncthreads();
-        for (int k = threadIdx.x; k < kStateWords; k += kEvalThreads)
+        for (int k = threadIdx.x; k < kStateWords; k += NT)
             reinterpret_cast<unsigned long long*>(st)[k] = reinterpret_cast<const unsigned long long*>(&s_state)[k];
         __syncthreads();
     }

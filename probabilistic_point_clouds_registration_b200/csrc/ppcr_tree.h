@@ -218,6 +218,40 @@ PPCR_HD void tree_split_node(const TreeGeom& g, const unsigned long long* keys, 
     nodes[ni] = parent;
 }
 
+// ---- loads ---------------------------------------------------------------------------------------------------
+//
+// On the device every node / point read is an explicit 128-bit read-only load: the pointers come out of a structure in
+// global memory, so without this the compiler emits generic 32-bit loads (six per node, two per point).
+
+PPCR_HD float4 load_point(const float4* p)
+{
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+PPCR_HD TreeNode load_node(const TreeNode* n)
+{
+#if defined(__CUDA_ARCH__)
+    const int4 a = __ldg(reinterpret_cast<const int4*>(n));
+    const int4 b = __ldg(reinterpret_cast<const int4*>(n) + 1);
+    TreeNode t;
+    t.cx = __int_as_float(a.x);
+    t.cy = __int_as_float(a.y);
+    t.cz = __int_as_float(a.z);
+    t.half = __int_as_float(a.w);
+    t.begin = b.x;
+    t.end = b.y;
+    t.child = b.z;
+    t.mask = b.w;
+    return t;
+#else
+    return *n;
+#endif
+}
+
 // ---- top-m list ----------------------------------------------------------------------------------------------
 //
 // Kept DESCENDING: k[0] is the current worst of the m best, k[m-1] the best; slots >= m are pinned to 0 (below
@@ -368,7 +402,7 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
     int pend[2 * kPend];
     int sp = 0, np = 0;
     {
-        const TreeNode root = nodes[0];
+        const TreeNode root = load_node(nodes);
         if (root.end <= root.begin) return;
         if (root.child < 0) {
             pend[0] = 0;
@@ -390,7 +424,7 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
                 continue;
             }
             PPCR_STAT(opens, 1);
-            const TreeNode n = nodes[stack[2 * sp]];
+            const TreeNode n = load_node(nodes + stack[2 * sp]);
             // Children far-to-near, so that the octant holding q is opened / scanned first.  The lower bound of a
             // child box is a sum of three per-axis gaps, each of which takes one of two values (the child's half on
             // q's side of the centre plane, or the other one): six gaps serve all eight children.
@@ -432,7 +466,7 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
                 PPCR_STAT(leaves_skipped, 1);
                 continue;
             }
-            const TreeNode n = nodes[pend[2 * np]];
+            const TreeNode n = load_node(nodes + pend[2 * np]);
             PPCR_STAT(leaves, 1);
             PPCR_STAT(points, n.end - n.begin);
             // 32 points at a time, in two passes so that the threads of a warp stay together: first a plain distance
@@ -443,7 +477,7 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
                 const int cnt = n.end - j0 < 32 ? n.end - j0 : 32;
                 uint32_t pass = 0;
                 for (int t = 0; t < cnt; ++t) {
-                    const float4 p = pts[j0 + t];
+                    const float4 p = load_point(pts + j0 + t);
                     const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
                     if (d2 <= bound_d2) pass |= 1u << t;
                 }
@@ -451,7 +485,7 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
                     const int t = lowest_bit(pass);
                     pass &= pass - 1;
                     PPCR_STAT(survivors, 1);
-                    const float4 p = pts[j0 + t];
+                    const float4 p = load_point(pts + j0 + t);
                     const float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
                     if (d2 <= bound_d2) {  // the bound may have shrunk since the first pass
                         const unsigned long long k2 = make_key(d2, static_cast<int>(float_bits(p.w)));
