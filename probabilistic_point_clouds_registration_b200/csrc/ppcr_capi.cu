@@ -125,6 +125,17 @@ struct Trace {
 static int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 static int g_sm_count = 0;
+
+// the search kernel; PPCR_SEARCH_VARIANT selects a tuning variant (0 is the product)
+using SearchKernel = void (*)(const PairDev*);
+static SearchKernel search_kernel()
+{
+    static const int variant = getenv("PPCR_SEARCH_VARIANT") ? atoi(getenv("PPCR_SEARCH_VARIANT")) : 0;
+    switch (variant) {
+        case 1: return k_search<1>;
+        default: return k_search<0>;
+    }
+}
 constexpr size_t kEvalSmem = static_cast<size_t>(kNSum) * kEvalThreads * sizeof(double);  // per-thread moment columns
 constexpr int kDefaultLeafCap = 32;
 
@@ -664,13 +675,10 @@ static void engine_commit(Engine& E)
         E.eval_smem = kEvalSmem;
     }
     if (E.search_smem > 48 * 1024)
-    {
-        CK(cudaFuncSetAttribute(k_search<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.search_smem)));
-        CK(cudaFuncSetAttribute(k_search<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.search_smem)));
-    }
+        CK(cudaFuncSetAttribute(search_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.search_smem)));
     {   // persistent grid: exactly as many blocks as the device keeps resident
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search<1>, kSearchThreads, E.search_smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel(), kSearchThreads, E.search_smem));
         E.search_blocks_per_sm = std::max(1, per_sm);
     }
     const int tiles = std::max(1, std::min(ceil_div(max_src, kSearchChunk), E.search_blocks_per_sm * std::max(g_sm_count, 1)));
@@ -718,9 +726,7 @@ static void launch_search(Engine& E)
 {
     const int np = static_cast<int>(E.pairs.size());
     dim3 grid(E.max_tiles, np);
-    static const int variant = getenv("PPCR_SEARCH_VARIANT") ? atoi(getenv("PPCR_SEARCH_VARIANT")) : 0;  // tuning only
-    if (variant & 1) k_search<1><<<grid, kSearchThreads, E.search_smem, E.stream>>>(E.d_pairs.p);
-    else k_search<0><<<grid, kSearchThreads, E.search_smem, E.stream>>>(E.d_pairs.p);
+    search_kernel()<<<grid, kSearchThreads, E.search_smem, E.stream>>>(E.d_pairs.p);
 }
 
 // weights + moments + (in its last block) reduction, controller and loop condition

@@ -402,14 +402,36 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
     int pend[2 * kPend];
     int sp = 0, np = 0;
     {
-        const TreeNode root = load_node(nodes);
-        if (root.end <= root.begin) return;
-        if (root.child < 0) {
-            pend[0] = 0;
+        // Start at the deepest node whose subtree holds every target within the bound, not at the root: while the
+        // search ball (inflated by twice the binning slack, so that a point's side of a centre plane is certain) lies
+        // on one side of all three centre planes of a node, only that child can hold candidates.  One comparison per
+        // axis and level replaces opening the node (eight child tests) on the shared upper part of every query's path.
+        TreeNode n = load_node(nodes);
+        if (n.end <= n.begin) return;
+        int at = 0;
+        const float rho = sqrtf(bound_d2) * 1.00001f + 2.0f * g.slack;
+        const float lox = qx - rho, hix = qx + rho, loy = qy - rho, hiy = qy + rho, loz = qz - rho, hiz = qz + rho;
+        bool leaf = n.child < 0;
+        while (!leaf) {
+            int oct;
+            if (lox >= n.cx) oct = 1;
+            else if (hix < n.cx) oct = 0;
+            else break;
+            if (loy >= n.cy) oct |= 2;
+            else if (!(hiy < n.cy)) break;
+            if (loz >= n.cz) oct |= 4;
+            else if (!(hiz < n.cz)) break;
+            if (!((n.mask >> oct) & 1)) return;  // the only octant the ball touches is empty
+            at = n.child + oct;
+            leaf = ((n.mask >> (16 + oct)) & 1) != 0;
+            if (!leaf) n = load_node(nodes + at);
+        }
+        if (leaf) {
+            pend[0] = at;
             pend[1] = 0;  // float bits of 0.0f
             np = 1;
         } else {
-            stack[0] = 0;
+            stack[0] = at;
             stack[1] = 0;
             sp = 1;
         }
