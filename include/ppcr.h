@@ -177,7 +177,9 @@ typedef struct ppcr_pair {
     const float* tgt_xyzw; int64_t n_tgt;
 } ppcr_pair;
 
-/* Registers n_pairs independent pairs with the same parameters on one device, `slots` pairs in flight at a time.
+/* Registers n_pairs independent pairs with the same parameters on one device.  `slots` lanes (host threads, each with
+ * its own stream and device-side iteration loop) pull pairs from a shared counter, so the set-up of one pair overlaps the
+ * iterations of the others and small pairs fill the device together; slots <= 0 picks the default (6).
  * out_T: [n_pairs][16] final transforms; out_n_outer[n_pairs]; out_corr[n_pairs] = sum over outer iterations of
  * the association size.  Pair buffers are host pointers unless options->input_on_device. */
 ppcr_status ppcr_align_batch(const ppcr_pair* pairs, int32_t n_pairs, const ppcr_params* params,

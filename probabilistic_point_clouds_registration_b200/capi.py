@@ -354,7 +354,7 @@ def transform(cloud, T):
     return out
 
 
-def align_batch(pairs, params: Params, options: Options | None = None, slots=16):
+def align_batch(pairs, params: Params, options: Options | None = None, slots=0):
     """pairs: list of (source, target) numpy clouds (or (src_ptr, n_src, tgt_ptr, n_tgt) device tuples when
     options.input_on_device).  Returns (T [n,4,4], n_outer [n], correspondences [n])."""
     n = len(pairs)

@@ -17,8 +17,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ppcr_kernels.cuh"
@@ -294,11 +296,18 @@ static void select_device(int device)
 }
 
 // one small pinned word per host thread for the "still running?" read-back of the host-stepped driver
+struct PinnedWord {
+    int* p = nullptr;
+    ~PinnedWord()
+    {
+        if (p) cudaFreeHost(p);  // a lane thread of ppcr_align_batch ends with its call
+    }
+};
 static int* pinned_flag()
 {
-    static thread_local int* p = nullptr;
-    if (!p) CK(cudaMallocHost(&p, 4 * sizeof(int)));
-    return p;
+    static thread_local PinnedWord w;
+    if (!w.p) CK(cudaMallocHost(&w.p, 4 * sizeof(int)));
+    return w.p;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -668,14 +677,22 @@ static void engine_commit(Engine& E)
     CK(cudaMemcpyAsync(E.d_pairs.p, host.data(), sizeof(PairDev) * np, cudaMemcpyHostToDevice, E.stream));
     CK(cudaStreamSynchronize(E.stream));
     E.search_smem = static_cast<size_t>(E.params.max_neighbours) * kSearchThreads * sizeof(unsigned long long);
-    if (!E.opts.exact_weights) {
-        E.eval_smem = eval_fast_smem(max_m);
-        CK(cudaFuncSetAttribute(k_evalctl<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.eval_smem)));
-    } else {
-        E.eval_smem = kEvalSmem;
+    E.eval_smem = E.opts.exact_weights ? kEvalSmem : eval_fast_smem(max_m);
+    {
+        // the opt-in shared-memory sizes are per function and process wide: only ever raise them (handles of several host
+        // threads, e.g. the lanes of ppcr_align_batch, launch the same kernels with different sizes)
+        static std::mutex attr_mutex;
+        static size_t eval_fast_max[64] = {}, search_max[64] = {};
+        std::lock_guard<std::mutex> lock(attr_mutex);
+        if (!E.opts.exact_weights && E.eval_smem > eval_fast_max[E.device]) {
+            CK(cudaFuncSetAttribute(k_evalctl<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.eval_smem)));
+            eval_fast_max[E.device] = E.eval_smem;
+        }
+        if (E.search_smem > 48 * 1024 && E.search_smem > search_max[E.device]) {
+            CK(cudaFuncSetAttribute(search_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.search_smem)));
+            search_max[E.device] = E.search_smem;
+        }
     }
-    if (E.search_smem > 48 * 1024)
-        CK(cudaFuncSetAttribute(search_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.search_smem)));
     {   // persistent grid: exactly as many blocks as the device keeps resident
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel(), kSearchThreads, E.search_smem));
@@ -1520,28 +1537,61 @@ ppcr_status ppcr_align_batch(const ppcr_pair* pairs, int32_t n_pairs, const ppcr
     if (!pairs || n_pairs < 0 || !params || !out_T) return fail(PPCR_ERR_INVALID, "bad argument");
     return guarded([&] {
         if (n_pairs == 0) return;
-        Engine E;
-        engine_init(E, *params, options);
-        if (slots <= 0) slots = 16;
-        slots = std::min(slots, n_pairs);
-        E.pairs.resize(slots);
-        const bool on_dev = E.opts.input_on_device != 0;
-        for (int base = 0; base < n_pairs; base += slots) {
-            const int wave = std::min(slots, n_pairs - base);
-            for (int s = 0; s < slots; ++s) {
-                const ppcr_pair& pr = pairs[base + std::min(s, wave - 1)];  // pad a short last wave with a repeat
-                pair_setup(E, E.pairs[s], pr.src_xyzw, pr.n_src, pr.tgt_xyzw, pr.n_tgt, on_dev);
-            }
-            engine_commit(E);
-            run_to_completion(E);
-            for (int s = 0; s < wave; ++s) {
-                PairState f = download_state(E, s);
-                check_state_error(f);
-                memcpy(out_T + static_cast<size_t>(base + s) * 16, f.T_total, sizeof(double) * 16);
-                if (out_n_outer) out_n_outer[base + s] = f.current_iteration;
-                if (out_corr) out_corr[base + s] = f.K_total;
-            }
+        // `slots` lanes, each a host thread with its own engine and stream, pull pairs from a shared counter: the set-up
+        // of one pair (upload, sorts, tree build) overlaps the iterations of the others, a 120k-point pair does not fill
+        // 148 SMs on its own, and a lane that draws a pair needing few outer iterations moves on at once.
+        if (slots <= 0) slots = 6;
+        const int lanes = std::min(slots, n_pairs);
+        ppcr_options lane_opt;
+        if (options) lane_opt = *options; else ppcr_default_options(&lane_opt);
+        if (lane_opt.stream && lanes > 1) {
+            // device-resident inputs were produced on the caller's stream: wait for them, then use one stream per lane
+            CK(cudaSetDevice(lane_opt.device));
+            CK(cudaStreamSynchronize(static_cast<cudaStream_t>(lane_opt.stream)));
+            lane_opt.stream = nullptr;
         }
+        std::atomic<int> next{0};
+        std::mutex err_mutex;
+        StatusError first_error{PPCR_OK, ""};
+        auto lane = [&]() {
+            try {
+                Engine E;
+                engine_init(E, *params, &lane_opt);
+                E.pairs.resize(1);
+                const bool on_dev = E.opts.input_on_device != 0;
+                for (;;) {
+                    const int i = next.fetch_add(1);
+                    if (i >= n_pairs) break;
+                    {
+                        std::lock_guard<std::mutex> lock(err_mutex);
+                        if (first_error.code != PPCR_OK) break;
+                    }
+                    const ppcr_pair& pr = pairs[i];
+                    pair_setup(E, E.pairs[0], pr.src_xyzw, pr.n_src, pr.tgt_xyzw, pr.n_tgt, on_dev);
+                    engine_commit(E);
+                    run_to_completion(E);
+                    PairState f = download_state(E, 0);
+                    check_state_error(f);
+                    memcpy(out_T + static_cast<size_t>(i) * 16, f.T_total, sizeof(double) * 16);
+                    if (out_n_outer) out_n_outer[i] = f.current_iteration;
+                    if (out_corr) out_corr[i] = f.K_total;
+                }
+            } catch (const StatusError& e) {
+                std::lock_guard<std::mutex> lock(err_mutex);
+                if (first_error.code == PPCR_OK) first_error = e;
+            } catch (const std::exception& e) {
+                std::lock_guard<std::mutex> lock(err_mutex);
+                if (first_error.code == PPCR_OK) first_error = StatusError{PPCR_ERR_CUDA, e.what()};
+            }
+        };
+        if (lanes == 1) {
+            lane();
+        } else {
+            std::vector<std::thread> threads;
+            for (int t = 0; t < lanes; ++t) threads.emplace_back(lane);
+            for (auto& t : threads) t.join();
+        }
+        if (first_error.code != PPCR_OK) throw first_error;
     });
 }
 
