@@ -101,7 +101,8 @@ def lib():
             raise FileNotFoundError(
                 f"{LIB_PATH} is missing: build it with `python -m probabilistic_point_clouds_registration_b200.build` "
                 "(there is no CPU fallback)")
-        L = C.CDLL(LIB_PATH)
+        # PPCR_CUDA_LIB: a differently tuned build of the same library (tools/tune_build.sh), tuning runs only
+        L = C.CDLL(os.environ.get("PPCR_CUDA_LIB", LIB_PATH))
         vp, i32, i64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
         L.ppcr_last_error.restype = C.c_char_p
         L.ppcr_version.restype = C.c_char_p

@@ -40,8 +40,14 @@ namespace ppcr {
 constexpr int kSearchThreads = 128;  // one query per thread
 constexpr int kEvalThreads = 256;      // float64 ("exact") evaluation: one row per thread, grid-stride, moments in shared memory
 constexpr int kEvalFastThreads = 128;  // float32-row evaluation: tiles of 128 rows staged by bulk copies, moments in registers
-constexpr int kEvalFastBlocks = 4;     // resident blocks per SM the fast evaluation is held to (128 registers per thread)
-constexpr int kEvalStages = 3;         // staged tiles per block
+#ifndef PPCR_EVAL_FAST_BLOCKS
+#define PPCR_EVAL_FAST_BLOCKS 4
+#endif
+constexpr int kEvalFastBlocks = PPCR_EVAL_FAST_BLOCKS;  // resident blocks per SM the fast evaluation is held to (4: 128 registers per thread)
+#ifndef PPCR_EVAL_STAGES
+#define PPCR_EVAL_STAGES 3
+#endif
+constexpr int kEvalStages = PPCR_EVAL_STAGES;  // staged tiles per block
 #ifndef PPCR_EVAL_BATCH
 #define PPCR_EVAL_BATCH 5
 #endif
@@ -505,11 +511,12 @@ __device__ __noinline__ void ctrl_finish(PairState* st, const Config* cfg, doubl
     outer_finish(st, cfg, history, stats, max_hist);
 }
 
-// (Hs + diag(D)^2) y = gs, rows of the factor spread over lanes 0..6; returns validity in every lane
+// (Hs + diag(D2)) y = gs, rows of the factor spread over lanes 0..6 (same operation order per entry as the serial
+// solve_damped: inverse diagonal, no division); returns validity in every lane
 __device__ __forceinline__ int warp_solve_damped(const PairState* st, CtrlShared* sh, int lane)
 {
     if (lane < kNP)
-        for (int c = 0; c < kNP; ++c) sh->L[lane][c] = st->Hs[lane * kNP + c] + (lane == c ? sh->D[lane] * sh->D[lane] : 0.0);
+        for (int c = 0; c < kNP; ++c) sh->L[lane][c] = st->Hs[lane * kNP + c] + (lane == c ? sh->D[lane] : 0.0);
     if (lane == 0) sh->flag = 1;
     __syncwarp();
     for (int c = 0; c < kNP; ++c) {
@@ -517,14 +524,14 @@ __device__ __forceinline__ int warp_solve_damped(const PairState* st, CtrlShared
             double d = sh->L[c][c];
             for (int k = 0; k < c; ++k) d -= sh->L[c][k] * sh->L[c][k];
             if (!(d > 0.0)) sh->flag = 0;
-            else sh->L[c][c] = sqrt(d);
+            else sh->L[c][c] = inv_sqrt(d);
         }
         __syncwarp();
         if (!sh->flag) break;
         if (lane > c && lane < kNP) {
             double s = sh->L[lane][c];
             for (int k = 0; k < c; ++k) s -= sh->L[lane][k] * sh->L[c][k];
-            sh->L[lane][c] = s / sh->L[c][c];
+            sh->L[lane][c] = s * sh->L[c][c];
         }
         __syncwarp();
     }
@@ -533,12 +540,12 @@ __device__ __forceinline__ int warp_solve_damped(const PairState* st, CtrlShared
         for (int r = 0; r < kNP; ++r) {
             double s = st->gs[r];
             for (int k = 0; k < r; ++k) s -= sh->L[r][k] * z[k];
-            z[r] = s / sh->L[r][r];
+            z[r] = s * sh->L[r][r];
         }
         for (int r = kNP - 1; r >= 0; --r) {
             double s = z[r];
             for (int k = r + 1; k < kNP; ++k) s -= sh->L[k][r] * sh->y[k];
-            sh->y[r] = s / sh->L[r][r];
+            sh->y[r] = s * sh->L[r][r];
         }
     }
     __syncwarp();

@@ -2,7 +2,7 @@
 // Levenberg-Marquardt controller, pose composition and the outer convergence test.
 //
 // Everything here is plain C++ qualified PPCR_HD so that the single-CTA controller kernel (ppcr_kernels.cu) and
-// the CPU unit tests of the host logic (tests/emu) run the same source.  No CUDA intrinsics in this file.
+// the CPU unit tests of the host logic (tests/emu) run the same source (one device-only shortcut: inv_sqrt).
 //
 // What it replaces in the reference (paths relative to the reference tree):
 //   * ceres::Solve on the problem built at prob_point_cloud_registration_iteration.hpp:24-57 with the options
@@ -104,8 +104,9 @@ struct PairState {
 
 PPCR_HD void pose_from_x(const double* x, Pose* p)
 {
-    const double n = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
-    const double a = x[0] / n, b0 = x[1] / n, b1 = x[2] / n, b2 = x[3] / n;
+    // one reciprocal instead of four divisions: this runs on a single device thread between two passes over the cloud
+    const double inv_n = 1.0 / sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+    const double a = x[0] * inv_n, b0 = x[1] * inv_n, b1 = x[2] * inv_n, b2 = x[3] * inv_n;
     // R = I + 2a[b]x + 2[b]x^2  (the unit-quaternion rotation Ceres applies after normalising)
     p->R[0] = 1.0 - 2.0 * (b1 * b1 + b2 * b2);
     p->R[1] = 2.0 * (b0 * b1 - a * b2);
@@ -124,8 +125,8 @@ PPCR_HD void pose_from_x(const double* x, Pose* p)
 // iteration.hpp:59-67 with Eigen's normalize()/toRotationMatrix(): [R | t] as a row-major 4x4
 PPCR_HD void matrix_from_x(const double* x, double* T)
 {
-    const double n = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
-    const double w = x[0] / n, qx = x[1] / n, qy = x[2] / n, qz = x[3] / n;
+    const double inv_n = 1.0 / sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+    const double w = x[0] * inv_n, qx = x[1] * inv_n, qy = x[2] * inv_n, qz = x[3] * inv_n;
     const double tx = 2.0 * qx, ty = 2.0 * qy, tz = 2.0 * qz;
     const double twx = tx * w, twy = ty * w, twz = tz * w;
     const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
@@ -245,33 +246,46 @@ PPCR_HD void expand_moments(const double* S, const double* x, Expanded* out)
     for (int t = 0; t < kExpandTasks; ++t) expand_task(S, N, t, out);
 }
 
-// Solve (Hs + diag(D)^2) y = gs by Cholesky; false when the matrix is not numerically positive definite.
-PPCR_HD bool solve_damped(const double* Hs, const double* gs, const double* D, double* y)
+// 1 / sqrt(d): one reciprocal square root on the device, sqrt + division on the host (last-bit differences only)
+PPCR_HD double inv_sqrt(double d)
+{
+#if defined(__CUDA_ARCH__)
+    return rsqrt(d);
+#else
+    return 1.0 / sqrt(d);
+#endif
+}
+
+// Solve (Hs + diag(D2)) y = gs by Cholesky (D2 = the SQUARED damping diagonal); false when the matrix is not numerically
+// positive definite.  The factor is kept with the INVERSE of its diagonal (L[c][c] holds 1 / l_cc), so the whole solve
+// costs seven reciprocal square roots and no division: on the device this is a dependent chain on one thread.
+PPCR_HD bool solve_damped(const double* Hs, const double* gs, const double* D2, double* y)
 {
     double L[kNP][kNP];
     for (int r = 0; r < kNP; ++r)
-        for (int c = 0; c < kNP; ++c) L[r][c] = Hs[r * kNP + c] + (r == c ? D[r] * D[r] : 0.0);
+        for (int c = 0; c < kNP; ++c) L[r][c] = Hs[r * kNP + c] + (r == c ? D2[r] : 0.0);
     for (int c = 0; c < kNP; ++c) {
         double d = L[c][c];
         for (int k = 0; k < c; ++k) d -= L[c][k] * L[c][k];
         if (!(d > 0.0)) return false;
-        L[c][c] = sqrt(d);
+        const double inv = inv_sqrt(d);
+        L[c][c] = inv;
         for (int r = c + 1; r < kNP; ++r) {
             double s = L[r][c];
             for (int k = 0; k < c; ++k) s -= L[r][k] * L[c][k];
-            L[r][c] = s / L[c][c];
+            L[r][c] = s * inv;
         }
     }
     double z[kNP];
     for (int r = 0; r < kNP; ++r) {
         double s = gs[r];
         for (int k = 0; k < r; ++k) s -= L[r][k] * z[k];
-        z[r] = s / L[r][r];
+        z[r] = s * L[r][r];
     }
     for (int r = kNP - 1; r >= 0; --r) {
         double s = z[r];
         for (int k = r + 1; k < kNP; ++k) s -= L[k][r] * y[k];
-        y[r] = s / L[r][r];
+        y[r] = s * L[r][r];
     }
     return true;
 }
@@ -303,7 +317,7 @@ PPCR_HD double vec_norm7(const double* v)
 
 // FinalizeIteration + ComputeTrustRegionStep of the restated Ceres minimiser, cut at the linear solve so that the
 // controller block can run the 7x7 Cholesky on several threads:
-//   step_prepare  -> false: the minimiser stopped (s->termination says why); true: D holds the damping diagonal
+//   step_prepare  -> false: the minimiser stopped (s->termination says why); true: D2 holds the squared damping diagonal
 //   [solve (Hs + diag(D)^2) y = gs]
 //   step_complete -> 0: candidate ready in s->cand / s->pose_e (evaluate it next), 1: invalid step, prepare again,
 //                    2: the minimiser stopped
@@ -327,7 +341,7 @@ PPCR_HD bool step_prepare(PairState* s, const Config* cfg, double* D)
         for (int p = 0; p < kNP; ++p) s->diag[p] = fmin(fmax(s->Hs[p * kNP + p], kMinDiag), kMaxDiag);
     }
     const double inv_radius = 1.0 / s->radius;
-    for (int p = 0; p < kNP; ++p) D[p] = sqrt(s->diag[p] * inv_radius);
+    for (int p = 0; p < kNP; ++p) D[p] = s->diag[p] * inv_radius;  // (sqrt(diag / radius))^2, what the solve adds to the diagonal
     return true;
 }
 

@@ -107,6 +107,10 @@ void eval(const Cloud& src, const Cloud& tgt, const std::vector<int>& idx, const
 
 }  // namespace
 
+#if defined(PPCR_TREE_STATS)
+static std::vector<float> g_query_cost;
+#endif
+
 extern "C" {
 
 // Full align() with the product's controller.  Returns the number of outer iterations.
@@ -253,10 +257,26 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
     int64_t total = 0;
     int stack[2 * kTreeStack];
     std::vector<unsigned long long> buf(static_cast<size_t>(std::max(m, 1)));
+#if defined(PPCR_TREE_STATS)
+    g_query_cost.assign(static_cast<size_t>(n_src), 0.f);
+#endif
     for (int64_t i = 0; i < n_src; ++i) {
         const float* q = src_xyzw + 4 * i;
         const float bound0 = bounds ? bounds[i] : r2f;
         std::vector<unsigned long long> found;
+#if defined(PPCR_TREE_STATS)
+        const TreeStats before = g_tree_stats;
+        struct CostNote {
+            const TreeStats& b;
+            float& out;
+            ~CostNote()
+            {
+                // rough thread-instruction weights of the search kernel (profiles/): open, scanned point, survivor, insertion
+                out = 120.f * (g_tree_stats.opens - b.opens) + 14.f * (g_tree_stats.points - b.points) +
+                      25.f * (g_tree_stats.survivors - b.survivors) + 65.f * (g_tree_stats.inserts - b.inserts) + 300.f;
+            }
+        } note{before, g_query_cost[static_cast<size_t>(i)]};
+#endif
         auto take = [&](const unsigned long long* k, int cap) {
             for (int s2 = 0; s2 < cap; ++s2) {
                 const int e = m - 1 - s2;
@@ -307,6 +327,10 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
 }
 
 #if defined(PPCR_TREE_STATS)
+void emu_tree_costs(float* out, long long n)
+{
+    for (long long i = 0; i < n && i < static_cast<long long>(g_query_cost.size()); ++i) out[i] = g_query_cost[static_cast<size_t>(i)];
+}
 void emu_tree_stats(long long* out7, int reset)
 {
     const long long v[7] = {g_tree_stats.opens, g_tree_stats.leaves, g_tree_stats.leaves_skipped, g_tree_stats.points,
