@@ -207,7 +207,7 @@ struct Engine {
     // graph driver
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
-    cudaGraphConditionalHandle cond = 0;
+    cudaGraphConditionalHandle cond = 0, cond_search = 0;
     bool graph_ready = false;
     bool graph_failed = false;
     // stage timing
@@ -753,9 +753,9 @@ static void launch_evalctl(Engine& E, bool use_cond, int probe = 0)
     dim3 grid(E.max_eval_blocks, np);
     const int flags = (use_cond ? 1 : 0) | probe;
     if (!E.opts.exact_weights)
-        k_evalctl<true><<<grid, kEvalFastThreads, E.eval_smem, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, flags, E.max_ticks);
+        k_evalctl<true><<<grid, kEvalFastThreads, E.eval_smem, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, E.cond_search, flags, E.max_ticks);
     else
-        k_evalctl<false><<<grid, kEvalThreads, E.eval_smem, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, flags, E.max_ticks);
+        k_evalctl<false><<<grid, kEvalThreads, E.eval_smem, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, E.cond_search, flags, E.max_ticks);
 }
 
 static int launches_per_tick(const Engine& E) { return E.skip_search ? 1 : 2; }
@@ -823,18 +823,32 @@ static bool build_graph(Engine& E)
         e = cudaGraphAddNode(&node, E.graph, nullptr, 0, &np);
         if (e != cudaSuccess) goto bad;
         cudaGraph_t body = np.conditional.phGraph_out[0];
-        e = cudaStreamBeginCaptureToGraph(E.stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
-        if (e != cudaSuccess) goto bad;
-        try {
-            launch_tick(E, true, false);
-        } catch (...) {
-            cudaGraph_t dummy;
-            cudaStreamEndCapture(E.stream, &dummy);
-            goto bad;
+        // body = one tick: [IF a pair is about to search: k_search] -> k_evalctl.  Three ticks out of four are LM
+        // iterations on an unchanged association; the IF node (set by the controller) saves their idle search launch.
+        cudaGraphNode_t if_node = nullptr;
+        if (!E.skip_search) {
+            e = cudaGraphConditionalHandleCreate(&E.cond_search, E.graph, 1, cudaGraphCondAssignDefault);
+            if (e != cudaSuccess) goto bad;
+            cudaGraphNodeParams ip{};
+            ip.type = cudaGraphNodeTypeConditional;
+            ip.conditional.handle = E.cond_search;
+            ip.conditional.type = cudaGraphCondTypeIf;
+            ip.conditional.size = 1;
+            e = cudaGraphAddNode(&if_node, body, nullptr, 0, &ip);
+            if (e != cudaSuccess) goto bad;
+            e = cudaStreamBeginCaptureToGraph(E.stream, ip.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+            if (e != cudaSuccess) goto bad;
+            launch_search(E);
+            e = cudaStreamEndCapture(E.stream, nullptr);
+            if (e != cudaSuccess) goto bad;
         }
-        E.times.ticks -= 1;
-        E.times.total_launches -= launches_per_tick(E);
+        e = cudaStreamBeginCaptureToGraph(E.stream, body, if_node ? &if_node : nullptr, nullptr, if_node ? 1 : 0,
+                                          cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) goto bad;
+        launch_evalctl(E, true);
         e = cudaStreamEndCapture(E.stream, nullptr);
+        if (e != cudaSuccess) goto bad;
+        e = cudaGetLastError();
         if (e != cudaSuccess) goto bad;
     }
     e = cudaGraphInstantiate(&E.graph_exec, E.graph, 0);
@@ -1256,10 +1270,10 @@ ppcr_status ppcr_get_stage_times(ppcr_handle* h, ppcr_stage_times* out)
         Engine& E = h->eng;
         use_engine(E);
         *out = E.times;
-        if (E.graph_ready) {  // the WHILE graph loops on the device: one body execution (4 kernels) per tick
+        if (E.graph_ready) {  // the WHILE graph loops on the device: k_evalctl every tick, k_search once per outer iteration
             const PairState s = download_state(E, 0);
             out->ticks = s.ticks;
-            out->total_launches = E.times.total_launches + launches_per_tick(E) * s.ticks;
+            out->total_launches = E.times.total_launches + s.ticks + (E.skip_search ? 0 : s.current_iteration);
         }
     });
 }

@@ -689,7 +689,7 @@ struct LoopCtl {   // one per engine
 template <bool kFast>
 __global__ void __launch_bounds__(eval_threads(kFast), kFast ? kEvalFastBlocks : PPCR_EVAL_MIN_BLOCKS)
     k_evalctl(const PairDev* __restrict__ pairs, int n_pairs, LoopCtl* __restrict__ loop, cudaGraphConditionalHandle cond,
-              int use_cond, int max_ticks)
+              cudaGraphConditionalHandle cond_search, int use_cond, int max_ticks)
 {
     constexpr int NT = eval_threads(kFast);
     const PairDev& P = pairs[blockIdx.y];
@@ -955,10 +955,17 @@ __global__ void __launch_bounds__(eval_threads(kFast), kFast ? kEvalFastBlocks :
         if (atomicAdd(&loop->pairs_done, 1) == n_pairs - 1) {
             __threadfence();
             loop->pairs_done = 0;
-            int active = 0;
-            for (int p = 0; p < n_pairs; ++p) active |= (*reinterpret_cast<volatile int*>(&pairs[p].state->phase) != PH_DONE);
+            int active = 0, searching = 0;
+            for (int p = 0; p < n_pairs; ++p) {
+                const int phase = *reinterpret_cast<volatile int*>(&pairs[p].state->phase);
+                active |= (phase != PH_DONE);
+                searching |= (phase == PH_SEARCH);
+            }
             loop->active = active;
-            if (use_cond & 1) cudaGraphSetConditional(cond, active ? 1u : 0u);
+            if (use_cond & 1) {
+                cudaGraphSetConditional(cond, active ? 1u : 0u);                 // WHILE: another tick
+                cudaGraphSetConditional(cond_search, searching ? 1u : 0u);       // IF: the next tick starts with a search
+            }
         }
     }
 }
