@@ -1,0 +1,64 @@
+"""BASELINE configs[3]: one large pair, source points sharded over the ranks, target (and its octree) replicated; the
+24 moments are exchanged peer-to-peer from inside the evaluation kernel every LM iteration.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/shard_bench.py [rings] [az] [reps]
+
+Defaults are the 10M-point pair (320 rings x 31250 azimuths).  World size 1 runs the same pair on one GPU.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from probabilistic_point_clouds_registration_b200 import capi, multi, synth  # noqa: E402
+
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rings = int(sys.argv[1]) if len(sys.argv) > 1 else 320
+az = int(sys.argv[2]) if len(sys.argv) > 2 else 31250
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+t0 = time.perf_counter()
+src, tgt, _ = synth.lidar_pair(4, rings, az)
+src, tgt = np.ascontiguousarray(src), np.ascontiguousarray(tgt)
+gen_s = time.perf_counter() - t0
+params = capi.make_params(max_neighbours=10, radius=0.5, dof=5.0)
+lo, hi = multi.slice_bounds(len(src), rank, world)
+# clouds resident in HBM, like bench.py's `value`
+d_src = torch.from_numpy(src[lo:hi]).cuda()
+d_tgt = torch.from_numpy(tgt).cuda()
+opt = capi.make_options(device=local, input_on_device=True)
+times = []
+for rep in range(reps + 1):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with multi.ShardedRegistration(d_src.data_ptr(), d_tgt.data_ptr(), params, rank, world, opt, n_source=hi - lo,
+                                   n_target=len(tgt)) as reg:
+        reg.align()
+        stats = reg.iteration_stats()
+        hist = reg.transformation_history()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    if rep > 0:
+        times.append(dt)
+if rank == 0:
+    corr = sum(s["n_correspondences"] for s in stats)
+    evals = sum(s["lm_iterations"] + 1 for s in stats)
+    ms = 1e3 * float(np.mean(times))
+    print(f"SHARD_BENCH n_gpus={world} n_src={len(src)} n_tgt={len(tgt)} outer={len(stats)} evals={evals} "
+          f"correspondences={corr} ms={ms:.1f} (min {1e3 * min(times):.1f}) corr_per_s={corr / (ms * 1e-3):.3e} gen_s={gen_s:.0f}")
+if world > 1:
+    dist.destroy_process_group()
