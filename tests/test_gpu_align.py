@@ -92,6 +92,29 @@ def test_config1_default_weights_path(capi, oracle, radius, dof):
     _assert_tolerance_parity(hist, stats, ref)
 
 
+@pytest.mark.parametrize("m,dof", [(5, 4.0), (33, 2.5), (64, 5.0), (128, np.inf), (7, 6.0)])
+def test_default_path_weight_models_and_row_lengths(capi, oracle, m, dof):
+    """Every instantiation of the default evaluation's row loop -- t with a half-integer exponent (dof 4), with a real
+    one (dof 2.5), with exponent 4 (dof 5), Gaussian, integer exponent (dof 6: (6+3)/2 is half-integer, dof 7 would be 5)
+    -- at row lengths that are not multiples of the gather batch, exceed one warp of bulk-copy lanes (m > 32) and
+    reach the maximum (128)."""
+    src, tgt, _ = synth.config1_plane_sphere(seed=31, n_plane=900, n_sphere=700)
+    hist, stats, moved, done, ref = _run_both(capi, oracle, src, tgt, exact=False, max_neighbours=m, dof=dof,
+                                              radius=1.0)
+    assert done
+    _assert_tolerance_parity(hist, stats, ref)
+
+
+def test_config2_gaussian_outliers_default_path(capi, oracle):
+    """BASELINE config 2, reduced, through the library defaults: 20% outliers, Gaussian weights, both voxel filters."""
+    src, tgt, _ = synth.lidar_pair(2, 32, 700, outlier_frac=0.2)
+    hist, stats, moved, done, ref = _run_both(capi, oracle, src, tgt, exact=False, max_neighbours=20, dof=np.inf,
+                                              radius=3.0, source_filter_size=0.25, target_filter_size=0.25)
+    assert done
+    assert len(moved) == ref.n_filtered_src < len(src)
+    _assert_tolerance_parity(hist, stats, ref)
+
+
 def test_config3_full_size_pose_parity(capi, oracle):
     """BASELINE config 3 at full size (1M-point pair, -m 10 -r 0.5 -d 5), library defaults, against the oracle run
     to its own stopping rule: final pose within 1e-4 rad / 1e-4 m."""
