@@ -128,14 +128,20 @@ static int ceil_div(long long a, long long b) { return static_cast<int>((a + b -
 
 static int g_sm_count = 0;
 
-// the search kernel; PPCR_SEARCH_VARIANT selects a tuning variant (0 is the product)
+// The search kernel.  The list of the m best candidates is an unordered column with a worst scan up to
+// kScanListMaxM, a binary max-heap above (ppcr_tree.h).  PPCR_SEARCH_VARIANT overrides the choice (tuning only).
+constexpr int kScanListMaxM = 0;   // measured on the 1M-point pair: the heap wins inside the loop (0.61 vs 0.65 ms per search), the column only on a converged pair (0.37 vs 0.43)
 using SearchKernel = void (*)(const PairDev*);
-static SearchKernel search_kernel()
+static SearchKernel search_kernel(int m)
 {
-    static const int variant = getenv("PPCR_SEARCH_VARIANT") ? atoi(getenv("PPCR_SEARCH_VARIANT")) : 0;
+    static const int variant = getenv("PPCR_SEARCH_VARIANT") ? atoi(getenv("PPCR_SEARCH_VARIANT")) : -1;
     switch (variant) {
+        case 0: return k_search<0>;
         case 1: return k_search<1>;
-        default: return k_search<0>;
+        case 2: return k_search<2>;  // heap, without the exact warm bound from the previous neighbours
+        case 4: return k_search<4>;
+        case 6: return k_search<6>;
+        default: return m <= kScanListMaxM ? k_search<4> : k_search<0>;
     }
 }
 constexpr size_t kEvalSmem = static_cast<size_t>(kNSum) * kEvalThreads * sizeof(double);  // per-thread moment columns
@@ -676,7 +682,7 @@ static void engine_commit(Engine& E)
     E.d_pairs.reserve(np);
     CK(cudaMemcpyAsync(E.d_pairs.p, host.data(), sizeof(PairDev) * np, cudaMemcpyHostToDevice, E.stream));
     CK(cudaStreamSynchronize(E.stream));
-    E.search_smem = static_cast<size_t>(E.params.max_neighbours) * kSearchThreads * sizeof(unsigned long long);
+    E.search_smem = static_cast<size_t>(heap_slots(E.params.max_neighbours)) * kSearchThreads * sizeof(unsigned long long);
     E.eval_smem = E.opts.exact_weights ? kEvalSmem : eval_fast_smem(max_m);
     {
         // the opt-in shared-memory sizes are per function and process wide: only ever raise them (handles of several host
@@ -689,13 +695,13 @@ static void engine_commit(Engine& E)
             eval_fast_max[E.device] = E.eval_smem;
         }
         if (E.search_smem > 48 * 1024 && E.search_smem > search_max[E.device]) {
-            CK(cudaFuncSetAttribute(search_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.search_smem)));
+            CK(cudaFuncSetAttribute(search_kernel(E.params.max_neighbours), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.search_smem)));
             search_max[E.device] = E.search_smem;
         }
     }
     {   // persistent grid: exactly as many blocks as the device keeps resident
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel(), kSearchThreads, E.search_smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel(E.params.max_neighbours), kSearchThreads, E.search_smem));
         E.search_blocks_per_sm = std::max(1, per_sm);
     }
     const int tiles = std::max(1, std::min(ceil_div(max_src, kSearchChunk), E.search_blocks_per_sm * std::max(g_sm_count, 1)));
@@ -743,7 +749,7 @@ static void launch_search(Engine& E)
 {
     const int np = static_cast<int>(E.pairs.size());
     dim3 grid(E.max_tiles, np);
-    search_kernel()<<<grid, kSearchThreads, E.search_smem, E.stream>>>(E.d_pairs.p);
+    search_kernel(E.params.max_neighbours)<<<grid, kSearchThreads, E.search_smem, E.stream>>>(E.d_pairs.p);
 }
 
 // weights + moments + (in its last block) reduction, controller and loop condition
@@ -787,11 +793,16 @@ static void launch_final_transform(Engine& E)
 
 static void collect_stage_times(Engine& E)
 {
+    static const bool trace = getenv("PPCR_TRACE_SEARCH") != nullptr;  // per-launch search times on stderr (tools/)
     for (auto& ep : E.events) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) {
             switch (ep.stage) {
-                case ST_SEARCH: E.times.search_ms += ms; E.times.search_launches++; break;
+                case ST_SEARCH:
+                    E.times.search_ms += ms;
+                    E.times.search_launches++;
+                    if (trace && ms > 0.02f) fprintf(stderr, "[ppcr trace] search launch %.3f ms\n", ms);
+                    break;
                 case ST_EVAL: E.times.eval_ms += ms; E.times.eval_launches++; break;
                 case ST_CTRL: E.times.controller_ms += ms; E.times.controller_launches++; break;
                 default: E.times.transform_ms += ms; E.times.transform_launches++; break;

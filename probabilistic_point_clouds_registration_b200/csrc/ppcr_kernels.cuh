@@ -363,8 +363,27 @@ constexpr int kSearchChunk = kSearchThreads;  // queries handed out per grab of 
 // dynamic shared memory per thread): replacing the root and sifting down costs ~log2(m) steps, about half the
 // instructions of a sorted register list at m = 10..20, and works for any m.  Rows are stored in heap order; nothing
 // downstream depends on the order inside a row (the host sorts rows it hands out).
+// VAR bit 0: heap filled by appends; bit 1: no exact warm bound (tuning); bit 2: unordered column + worst scan
 template <int VAR>
-__global__ void __launch_bounds__(kSearchThreads) k_search(const PairDev* __restrict__ pairs)
+struct SearchList {
+    using type = HeapList<kSearchThreads, (VAR & 1) != 0>;
+};
+template <>
+struct SearchList<4> {
+    using type = ScanList<kSearchThreads>;
+};
+template <>
+struct SearchList<6> {
+    using type = ScanList<kSearchThreads>;
+};
+
+#if defined(PPCR_SEARCH_MIN_BLOCKS)  // tuning builds only: ptxas' own choice (48 registers) measured fastest
+#define PPCR_SEARCH_BOUNDS __launch_bounds__(kSearchThreads, PPCR_SEARCH_MIN_BLOCKS)
+#else
+#define PPCR_SEARCH_BOUNDS __launch_bounds__(kSearchThreads)
+#endif
+template <int VAR>
+__global__ void PPCR_SEARCH_BOUNDS k_search(const PairDev* __restrict__ pairs)
 {
     extern __shared__ unsigned long long s_heap[];
     const PairDev& P = pairs[blockIdx.y];
@@ -411,18 +430,42 @@ __global__ void __launch_bounds__(kSearchThreads) k_search(const PairDev* __rest
             q.y = ny;
             q.z = nz;
             src[i] = q;
+            if ((VAR & 2) == 0 && prev < __int_as_float(0x7f800000)) {
+                // A saturated row: its m neighbours of the last search are m distinct targets, so the largest of their
+                // distances to the MOVED query (same arithmetic as the walk, hence the same bits) bounds the new m-th
+                // distance -- usually far tighter than the triangle inequality above, and independent of how far the
+                // cloud moved.  The positions stream from the slot-major plane, the points come from L2 / L1.
+                const int* __restrict__ pp = out.nbr_pos + i;
+                float far2 = 0.f;
+                int k = 0;
+                for (; k + 5 <= m; k += 5) {
+                    int pos[5];
+#pragma unroll
+                    for (int u = 0; u < 5; ++u) pos[u] = pp[static_cast<size_t>(k + u) * out.n_pad];
+                    float4 t[5];
+#pragma unroll
+                    for (int u = 0; u < 5; ++u) t[u] = load_point(tgt_sorted + pos[u]);
+#pragma unroll
+                    for (int u = 0; u < 5; ++u) far2 = fmaxf(far2, dist2_exact(nx, ny, nz, t[u].x, t[u].y, t[u].z));
+                }
+                for (; k < m; ++k) {
+                    const float4 t = load_point(tgt_sorted + pp[static_cast<size_t>(k) * out.n_pad]);
+                    far2 = fmaxf(far2, dist2_exact(nx, ny, nz, t.x, t.y, t.z));
+                }
+                bound0 = fminf(bound0, far2);
+            }
         }
         int cnt = 0;
         float kth = __int_as_float(0x7f800000);
-        HeapList<kSearchThreads, (VAR & 1) != 0> L;
+        typename SearchList<VAR>::type L;
         L.k = s_heap + threadIdx.x;
         L.init(m);
         tree_search(geom, nodes, tgt_sorted, q.x, q.y, q.z, r2f, bound0, L, stack);
         for (int s = 0; s < L.n; ++s) {
             const unsigned long long key = L.k[s * kSearchThreads];
-            if ((VAR & 1) || key != kKeyInf) search_store(out, i, cnt++, key);
+            if ((VAR & 5) || key != kKeyInf) search_store(out, i, cnt++, key);
         }
-        if (L.n == m && L.k[0] != kKeyInf) kth = key_d2(L.k[0]);
+        if (L.kth_key() != kKeyInf) kth = key_d2(L.kth_key());
         nbr_cnt[i] = cnt;
         nbr_kth[i] = kth;
         cnt_total += cnt;

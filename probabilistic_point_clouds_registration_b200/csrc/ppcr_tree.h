@@ -311,6 +311,8 @@ PPCR_HD void tree_mark_leaf_children(TreeNode* nodes, int ni)
 // be rejected before m are known, so no order is needed -- and the heap is built once, when the m-th arrives
 // (Floyd, ~m/2 short sift-downs); from then on a better candidate replaces the root and sifts down.  Entries
 // [0, n) are valid and come out unordered.
+PPCR_HD constexpr int heap_slots(int m) { return m < 1 ? 1 : m; }
+
 template <int STRIDE, bool APPEND = true>
 struct HeapList {
     unsigned long long* k;
@@ -358,6 +360,62 @@ struct HeapList {
             sift_down(0, x);
         }
     }
+    // key of the m-th best, kKeyInf when fewer than m real keys are held
+    PPCR_HD unsigned long long kth_key() const { return n == m ? k[0] : kKeyInf; }
+};
+
+// The m best keys as an UNORDERED column plus the position and key of the current worst in registers.  The first m
+// candidates are appended (one store each); after that a better candidate overwrites the worst and the column is
+// scanned once for the new worst.  That scan has the same trip count (m) in every thread of a warp, so -- unlike
+// the sift-down of the heap, whose length differs from thread to thread -- the threads that insert at the same time
+// stay together; and worst() costs nothing.  m loads + compares per replacement: the cheaper list up to m of a few
+// dozen, which is where the reference's defaults live (max_neighbours = 20, the benchmark's 10); the heap takes over
+// for large m.  Entries [0, n) are valid and come out unordered.
+template <int STRIDE>
+struct ScanList {
+    unsigned long long* k;
+    unsigned long long w;  // key of the worst of the m best; kKeyInf while fewer than m are known
+    int m;
+    int n;
+    int wi;                // its position, valid when n == m
+    PPCR_HD void init(int m_)
+    {
+        m = m_;
+        n = 0;
+        wi = 0;
+        w = kKeyInf;
+    }
+    PPCR_HD unsigned long long worst() const { return w; }
+    PPCR_HD void rescan()
+    {
+        unsigned long long best = 0ull;
+        int at = 0;
+#if defined(PPCR_SCAN_UNROLL)
+        constexpr int kUnroll = PPCR_SCAN_UNROLL;
+#pragma unroll kUnroll
+#endif
+        for (int i = 0; i < m; ++i) {
+            const unsigned long long v = k[i * STRIDE];
+            if (v > best) {
+                best = v;
+                at = i;
+            }
+        }
+        w = best;
+        wi = at;
+    }
+    // pre: x < worst()
+    PPCR_HD void insert(unsigned long long x)
+    {
+        if (n < m) {
+            k[n * STRIDE] = x;
+            if (++n == m) rescan();
+        } else {
+            k[wi * STRIDE] = x;
+            rescan();
+        }
+    }
+    PPCR_HD unsigned long long kth_key() const { return w; }
 };
 
 // ---- traversal -----------------------------------------------------------------------------------------------

@@ -193,7 +193,8 @@ void emu_normal_eq(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, 
 
 // The product's octree (csrc/ppcr_tree.h): serial build with the same split routine the build kernel calls, then the
 // same traversal the search kernel runs, one query at a time.  Rows come back sorted ascending by (d2, index).
-// list_kind: 0 = sorted register list, 1 = sorted addressable list, 2 = max-heap (what the search kernel uses).
+// list_kind: 0 = sorted register list, 1 = sorted addressable list, 2 = max-heap, 3 = unordered column + worst scan
+// (the search kernel uses 3 up to max_neighbours = 32 and 2 above).
 int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, int64_t n_tgt, double radius,
                         int max_nn, int leaf_cap, int list_kind, const float* bounds, int* out_idx, float* out_d2,
                         int* out_cnt, int* out_n_nodes)
@@ -256,7 +257,7 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
     if (out_n_nodes) *out_n_nodes = n_nodes;
     int64_t total = 0;
     int stack[2 * kTreeStack];
-    std::vector<unsigned long long> buf(static_cast<size_t>(std::max(m, 1)));
+    std::vector<unsigned long long> buf(static_cast<size_t>(heap_slots(std::max(m, 1))));
 #if defined(PPCR_TREE_STATS)
     g_query_cost.assign(static_cast<size_t>(n_src), 0.f);
 #endif
@@ -304,6 +305,12 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
 #undef EMU_RUN
         } else if (list_kind == 2) {  // the search kernel's list: a max-heap (one column per thread on the device)
             HeapList<1> L;
+            L.k = buf.data();
+            L.init(m);
+            tree_search(g, nodes.data(), pts.data(), q[0], q[1], q[2], r2f, bound0, L, stack);
+            for (int s2 = 0; s2 < L.n; ++s2) found.push_back(buf[s2]);
+        } else if (list_kind == 3) {  // the search kernel's list for small m: unordered column + worst scan
+            ScanList<1> L;
             L.k = buf.data();
             L.init(m);
             tree_search(g, nodes.data(), pts.data(), q[0], q[1], q[2], r2f, bound0, L, stack);

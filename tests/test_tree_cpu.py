@@ -38,6 +38,9 @@ def test_lidar_with_outliers_and_all_list_kinds(emu, oracle):
     _check(emu, oracle, src, tgt, 3.0, 20, list_kind=0)
     _check(emu, oracle, src, tgt, 0.5, 10, list_kind=1)
     _check(emu, oracle, src, tgt, 3.0, 50, list_kind=2)
+    _check(emu, oracle, src, tgt, 3.0, 20, list_kind=3)
+    _check(emu, oracle, src, tgt, 0.5, 10, list_kind=3)
+    _check(emu, oracle, src, tgt, 3.0, 1, list_kind=3)
 
 
 @pytest.mark.parametrize("m", [3, 5, 20])
@@ -47,6 +50,7 @@ def test_lattice_with_exact_ties(emu, oracle, m):
     pts = np.ones((400, 4), dtype=np.float32)
     pts[:, 0], pts[:, 1], pts[:, 2] = xx.ravel(), yy.ravel(), 0.0
     _check(emu, oracle, pts, pts, 0.75, m, leaf_cap=4)
+    _check(emu, oracle, pts, pts, 0.75, m, leaf_cap=4, list_kind=3)
     gi, gd, gc, _ = emu_tree_search(emu, pts, pts, 0.5, m)
     assert np.all(gc == 1) and np.array_equal(gi[:, 0], np.arange(400))
 

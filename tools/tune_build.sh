@@ -6,4 +6,4 @@ name=$1; shift
 cd "$(dirname "$0")/.."
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -shared \
   -ccbin /usr/bin/g++ -I include $@ -Xptxas=-v -o probabilistic_point_clouds_registration_b200/csrc/tune_${name}.so \
-  probabilistic_point_clouds_registration_b200/csrc/ppcr_capi.cu -lcudart 2>&1 | grep -A3 "k_evalctlILb1" | grep "Used\|spill"
+  probabilistic_point_clouds_registration_b200/csrc/ppcr_capi.cu -lcudart 2>&1 | grep -A3 "k_evalctlILb1\|k_searchILi[04]" | grep "Used\|spill"
