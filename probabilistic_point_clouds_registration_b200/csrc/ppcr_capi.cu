@@ -128,21 +128,32 @@ static int ceil_div(long long a, long long b) { return static_cast<int>((a + b -
 
 static int g_sm_count = 0;
 
-// The search kernel.  The list of the m best candidates is an unordered column with a worst scan up to
-// kScanListMaxM, a binary max-heap above (ppcr_tree.h).  PPCR_SEARCH_VARIANT overrides the choice (tuning only).
-constexpr int kScanListMaxM = 0;   // measured on the 1M-point pair: the heap wins inside the loop (0.61 vs 0.65 ms per search), the column only on a converged pair (0.37 vs 0.43)
+// The search kernel.  PPCR_SEARCH_VARIANT selects a tuning variant (ppcr_kernels.cuh, SearchList) and PPCR_SEARCH_CAP the
+// slots per query of the collect + select variant's column; unset = the product (max-heap column of m slots).
 using SearchKernel = void (*)(const PairDev*);
-static SearchKernel search_kernel(int m)
+static int search_variant()
 {
-    static const int variant = getenv("PPCR_SEARCH_VARIANT") ? atoi(getenv("PPCR_SEARCH_VARIANT")) : -1;
-    switch (variant) {
-        case 0: return k_search<0>;
+    static const int variant = getenv("PPCR_SEARCH_VARIANT") ? atoi(getenv("PPCR_SEARCH_VARIANT")) : 0;
+    return variant;
+}
+static bool search_collects() { return search_variant() == 16; }
+static SearchKernel search_kernel()
+{
+    switch (search_variant()) {
         case 1: return k_search<1>;
-        case 2: return k_search<2>;  // heap, without the exact warm bound from the previous neighbours
+        case 3: return k_search<3>;
         case 4: return k_search<4>;
-        case 6: return k_search<6>;
-        default: return m <= kScanListMaxM ? k_search<4> : k_search<0>;
+        case 16: return k_search<16>;
+        case 32: return k_search<32>;  // without the exact warm bound from the previous neighbours
+        default: return k_search<0>;
     }
+}
+// slots per query in the search kernel's shared-memory column
+static int search_cap(int max_nn)
+{
+    if (!search_collects()) return heap_slots(max_nn);
+    static const int forced = getenv("PPCR_SEARCH_CAP") ? atoi(getenv("PPCR_SEARCH_CAP")) : 0;
+    return std::max(forced > 0 ? forced : 24, max_nn + 4);
 }
 constexpr size_t kEvalSmem = static_cast<size_t>(kNSum) * kEvalThreads * sizeof(double);  // per-thread moment columns
 constexpr int kDefaultLeafCap = 32;
@@ -553,6 +564,7 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     D.n_pad = (D.n_src + kEvalFastThreads - 1) / kEvalFastThreads * kEvalFastThreads;
     if (D.n_pad == 0) D.n_pad = kEvalFastThreads;
     D.m = static_cast<int>(std::min<int64_t>(prm.max_neighbours, std::max<int64_t>(P.n_tgt, 1)));
+    D.search_cap = search_cap(prm.max_neighbours);
     D.r2f = static_cast<float>(prm.radius * prm.radius);
     D.src = P.src.p;
     if (D.n_src > 0) {
@@ -682,26 +694,28 @@ static void engine_commit(Engine& E)
     E.d_pairs.reserve(np);
     CK(cudaMemcpyAsync(E.d_pairs.p, host.data(), sizeof(PairDev) * np, cudaMemcpyHostToDevice, E.stream));
     CK(cudaStreamSynchronize(E.stream));
-    E.search_smem = static_cast<size_t>(heap_slots(E.params.max_neighbours)) * kSearchThreads * sizeof(unsigned long long);
+    E.search_smem = static_cast<size_t>(search_cap(E.params.max_neighbours)) * kSearchThreads * sizeof(unsigned long long);
     E.eval_smem = E.opts.exact_weights ? kEvalSmem : eval_fast_smem(max_m);
     {
         // the opt-in shared-memory sizes are per function and process wide: only ever raise them (handles of several host
         // threads, e.g. the lanes of ppcr_align_batch, launch the same kernels with different sizes)
         static std::mutex attr_mutex;
-        static size_t eval_fast_max[64] = {}, search_max[64] = {};
+        static size_t eval_fast_max[64] = {}, search_max_of[2][64] = {};
+        size_t* search_max = search_max_of[search_collects() ? 1 : 0];
         std::lock_guard<std::mutex> lock(attr_mutex);
         if (!E.opts.exact_weights && E.eval_smem > eval_fast_max[E.device]) {
             CK(cudaFuncSetAttribute(k_evalctl<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.eval_smem)));
             eval_fast_max[E.device] = E.eval_smem;
         }
-        if (E.search_smem > 48 * 1024 && E.search_smem > search_max[E.device]) {
-            CK(cudaFuncSetAttribute(search_kernel(E.params.max_neighbours), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.search_smem)));
+        // (the kernel also has a little static shared memory: opt in from just below the 48 KiB default limit)
+        if (E.search_smem > 47 * 1024 && E.search_smem > search_max[E.device]) {
+            CK(cudaFuncSetAttribute(search_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.search_smem)));
             search_max[E.device] = E.search_smem;
         }
     }
     {   // persistent grid: exactly as many blocks as the device keeps resident
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel(E.params.max_neighbours), kSearchThreads, E.search_smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel(), kSearchThreads, E.search_smem));
         E.search_blocks_per_sm = std::max(1, per_sm);
     }
     const int tiles = std::max(1, std::min(ceil_div(max_src, kSearchChunk), E.search_blocks_per_sm * std::max(g_sm_count, 1)));
@@ -749,7 +763,7 @@ static void launch_search(Engine& E)
 {
     const int np = static_cast<int>(E.pairs.size());
     dim3 grid(E.max_tiles, np);
-    search_kernel(E.params.max_neighbours)<<<grid, kSearchThreads, E.search_smem, E.stream>>>(E.d_pairs.p);
+    search_kernel()<<<grid, kSearchThreads, E.search_smem, E.stream>>>(E.d_pairs.p);
 }
 
 // weights + moments + (in its last block) reduction, controller and loop condition

@@ -69,6 +69,7 @@ struct PairDev {
     int n_src;
     int n_pad;
     int m;          // result capacity = min(max_neighbours, n_tgt)
+    int search_cap; // slots per query in the search kernel's shared-memory column (CollectList: > m)
     float r2f;      // float(radius * radius): strict membership bound (FLANN)
     int* nbr_pos;   // [m][n_pad] slot-major association: positions in tgt_sorted
     const int* inv_perm;  // [n_tgt] original index -> position in tgt_sorted
@@ -363,18 +364,28 @@ constexpr int kSearchChunk = kSearchThreads;  // queries handed out per grab of 
 // dynamic shared memory per thread): replacing the root and sifting down costs ~log2(m) steps, about half the
 // instructions of a sorted register list at m = 10..20, and works for any m.  Rows are stored in heap order; nothing
 // downstream depends on the order inside a row (the host sorts rows it hands out).
-// VAR bit 0: heap filled by appends; bit 1: no exact warm bound (tuning); bit 2: unordered column + worst scan
+// The list of the m best candidates.  VAR 0 (the product): max-heap that starts full of kKeyInf.  Tuning variants, all
+// measured slower on the 1M-point pair: 1 heap filled by appends, 3 heap filled bottom-up, 4 unordered
+// column + worst scan, 16 collect + select; 32 = the product without the exact warm bound.
 template <int VAR>
 struct SearchList {
-    using type = HeapList<kSearchThreads, (VAR & 1) != 0>;
+    using type = HeapList<kSearchThreads, 0>;
+};
+template <>
+struct SearchList<1> {
+    using type = HeapList<kSearchThreads, 1>;
+};
+template <>
+struct SearchList<3> {
+    using type = HeapList<kSearchThreads, 2>;
 };
 template <>
 struct SearchList<4> {
     using type = ScanList<kSearchThreads>;
 };
 template <>
-struct SearchList<6> {
-    using type = ScanList<kSearchThreads>;
+struct SearchList<16> {
+    using type = CollectList<kSearchThreads>;
 };
 
 #if defined(PPCR_SEARCH_MIN_BLOCKS)  // tuning builds only: ptxas' own choice (48 registers) measured fastest
@@ -395,6 +406,7 @@ __global__ void PPCR_SEARCH_BOUNDS k_search(const PairDev* __restrict__ pairs)
     if (threadIdx.x < 12) s_T[threadIdx.x] = st->dT[threadIdx.x];
     // the geometry and the pointers the walk uses, held in registers (P lives in global memory)
     const int m = P.m;
+    const int cap = P.search_cap;
     const int n_src = P.n_src;
     const float r2f = P.r2f;
     const TreeGeom geom = P.tree;
@@ -430,7 +442,7 @@ __global__ void PPCR_SEARCH_BOUNDS k_search(const PairDev* __restrict__ pairs)
             q.y = ny;
             q.z = nz;
             src[i] = q;
-            if ((VAR & 2) == 0 && prev < __int_as_float(0x7f800000)) {
+            if ((VAR & 32) == 0 && prev < __int_as_float(0x7f800000)) {
                 // A saturated row: its m neighbours of the last search are m distinct targets, so the largest of their
                 // distances to the MOVED query (same arithmetic as the walk, hence the same bits) bounds the new m-th
                 // distance -- usually far tighter than the triangle inequality above, and independent of how far the
@@ -459,11 +471,12 @@ __global__ void PPCR_SEARCH_BOUNDS k_search(const PairDev* __restrict__ pairs)
         float kth = __int_as_float(0x7f800000);
         typename SearchList<VAR>::type L;
         L.k = s_heap + threadIdx.x;
-        L.init(m);
+        L.init(m, cap);
         tree_search(geom, nodes, tgt_sorted, q.x, q.y, q.z, r2f, bound0, L, stack);
-        for (int s = 0; s < L.n; ++s) {
+        L.finish();
+        for (int s = L.begin(); s < L.end(); ++s) {
             const unsigned long long key = L.k[s * kSearchThreads];
-            if ((VAR & 5) || key != kKeyInf) search_store(out, i, cnt++, key);
+            if (key != kKeyInf) search_store(out, i, cnt++, key);
         }
         if (L.kth_key() != kKeyInf) kth = key_d2(L.kth_key());
         nbr_cnt[i] = cnt;

@@ -307,22 +307,28 @@ PPCR_HD void tree_mark_leaf_children(TreeNode* nodes, int ni)
 }
 
 // binary max-heap of the m best keys in addressable memory, element i at k[i * STRIDE] (the search kernel keeps one
-// column per thread in shared memory, STRIDE = block size).  The first m candidates are only appended -- nothing can
-// be rejected before m are known, so no order is needed -- and the heap is built once, when the m-th arrives
-// (Floyd, ~m/2 short sift-downs); from then on a better candidate replaces the root and sifts down.  Entries
-// [0, n) are valid and come out unordered.
+// column per thread in shared memory, STRIDE = block size).  Once m candidates are known a better one replaces the
+// root and sifts down.  How the first m get in is what FILL selects; measured on the 1M-point pair (profiles/):
+//   0  the column starts full of kKeyInf and every candidate replaces the root.  Most instructions, but ONE code
+//      path walked from the same slot by every thread: the threads of a warp that insert at the same time stay in
+//      step (13.2 of 32 lanes active over the kernel).  The fastest of the three.
+//   1  the first m are appended, the heap is built when the m-th arrives: three code paths the warp serialises on.
+//   2  bottom-up: the n-th candidate goes to slot m-1-n and sifts down inside the part already filled (Floyd's
+//      construction one element at a time).  13 % fewer thread instructions than 0 but every thread starts from
+//      another slot: 8.1 lanes active, 40 % MORE warp instructions, 0.62 ms against 0.43.
+// Valid entries are the slots [begin(), end()) that do not hold kKeyInf.
 PPCR_HD constexpr int heap_slots(int m) { return m < 1 ? 1 : m; }
 
-template <int STRIDE, bool APPEND = true>
+template <int STRIDE, int FILL = 0>
 struct HeapList {
     unsigned long long* k;
     int m;
     int n;
-    PPCR_HD void init(int m_)
+    PPCR_HD void init(int m_, int /*cap*/ = 0)
     {
         m = m_;
         n = 0;
-        if (!APPEND) {
+        if (FILL == 0) {
             n = m;
             for (int i = 0; i < m; ++i) k[i * STRIDE] = kKeyInf;
         }
@@ -352,7 +358,11 @@ struct HeapList {
     // pre: x < worst()
     PPCR_HD void insert(unsigned long long x)
     {
-        if (n < m) {
+        if (FILL == 2) {
+            int at = 0;
+            if (n < m) at = m - 1 - n++;
+            sift_down(at, x);
+        } else if (n < m) {
             k[n * STRIDE] = x;
             if (++n == m)
                 for (int i = m / 2 - 1; i >= 0; --i) sift_down(i, k[i * STRIDE]);
@@ -360,6 +370,9 @@ struct HeapList {
             sift_down(0, x);
         }
     }
+    PPCR_HD void finish() {}
+    PPCR_HD int begin() const { return FILL == 2 ? m - n : 0; }
+    PPCR_HD int end() const { return FILL == 2 ? m : n; }
     // key of the m-th best, kKeyInf when fewer than m real keys are held
     PPCR_HD unsigned long long kth_key() const { return n == m ? k[0] : kKeyInf; }
 };
@@ -378,7 +391,7 @@ struct ScanList {
     int m;
     int n;
     int wi;                // its position, valid when n == m
-    PPCR_HD void init(int m_)
+    PPCR_HD void init(int m_, int /*cap*/ = 0)
     {
         m = m_;
         n = 0;
@@ -415,7 +428,82 @@ struct ScanList {
             rescan();
         }
     }
+    PPCR_HD void finish() {}
+    PPCR_HD int begin() const { return 0; }
+    PPCR_HD int end() const { return n; }
     PPCR_HD unsigned long long kth_key() const { return w; }
+};
+
+// Collect first, select later (tuning variant 16): only APPENDS while the walk runs and picks the m best when the walk
+// is over -- Floyd's heap construction over the first m entries, then the rest streamed through the root -- relying on
+// the warm pruning bound being good from the start (15-20 targets lie within it at m = 10).  When the column fills up
+// (cap entries) the selection runs early, the m best stay in slots [0, m) as a heap, the bound drops to their worst and
+// collection goes on behind them.  12 % fewer thread instructions than the heap, and slower (0.63 ms against 0.42 on
+// the converged 1M-point pair, 4.5 ms against 0.97 for a search without a bound): the wider column costs resident
+// blocks, and without the heap updates the threads of a warp drift apart in the leaf scans (7-8 lanes active there
+// instead of 15).  cap > m.  After finish() the valid entries are [0, n), unordered.
+template <int STRIDE>
+struct CollectList {
+    unsigned long long* k;
+    int m;
+    int cap;
+    int n;
+    bool heaped;  // slots [0, m) hold the m best seen so far as a max-heap; [m, n) are pending
+    PPCR_HD void init(int m_, int cap_)
+    {
+        m = m_;
+        cap = cap_;
+        n = 0;
+        heaped = false;
+    }
+    PPCR_HD unsigned long long worst() const { return heaped ? k[0] : kKeyInf; }
+    PPCR_HD void sift_down(int i, unsigned long long x)
+    {
+        for (;;) {
+            const int l = 2 * i + 1;
+            if (l >= m) break;
+            unsigned long long vc = k[l * STRIDE];
+            int c = l;
+            if (l + 1 < m) {
+                const unsigned long long vr = k[(l + 1) * STRIDE];
+                if (vr > vc) {
+                    vc = vr;
+                    c = l + 1;
+                }
+            }
+            if (vc <= x) break;
+            k[i * STRIDE] = vc;
+            i = c;
+        }
+        k[i * STRIDE] = x;
+    }
+    // pre: n >= m.  Leaves the m best of the n entries in [0, m) as a heap.
+    PPCR_HD void select()
+    {
+        if (!heaped) {
+            for (int i = m / 2 - 1; i >= 0; --i) sift_down(i, k[i * STRIDE]);
+            heaped = true;
+        }
+        for (int j = m; j < n; ++j) {
+            const unsigned long long x = k[j * STRIDE];
+            if (x < k[0]) sift_down(0, x);
+        }
+        n = m;
+    }
+    // pre: x < worst()
+    PPCR_HD void insert(unsigned long long x)
+    {
+        k[n * STRIDE] = x;
+        if (++n == cap) select();
+    }
+    PPCR_HD void finish()
+    {
+        if (n > m || (n == m && !heaped)) select();
+    }
+    PPCR_HD int begin() const { return 0; }
+    PPCR_HD int end() const { return n; }
+    // after finish(): key of the m-th best, kKeyInf when fewer than m were found
+    PPCR_HD unsigned long long kth_key() const { return (n == m && heaped) ? k[0] : kKeyInf; }
 };
 
 // ---- traversal -----------------------------------------------------------------------------------------------

@@ -193,8 +193,9 @@ void emu_normal_eq(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, 
 
 // The product's octree (csrc/ppcr_tree.h): serial build with the same split routine the build kernel calls, then the
 // same traversal the search kernel runs, one query at a time.  Rows come back sorted ascending by (d2, index).
-// list_kind: 0 = sorted register list, 1 = sorted addressable list, 2 = max-heap, 3 = unordered column + worst scan
-// (the search kernel uses 3 up to max_neighbours = 32 and 2 above).
+// list_kind: 0 = sorted register list, 1 = sorted addressable list, 2 = max-heap that starts full of infinity (the search
+// kernel's list for large m), 3 = unordered column + worst scan, 4 / 5 = the heap's append / bottom-up fill modes,
+// 100 + e = collect + select with a column of m + e slots (the search kernel's default list).
 int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, int64_t n_tgt, double radius,
                         int max_nn, int leaf_cap, int list_kind, const float* bounds, int* out_idx, float* out_d2,
                         int* out_cnt, int* out_n_nodes)
@@ -308,7 +309,35 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
             L.k = buf.data();
             L.init(m);
             tree_search(g, nodes.data(), pts.data(), q[0], q[1], q[2], r2f, bound0, L, stack);
-            for (int s2 = 0; s2 < L.n; ++s2) found.push_back(buf[s2]);
+            for (int s2 = L.begin(); s2 < L.end(); ++s2)
+                if (buf[s2] != kKeyInf) found.push_back(buf[s2]);
+        } else if (list_kind >= 100) {  // collect + select, the search kernel's list; column of m + (list_kind - 100) slots
+            const int cap = m + (list_kind - 100);
+            std::vector<unsigned long long> col(static_cast<size_t>(cap));
+            CollectList<1> L;
+            L.k = col.data();
+            L.init(m, cap);
+            tree_search(g, nodes.data(), pts.data(), q[0], q[1], q[2], r2f, bound0, L, stack);
+            L.finish();
+            for (int s2 = L.begin(); s2 < L.end(); ++s2) found.push_back(col[s2]);
+            if (L.kth_key() != kKeyInf && (static_cast<int>(found.size()) != m ||
+                                           L.kth_key() != *std::max_element(found.begin(), found.end())))
+                return -1;  // the warm-start distance the kernel stores must be the m-th best
+        } else if (list_kind == 4 || list_kind == 5) {  // the heap's other fill modes (tuning variants)
+            auto run = [&](auto& L) {
+                L.k = buf.data();
+                L.init(m);
+                tree_search(g, nodes.data(), pts.data(), q[0], q[1], q[2], r2f, bound0, L, stack);
+                for (int s2 = L.begin(); s2 < L.end(); ++s2)
+                    if (buf[s2] != kKeyInf) found.push_back(buf[s2]);
+            };
+            if (list_kind == 4) {
+                HeapList<1, 1> L;
+                run(L);
+            } else {
+                HeapList<1, 2> L;
+                run(L);
+            }
         } else if (list_kind == 3) {  // the search kernel's list for small m: unordered column + worst scan
             ScanList<1> L;
             L.k = buf.data();

@@ -24,7 +24,7 @@ def _compare(capi, oracle, src, tgt, radius, m, leaf_capacity=0):
 
 
 @pytest.mark.parametrize("radius,m", [(1.0, 20), (3.0, 20), (0.3, 10), (0.05, 5), (1.0, 1), (1.0, 32), (1.0, 33),
-                                      (1.0, 64), (2.0, 100)])
+                                      (1.0, 48), (1.0, 64), (2.0, 100)])
 def test_plane_sphere(capi, oracle, radius, m):
     src, tgt, _ = synth.config1_plane_sphere(seed=1, n_plane=3000, n_sphere=3000)
     cnt = _compare(capi, oracle, src, tgt, radius, m)
