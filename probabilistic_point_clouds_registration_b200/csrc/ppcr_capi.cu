@@ -155,6 +155,7 @@ static int search_cap(int max_nn)
     static const int forced = getenv("PPCR_SEARCH_CAP") ? atoi(getenv("PPCR_SEARCH_CAP")) : 0;
     return std::max(forced > 0 ? forced : 24, max_nn + 4);
 }
+constexpr int kSearchQueuedMaxM = 32;  // k_search_q's shared-memory heap columns: m KiB per block on top of 35 KiB of queues
 constexpr size_t kEvalSmem = static_cast<size_t>(kNSum) * kEvalThreads * sizeof(double);  // per-thread moment columns
 constexpr int kDefaultLeafCap = 32;
 
@@ -220,6 +221,9 @@ struct Engine {
     // launch geometry (capacity based, so a captured graph stays valid while the slots are refilled)
     int max_tiles = 1, max_eval_blocks = 1, max_tr_blocks = 1;
     bool skip_search = false;
+    bool search_queued = false;  // searches after a cloud move go through k_search_q
+    size_t search_q_smem_bytes = 0;
+    int q_tiles = 1;
     int max_ticks = 0;
     // graph driver
     cudaGraph_t graph = nullptr;
@@ -685,7 +689,17 @@ static void engine_commit(Engine& E)
     int max_m = 1;
     long long max_src = 1;
     int max_eval = 1;
+    // The queued search (k_search_q) is opt-in, PPCR_SEARCH_QUEUED=1: on the 1M-point pair it needs a third fewer warp
+    // instructions than k_search (218 M against 331 M, 21 lanes active instead of 13) but its shared-memory queues cost L1
+    // capacity and resident warps, and it ends level: 0.43 ms on a converged pair, 0.69 against 0.61 ms inside the loop.
+    // Read at every commit (not cached) so that a test can switch it inside one process.
+    const bool queued_wanted = getenv("PPCR_SEARCH_QUEUED") && atoi(getenv("PPCR_SEARCH_QUEUED")) != 0;
+    bool queued = queued_wanted && search_variant() == 0 && E.params.max_neighbours <= kSearchQueuedMaxM;
+    for (int p = 0; p < np; ++p)
+        queued = queued && E.pairs[p].dev.tree.n_nodes_cap < (1 << kQNodeBits) && E.pairs[p].dev.n_tgt < (1 << kQNodeBits);
+    E.search_queued = queued;
     for (int p = 0; p < np; ++p) {
+        E.pairs[p].dev.search_queued = queued ? 1 : 0;
         host[p] = E.pairs[p].dev;
         max_m = std::max(max_m, host[p].m);
         max_src = std::max<long long>(max_src, host[p].n_src);
@@ -695,6 +709,7 @@ static void engine_commit(Engine& E)
     CK(cudaMemcpyAsync(E.d_pairs.p, host.data(), sizeof(PairDev) * np, cudaMemcpyHostToDevice, E.stream));
     CK(cudaStreamSynchronize(E.stream));
     E.search_smem = static_cast<size_t>(search_cap(E.params.max_neighbours)) * kSearchThreads * sizeof(unsigned long long);
+    if (const char* pad = getenv("PPCR_SEARCH_PAD_SMEM")) E.search_smem += static_cast<size_t>(atoi(pad));  // occupancy experiments
     E.eval_smem = E.opts.exact_weights ? kEvalSmem : eval_fast_smem(max_m);
     {
         // the opt-in shared-memory sizes are per function and process wide: only ever raise them (handles of several host
@@ -717,11 +732,34 @@ static void engine_commit(Engine& E)
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel(), kSearchThreads, E.search_smem));
         E.search_blocks_per_sm = std::max(1, per_sm);
+        // tuning: PPCR_SEARCH_BLOCKS caps the resident blocks per SM, PPCR_SEARCH_CARVEOUT (percent) sets the shared-memory
+        // carve-out preference (what is not carved out is L1, which the tree walk lives on)
+        if (const char* b = getenv("PPCR_SEARCH_BLOCKS")) E.search_blocks_per_sm = std::max(1, std::min(per_sm, atoi(b)));
+        if (const char* c = getenv("PPCR_SEARCH_CARVEOUT"))
+            CK(cudaFuncSetAttribute(search_kernel(), cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c)));
+    }
+    int q_tiles = 1;
+    if (E.search_queued) {
+        E.search_q_smem_bytes = search_q_smem(E.params.max_neighbours);
+        static std::mutex q_mutex;
+        static size_t q_max[64] = {};
+        {
+            std::lock_guard<std::mutex> lock(q_mutex);
+            if (E.search_q_smem_bytes > q_max[E.device]) {
+                CK(cudaFuncSetAttribute(k_search_q, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(E.search_q_smem_bytes)));
+                q_max[E.device] = E.search_q_smem_bytes;
+            }
+        }
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_search_q, kSearchThreads, E.search_q_smem_bytes));
+        if (const char* b = getenv("PPCR_SEARCH_Q_BLOCKS")) per_sm = std::min(per_sm, atoi(b));
+        q_tiles = std::max(1, std::min(ceil_div(max_src, kSearchChunk), std::max(1, per_sm) * std::max(g_sm_count, 1)));
     }
     const int tiles = std::max(1, std::min(ceil_div(max_src, kSearchChunk), E.search_blocks_per_sm * std::max(g_sm_count, 1)));
     const int trb = std::max(1, std::min(ceil_div(max_src, 256), 8 * std::max(g_sm_count, 1)));
-    if (tiles > E.max_tiles || max_eval > E.max_eval_blocks || trb > E.max_tr_blocks) {
+    if (tiles > E.max_tiles || max_eval > E.max_eval_blocks || trb > E.max_tr_blocks || q_tiles > E.q_tiles) {
         E.max_tiles = std::max(E.max_tiles, tiles);
+        E.q_tiles = std::max(E.q_tiles, q_tiles);
         E.max_eval_blocks = std::max(E.max_eval_blocks, max_eval);
         E.max_tr_blocks = std::max(E.max_tr_blocks, trb);
         if (E.graph_exec) {  // geometry changed: the captured graph is stale
@@ -764,7 +802,11 @@ static void launch_search(Engine& E)
     const int np = static_cast<int>(E.pairs.size());
     dim3 grid(E.max_tiles, np);
     search_kernel()<<<grid, kSearchThreads, E.search_smem, E.stream>>>(E.d_pairs.p);
+    // the first search of an align() is k_search's, every later one (fused with the cloud move, tight bounds known)
+    // k_search_q's; each returns at once when the search is the other's
+    if (E.search_queued) k_search_q<<<dim3(E.q_tiles, np), kSearchThreads, E.search_q_smem_bytes, E.stream>>>(E.d_pairs.p);
 }
+static int search_launches(const Engine& E) { return E.search_queued ? 2 : 1; }
 
 // weights + moments + (in its last block) reduction, controller and loop condition
 static void launch_evalctl(Engine& E, bool use_cond, int probe = 0)
@@ -778,7 +820,7 @@ static void launch_evalctl(Engine& E, bool use_cond, int probe = 0)
         k_evalctl<false><<<grid, kEvalThreads, E.eval_smem, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, E.cond_search, flags, E.max_ticks);
 }
 
-static int launches_per_tick(const Engine& E) { return E.skip_search ? 1 : 2; }
+static int launches_per_tick(const Engine& E) { return E.skip_search ? 1 : 1 + search_launches(E); }
 
 static void launch_tick(Engine& E, bool use_cond, bool rec)
 {
@@ -1298,7 +1340,7 @@ ppcr_status ppcr_get_stage_times(ppcr_handle* h, ppcr_stage_times* out)
         if (E.graph_ready) {  // the WHILE graph loops on the device: k_evalctl every tick, k_search once per outer iteration
             const PairState s = download_state(E, 0);
             out->ticks = s.ticks;
-            out->total_launches = E.times.total_launches + s.ticks + (E.skip_search ? 0 : s.current_iteration);
+            out->total_launches = E.times.total_launches + s.ticks + (E.skip_search ? 0 : search_launches(E) * s.current_iteration);
         }
     });
 }

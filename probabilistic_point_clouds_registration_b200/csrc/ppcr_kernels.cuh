@@ -70,6 +70,7 @@ struct PairDev {
     int n_pad;
     int m;          // result capacity = min(max_neighbours, n_tgt)
     int search_cap; // slots per query in the search kernel's shared-memory column (CollectList: > m)
+    int search_queued;  // 1: searches that follow a cloud move are k_search_q's, k_search only does the first of an align()
     float r2f;      // float(radius * radius): strict membership bound (FLANN)
     int* nbr_pos;   // [m][n_pad] slot-major association: positions in tgt_sorted
     const int* inv_perm;  // [n_tgt] original index -> position in tgt_sorted
@@ -403,6 +404,7 @@ __global__ void PPCR_SEARCH_BOUNDS k_search(const PairDev* __restrict__ pairs)
     __shared__ double s_T[12];
     __shared__ int s_chunk;
     const bool moving = st->apply_dT != 0;
+    if (moving && P.search_queued) return;  // k_search_q, launched right behind this kernel, does this one
     if (threadIdx.x < 12) s_T[threadIdx.x] = st->dT[threadIdx.x];
     // the geometry and the pointers the walk uses, held in registers (P lives in global memory)
     const int m = P.m;
@@ -484,6 +486,242 @@ __global__ void PPCR_SEARCH_BOUNDS k_search(const PairDev* __restrict__ pairs)
         cnt_total += cnt;
     }
     // association size: warp sum, one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) cnt_total += __shfl_xor_sync(kFull, cnt_total, o);
+    if ((threadIdx.x & 31) == 0 && cnt_total)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&st->K), static_cast<unsigned long long>(cnt_total));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// radius search, queued form: every search of an align() but the first
+// ------------------------------------------------------------------------------------------------------------
+//
+// k_search is bound by instruction issue on a divergent walk: a thread opens nodes, tests points and updates its heap in
+// turns, and at any moment the 32 threads of a warp want different turns (13 of 32 lanes active on average, 7 in the heap
+// updates).  Every search but the first of an align() knows a tight pruning bound per query BEFORE it starts -- the
+// distance of the farthest of last iteration's neighbours to the moved query -- so the walk does not need the heap to prune.
+// That allows the three kinds of work to be separated and each to be done by all threads of the block at the same time,
+// for whichever query it belongs to, through queues in shared memory:
+//   A  (thread per query)   move the query, bound from the previous neighbours, walk the octree with that fixed bound and
+//                           push every leaf within it as a task (query slot, node) on the block's task queue
+//   B  (thread per task)    test the leaf's points against its query; survivors' positions go to the query's candidate list
+//   C  (thread per query)   the m best of the candidates: build a heap of the first m, stream the rest through its root
+// A query whose tasks or candidates overflow the queues (no useful bound: a row that had fewer than m neighbours in a dense
+// region) is searched by tree_search with the heap, as in k_search.  Results are bit-identical to k_search's: same distance
+// arithmetic, same strict radius test, same (distance, index) order.
+constexpr int kQTaskPerQuery = 16;               // leaves one query may queue; beyond that it is searched by tree_search
+constexpr int kQTaskCap = kSearchThreads * kQTaskPerQuery;  // leaf tasks per block of 128 queries: the queue cannot overflow
+constexpr int kQCand = 48;                       // candidates per query
+constexpr int kQNodeBits = 25;                   // task = query slot << 25 | node index (phase A), | first position (from phase B on)
+constexpr uint32_t kQLowMask = (1u << kQNodeBits) - 1u;
+// a candidate is named by 16 bits: task index << 5 | offset in the task's leaf (leaves hold at most 32 points, except
+// finest-level cells full of near-duplicates: a query that meets one falls back)
+PPCR_HD constexpr size_t search_q_smem(int m)
+{
+    return static_cast<size_t>(kSearchThreads) * (16u + 4u) + 4u * kQTaskCap + 2u * kSearchThreads * kQCand +
+           8u * static_cast<size_t>(kSearchThreads) * static_cast<size_t>(m);
+}
+
+struct QEmit {  // phase A -> task queue
+    uint32_t* tasks;
+    int* n_tasks;
+    uint32_t slot;
+    int mine;
+    __device__ __forceinline__ bool operator()(int node)
+    {
+        if (++mine > kQTaskPerQuery) return false;
+        tasks[atomicAdd(n_tasks, 1)] = (slot << kQNodeBits) | static_cast<uint32_t>(node);
+        return true;
+    }
+};
+struct QPush {  // phase B -> candidate list of one query (slot-major: entry c of query ql at [c * 128 + ql])
+    unsigned short* cand;
+    int* cnt;
+    uint32_t task;   // index of the task in the queue
+    int begin;       // first position of its leaf
+    __device__ __forceinline__ void operator()(int j0, uint32_t pass)
+    {
+        if (j0 != begin) {  // the second 32 points of an oversized leaf: not nameable, the query falls back
+            atomicAdd(cnt, 2 * kQCand);
+            return;
+        }
+        int c = atomicAdd(cnt, __popc(pass));  // room for every survivor of the leaf at once
+        while (pass && c < kQCand) {
+            cand[c++ * kSearchThreads] = static_cast<unsigned short>((task << 5) | static_cast<uint32_t>(lowest_bit(pass)));
+            pass &= pass - 1;
+        }
+    }
+};
+struct QCand {  // phase C: candidate c of one query -> position in the sorted target
+    const unsigned short* cand;
+    const uint32_t* tasks;
+    __device__ __forceinline__ int operator()(int c) const
+    {
+        const uint32_t v = cand[c * kSearchThreads];
+        return static_cast<int>((tasks[v >> 5] & kQLowMask) + (v & 31u));
+    }
+};
+
+__global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __restrict__ pairs)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const PairDev& P = pairs[blockIdx.y];
+    PairState* st = P.state;
+    if (st->phase != PH_SEARCH || st->apply_dT == 0 || !P.search_queued) return;
+    float4* s_q = reinterpret_cast<float4*>(s_raw);                       // query, .w = its pruning bound
+    int* s_cnt = reinterpret_cast<int*>(s_q + kSearchThreads);            // candidates pushed per query
+    uint32_t* s_tasks = reinterpret_cast<uint32_t*>(s_cnt + kSearchThreads);
+    unsigned short* s_cand = reinterpret_cast<unsigned short*>(s_tasks + kQTaskCap);
+    unsigned long long* s_heap = reinterpret_cast<unsigned long long*>(s_cand + kSearchThreads * kQCand);
+    __shared__ double s_T[12];
+    __shared__ int s_chunk, s_ntasks;
+    if (threadIdx.x < 12) s_T[threadIdx.x] = st->dT[threadIdx.x];
+    const int m = P.m;
+    const int n_src = P.n_src;
+    const float r2f = P.r2f;
+    const TreeGeom geom = P.tree;
+    const TreeNode* __restrict__ nodes = P.nodes;
+    const float4* __restrict__ tgt_sorted = P.tgt_sorted;
+    const SearchOut out{P.nbr_pos, P.nbr_d2, P.inv_perm, static_cast<size_t>(P.n_pad)};
+    float4* __restrict__ src = P.src;
+    float* __restrict__ nbr_kth = P.nbr_kth;
+    int* __restrict__ nbr_cnt = P.nbr_cnt;
+    const int n_chunks = (n_src + kSearchChunk - 1) / kSearchChunk;
+    const float kInf = __int_as_float(0x7f800000);
+    int stack[2 * kTreeStack];
+    int cnt_total = 0;
+#if defined(PPCR_Q_PROFILE)
+    long long t_phase[4] = {0, 0, 0, 0}, t_mark = clock64();
+    long long n_task_sum = 0, n_fall = 0, n_fall_task = 0;
+#define PPCR_Q_MARK(ph) { const long long now = clock64(); t_phase[ph] += now - t_mark; t_mark = now; }
+#else
+#define PPCR_Q_MARK(ph)
+#endif
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_chunk = atomicAdd(&st->search_cursor, 1);
+            s_ntasks = 0;
+        }
+        s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        PPCR_Q_MARK(3)
+        const int chunk = s_chunk;
+        if (chunk >= n_chunks) break;
+        const int i = chunk * kSearchChunk + threadIdx.x;
+        const bool valid = i < n_src;
+        // ---- A: the query, its bound, its leaves ----
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        float bound0 = r2f;
+        bool fallback = false;
+        if (valid) {
+            q = src[i];
+            const double x = q.x, y = q.y, z = q.z;
+            const float nx = transform_row(s_T, x, y, z), ny = transform_row(s_T + 4, x, y, z),
+                        nz = transform_row(s_T + 8, x, y, z);
+            const float prev = nbr_kth[i];
+            q.x = nx;
+            q.y = ny;
+            q.z = nz;
+            src[i] = q;
+            if (prev < kInf) {  // a saturated row: the farthest of its previous neighbours bounds the new m-th distance
+                const int* __restrict__ pp = out.nbr_pos + i;
+                float far2 = 0.f;
+                int k = 0;
+                for (; k + 5 <= m; k += 5) {
+                    int pos[5];
+#pragma unroll
+                    for (int u = 0; u < 5; ++u) pos[u] = pp[static_cast<size_t>(k + u) * out.n_pad];
+                    float4 t[5];
+#pragma unroll
+                    for (int u = 0; u < 5; ++u) t[u] = load_point(tgt_sorted + pos[u]);
+#pragma unroll
+                    for (int u = 0; u < 5; ++u) far2 = fmaxf(far2, dist2_exact(nx, ny, nz, t[u].x, t[u].y, t[u].z));
+                }
+                for (; k < m; ++k) {
+                    const float4 t = load_point(tgt_sorted + pp[static_cast<size_t>(k) * out.n_pad]);
+                    far2 = fmaxf(far2, dist2_exact(nx, ny, nz, t.x, t.y, t.z));
+                }
+                bound0 = fminf(r2f, far2);
+            }
+            s_q[threadIdx.x] = make_float4(q.x, q.y, q.z, bound0);
+            QEmit emit{s_tasks, &s_ntasks, threadIdx.x, 0};
+            fallback = !tree_collect_leaves(geom, nodes, q.x, q.y, q.z, bound0, emit, stack);
+        }
+        __syncthreads();
+        PPCR_Q_MARK(0)
+        // ---- B: every queued leaf against its query ----
+        const int n_tasks = s_ntasks;
+        for (int t = threadIdx.x; t < n_tasks; t += kSearchThreads) {
+            const uint32_t task = s_tasks[t];
+            const uint32_t ql = task >> kQNodeBits;
+            const float4 qq = s_q[ql];
+            const int node = static_cast<int>(task & kQLowMask);
+            const int begin = __ldg(&nodes[node].begin);
+            s_tasks[t] = (task & ~kQLowMask) | static_cast<uint32_t>(begin);  // phase C turns candidates back into positions with it
+            QPush push{s_cand + ql, s_cnt + ql, static_cast<uint32_t>(t), begin};
+            leaf_candidates(nodes, tgt_sorted, node, qq.x, qq.y, qq.z, qq.w, r2f, push);
+        }
+        __syncthreads();
+        PPCR_Q_MARK(1)
+#if defined(PPCR_Q_PROFILE)
+        n_task_sum += n_tasks;
+        {
+            const int n_cold = __syncthreads_count(valid && bound0 >= r2f);
+            const int n_big = __syncthreads_count(valid && bound0 > 0.04f);
+            if (false && threadIdx.x == 0 && (chunk % 7) == 0)
+                printf("[k_search_q overflow] chunk %d tasks %d, queries with bound = r2: %d, with bound > (0.2 m)^2: %d, q0 = (%.2f %.2f %.2f) bound0 %.4f\n",
+                       chunk, s_ntasks, n_cold, n_big, q.x, q.y, q.z, bound0);
+        }
+#endif
+        // ---- C: the m best of each query's candidates ----
+        if (valid) {
+            const int n_c = s_cnt[threadIdx.x];
+#if defined(PPCR_Q_PROFILE)
+            n_fall_task += fallback ? 1 : 0;
+#endif
+            if (n_c > kQCand) fallback = true;
+            int cnt = 0;
+            float kth = kInf;
+            if (!fallback) {
+                unsigned long long kk;
+                const QCand at{s_cand + threadIdx.x, s_tasks};
+                const int n = select_candidates<kSearchThreads>(tgt_sorted, at, n_c, m, q.x, q.y, q.z, s_heap + threadIdx.x, &kk);
+                for (int s = 0; s < n; ++s) search_store(out, i, cnt++, s_heap[threadIdx.x + s * kSearchThreads]);
+                if (kk != kKeyInf) kth = key_d2(kk);
+            } else {
+                HeapList<kSearchThreads, 0> L;
+                L.k = s_heap + threadIdx.x;
+                L.init(m);
+                tree_search(geom, nodes, tgt_sorted, q.x, q.y, q.z, r2f, bound0, L, stack);
+                for (int s = 0; s < m; ++s) {
+                    const unsigned long long key = L.k[s * kSearchThreads];
+                    if (key != kKeyInf) search_store(out, i, cnt++, key);
+                }
+                if (L.kth_key() != kKeyInf) kth = key_d2(L.kth_key());
+            }
+            nbr_cnt[i] = cnt;
+            nbr_kth[i] = kth;
+            cnt_total += cnt;
+#if defined(PPCR_Q_PROFILE)
+            n_fall += fallback ? 1 : 0;
+#endif
+        }
+#if defined(PPCR_Q_PROFILE)
+        __syncthreads();
+        PPCR_Q_MARK(2)
+#endif
+    }
+#if defined(PPCR_Q_PROFILE)
+    __shared__ int s_prof[2];
+    if (threadIdx.x == 0) s_prof[0] = s_prof[1] = 0;
+    __syncthreads();
+    atomicAdd(&s_prof[0], static_cast<int>(n_fall));
+    atomicAdd(&s_prof[1], static_cast<int>(n_fall_task));
+    __syncthreads();
+    if (threadIdx.x == 0 && (blockIdx.x % 97) == 0)
+        printf("[k_search_q block %d] cycles A %lld B %lld C %lld idle %lld; tasks %lld; fallbacks %d (task-queue overflow %d)\n", blockIdx.x,
+               t_phase[0], t_phase[1], t_phase[2], t_phase[3], n_task_sum, s_prof[0], s_prof[1]);
+#endif
     for (int o = 16; o > 0; o >>= 1) cnt_total += __shfl_xor_sync(kFull, cnt_total, o);
     if ((threadIdx.x & 31) == 0 && cnt_total)
         atomicAdd(reinterpret_cast<unsigned long long*>(&st->K), static_cast<unsigned long long>(cnt_total));

@@ -674,5 +674,146 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
     }
 }
 
+// ---- traversal with a fixed bound: which leaves can hold a target within bound_d2 of q ------------------------------
+//
+// First phase of the queued search kernel (k_search_q): the pruning bound is known up front (the search kernel's warm
+// bound) and does not change during the walk, so the walk only has to NAME the leaves -- emit(node index) -- whose boxes
+// come within the bound; testing their points is somebody else's work.  Same start-node descent, same box lower bounds
+// and the same pruning threshold as tree_search: a leaf tree_search would scan under this bound is always emitted.
+// `stack` must hold kTreeStack ints.  Returns false when emit refused a leaf (queue full): the caller falls back.
+template <class Emit>
+PPCR_HD bool tree_collect_leaves(const TreeGeom& g, const TreeNode* __restrict__ nodes, float qx, float qy, float qz,
+                                 float bound_d2, Emit& emit, int* stack)
+{
+    const float thr = prune_threshold(bound_d2);
+    int sp = 0;
+    {
+        TreeNode n = load_node(nodes);
+        if (n.end <= n.begin) return true;
+        int at = 0;
+        const float rho = sqrtf(bound_d2) * 1.00001f + 2.0f * g.slack;
+        const float lox = qx - rho, hix = qx + rho, loy = qy - rho, hiy = qy + rho, loz = qz - rho, hiz = qz + rho;
+        bool leaf = n.child < 0;
+        while (!leaf) {
+            int oct;
+            if (lox >= n.cx) oct = 1;
+            else if (hix < n.cx) oct = 0;
+            else break;
+            if (loy >= n.cy) oct |= 2;
+            else if (!(hiy < n.cy)) break;
+            if (loz >= n.cz) oct |= 4;
+            else if (!(hiz < n.cz)) break;
+            if (!((n.mask >> oct) & 1)) return true;  // the only octant the ball touches is empty
+            at = n.child + oct;
+            leaf = ((n.mask >> (16 + oct)) & 1) != 0;
+            if (!leaf) n = load_node(nodes + at);
+        }
+        if (leaf) return emit(at);
+        stack[sp++] = at;
+    }
+    bool ok = true;
+    while (sp > 0) {
+        const TreeNode n = load_node(nodes + stack[--sp]);
+        PPCR_STAT(opens, 1);
+        const float ch = n.half * 0.5f;
+        const float hi = ch + g.slack;
+        const float gx[2] = {axis_gap2(qx, n.cx - ch, hi), axis_gap2(qx, n.cx + ch, hi)};
+        const float gy[2] = {axis_gap2(qy, n.cy - ch, hi), axis_gap2(qy, n.cy + ch, hi)};
+        const float gz[2] = {axis_gap2(qz, n.cz - ch, hi), axis_gap2(qz, n.cz + ch, hi)};
+        const int mask = n.mask;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float lb = gx[c & 1] + gy[(c >> 1) & 1] + gz[(c >> 2) & 1];
+            if (((mask >> c) & 1) && !(lb > thr)) {
+                if ((mask >> (16 + c)) & 1) ok = emit(n.child + c) && ok;
+                else stack[sp++] = n.child + c;
+            }
+        }
+    }
+    return ok;
+}
+
+// Second phase: the points of one emitted leaf against one query.  Every point of the leaf that passes the same two tests
+// a candidate passes in tree_search -- d2 <= bound_d2 and d2 < r2f (strict) -- is reported, 32 points at a time:
+// push(first position, survivor bit mask).  Two passes like tree_search's leaf scan: the point loop only sets bits, so
+// the caller reserves room for all survivors of the group with ONE atomic instead of one per survivor.
+template <class Push>
+PPCR_HD void leaf_candidates(const TreeNode* __restrict__ nodes, const float4* __restrict__ pts, int node, float qx, float qy,
+                             float qz, float bound_d2, float r2f, Push& push)
+{
+    const TreeNode n = load_node(nodes + node);
+    PPCR_STAT(leaves, 1);
+    PPCR_STAT(points, n.end - n.begin);
+    const int last = n.end - 1;
+    for (int j0 = n.begin; j0 < n.end; j0 += 32) {
+        const int stop = n.end - j0 < 32 ? n.end - j0 : 32;
+        uint32_t pass = 0;
+        // four independent loads in flight per thread (the index is clamped, the surplus results are discarded)
+        for (int t = 0; t < stop; t += 4) {
+            float4 p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] = load_point(pts + (j0 + t + u < last ? j0 + t + u : last));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float d2 = dist2_exact(qx, qy, qz, p[u].x, p[u].y, p[u].z);
+                if (t + u < stop && d2 <= bound_d2 && d2 < r2f) pass |= 1u << (t + u);
+            }
+        }
+        if (pass) push(j0, pass);
+    }
+}
+
+// Third phase: the m best of a query's n candidates (every one within the radius and distinct; cand(c) = position of
+// candidate c in the sorted target), as keys in the heap column k[i * STRIDE].  Fewer than m: all of them.  Otherwise
+// the first m are stored, made a max-heap (Floyd) and the rest streamed through its root.  The candidates arrive in no
+// particular order (they were pushed by many threads), and the order of a row decides the last bits of its float32
+// weight sums: the results are therefore SORTED ascending by (distance, index) -- FLANN's own order -- by an in-place
+// heap sort, which makes the association a pure function of the two clouds.  Returns the number of results, left in
+// slots [0, count); *kth = the key of the m-th best when m were found, kKeyInf otherwise.
+template <int STRIDE, class Cand>
+PPCR_HD int select_candidates(const float4* __restrict__ pts, const Cand& cand, int n, int m, float qx, float qy, float qz,
+                              unsigned long long* k, unsigned long long* kth)
+{
+    HeapList<STRIDE, 1> H;
+    H.k = k;
+    H.m = n < m ? n : m;  // heap size: all n candidates when fewer than m
+    H.n = 0;
+    const int n0 = H.m;
+    // candidates are fetched four at a time (clamped index, surplus discarded) so that their latencies overlap
+    for (int c = 0; c < n0; c += 4) {
+        float4 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) p[u] = load_point(pts + cand(c + u < n0 ? c + u : n0 - 1));
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (c + u < n0)
+                k[(c + u) * STRIDE] = make_key(dist2_exact(qx, qy, qz, p[u].x, p[u].y, p[u].z), static_cast<int>(float_bits(p[u].w)));
+    }
+    for (int i = n0 / 2 - 1; i >= 0; --i) H.sift_down(i, k[i * STRIDE]);
+    for (int c = m; c < n; c += 4) {
+        float4 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) p[u] = load_point(pts + cand(c + u < n ? c + u : n - 1));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned long long x =
+                make_key(dist2_exact(qx, qy, qz, p[u].x, p[u].y, p[u].z), static_cast<int>(float_bits(p[u].w)));
+            if (c + u < n && x < k[0]) {
+                H.sift_down(0, x);
+                PPCR_STAT(inserts, 1);
+            }
+        }
+    }
+    *kth = (n >= m && n0 > 0) ? k[0] : kKeyInf;
+    // heap sort: the root (largest) goes to the end of the shrinking heap
+    for (int e = n0 - 1; e > 0; --e) {
+        const unsigned long long top = k[0], x = k[e * STRIDE];
+        H.m = e;
+        H.sift_down(0, x);
+        k[e * STRIDE] = top;
+    }
+    return n0;
+}
+
 }  // namespace ppcr
 #endif

@@ -195,7 +195,8 @@ void emu_normal_eq(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, 
 // same traversal the search kernel runs, one query at a time.  Rows come back sorted ascending by (d2, index).
 // list_kind: 0 = sorted register list, 1 = sorted addressable list, 2 = max-heap that starts full of infinity (the search
 // kernel's list for large m), 3 = unordered column + worst scan, 4 / 5 = the heap's append / bottom-up fill modes,
-// 100 + e = collect + select with a column of m + e slots (the search kernel's default list).
+// 100 + e = collect + select with a column of m + e slots, 200 + c = the three phases of the queued search kernel
+// (k_search_q) with room for c candidates per query.
 int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, int64_t n_tgt, double radius,
                         int max_nn, int leaf_cap, int list_kind, const float* bounds, int* out_idx, float* out_d2,
                         int* out_cnt, int* out_n_nodes)
@@ -311,6 +312,36 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
             tree_search(g, nodes.data(), pts.data(), q[0], q[1], q[2], r2f, bound0, L, stack);
             for (int s2 = L.begin(); s2 < L.end(); ++s2)
                 if (buf[s2] != kKeyInf) found.push_back(buf[s2]);
+        } else if (list_kind >= 200) {
+            // the queued search kernel's three phases, one query at a time: leaves within the (fixed) bound -> candidate
+            // positions -> the m best.  list_kind - 200 = candidate capacity; a query that overflows it (or has no finite
+            // bound... the kernel falls back to tree_search for those) is searched with the heap, like the kernel does.
+            const int qcap = list_kind - 200;
+            std::vector<int> leaves;
+            std::vector<uint32_t> cand;
+            const float b0 = bound0 < r2f ? bound0 : r2f;
+            auto emit = [&](int node) { leaves.push_back(node); return true; };
+            tree_collect_leaves(g, nodes.data(), q[0], q[1], q[2], b0, emit, stack);
+            auto push = [&](int j0, uint32_t pass) {
+                for (; pass; pass &= pass - 1) cand.push_back(static_cast<uint32_t>(j0 + lowest_bit(pass)));
+            };
+            for (int node : leaves) leaf_candidates(nodes.data(), pts.data(), node, q[0], q[1], q[2], b0, r2f, push);
+            if (static_cast<int>(cand.size()) <= qcap) {
+                unsigned long long kth = 0;
+                auto at = [&](int c) { return static_cast<int>(cand[static_cast<size_t>(c)]); };
+                const int cnt = select_candidates<1>(pts.data(), at, static_cast<int>(cand.size()), m, q[0], q[1], q[2], buf.data(), &kth);
+                for (int s2 = 0; s2 < cnt; ++s2) found.push_back(buf[s2]);
+                if (!std::is_sorted(found.begin(), found.end())) return -2;  // rows come out in FLANN's order
+                if ((kth != kKeyInf) != (cnt == m) || (cnt == m && kth != *std::max_element(found.begin(), found.end())))
+                    return -1;
+            } else {
+                HeapList<1> L;
+                L.k = buf.data();
+                L.init(m);
+                tree_search(g, nodes.data(), pts.data(), q[0], q[1], q[2], r2f, bound0, L, stack);
+                for (int s2 = L.begin(); s2 < L.end(); ++s2)
+                    if (buf[s2] != kKeyInf) found.push_back(buf[s2]);
+            }
         } else if (list_kind >= 100) {  // collect + select, the search kernel's list; column of m + (list_kind - 100) slots
             const int cap = m + (list_kind - 100);
             std::vector<unsigned long long> col(static_cast<size_t>(cap));

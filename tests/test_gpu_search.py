@@ -116,3 +116,35 @@ def test_full_size_properties(capi, oracle):
     oi, od, oc, _ = oracle.radius_search(src[sel], tgt, radius, m, use_grid=True)
     assert np.array_equal(oc, gc[sel])
     assert rows_as_sets(oi, oc) == rows_as_sets(gi[sel], gc[sel])
+
+
+def _moved_search_rows(capi, src, tgt, n_iter, **kw):
+    """Association of the n_iter-th search of an align() and the (moved) cloud that search saw."""
+    with capi.Registration(src, tgt, capi.make_params(n_iter=n_iter - 1, **kw)) as reg:
+        reg.align()
+        cloud = reg.filtered_source()  # after n_iter - 1 increments: what search n_iter starts from
+    with capi.Registration(src, tgt, capi.make_params(n_iter=n_iter, **kw)) as reg:
+        reg.align()
+        idx, cnt = reg.association()
+        n_done = len(reg.iteration_stats())
+    return cloud, idx, cnt, n_done
+
+
+@pytest.mark.parametrize("queued", [0, 1])
+@pytest.mark.parametrize("radius,m", [(0.5, 10), (1.5, 20), (3.0, 5)])
+def test_searches_after_a_cloud_move(capi, oracle, monkeypatch, queued, radius, m):
+    """Every search of an align() but the first is fused with the cloud move and pruned by a bound taken from the previous
+    association (the farthest previous neighbour of the moved query).  Its rows must still be exactly the m nearest
+    in-radius targets of the moved cloud -- for the default kernel and for the queued variant (PPCR_SEARCH_QUEUED=1)."""
+    monkeypatch.setenv("PPCR_SEARCH_QUEUED", str(queued))
+    src, tgt, _ = synth.lidar_pair(23, 32, 700, yaw_deg=1.0, trans=(0.2, 0.05, 0.0))
+    for n_iter in (2, 4):
+        cloud, idx, cnt, n_done = _moved_search_rows(capi, src, tgt, n_iter, max_neighbours=m, radius=radius, dof=5.0)
+        assert n_done == n_iter
+        oi, od, oc, _ = oracle.radius_search(cloud, tgt, radius, m, use_grid=True)
+        assert np.array_equal(cnt, oc)
+        w = min(m, oi.shape[1], idx.shape[1])
+        valid = np.arange(w)[None, :] < oc[:, None]
+        got = np.sort(np.where(valid, idx[:, :w], -1), axis=1)
+        want = np.sort(np.where(valid, oi[:, :w], -1), axis=1)
+        assert np.array_equal(got, want)

@@ -41,7 +41,7 @@ def test_lidar_with_outliers_and_all_list_kinds(emu, oracle):
     _check(emu, oracle, src, tgt, 3.0, 20, list_kind=3)
     _check(emu, oracle, src, tgt, 0.5, 10, list_kind=3)
     _check(emu, oracle, src, tgt, 3.0, 1, list_kind=3)
-    for kind in (2, 4, 5, 101, 104, 122):
+    for kind in (2, 4, 5, 101, 104, 122, 200 + 48, 200 + 100000):
         for m in (1, 2, 3, 7, 10, 16):
             _check(emu, oracle, src[::5], tgt, 2.0, m, list_kind=kind)
 
@@ -56,6 +56,7 @@ def test_lattice_with_exact_ties(emu, oracle, m):
     _check(emu, oracle, pts, pts, 0.75, m, leaf_cap=4, list_kind=3)
     _check(emu, oracle, pts, pts, 0.75, m, leaf_cap=4, list_kind=101)
     _check(emu, oracle, pts, pts, 0.75, m, leaf_cap=4, list_kind=112)
+    _check(emu, oracle, pts, pts, 0.75, m, leaf_cap=4, list_kind=200 + 100000)
     gi, gd, gc, _ = emu_tree_search(emu, pts, pts, 0.5, m)
     assert np.all(gc == 1) and np.array_equal(gi[:, 0], np.arange(400))
 
@@ -92,7 +93,7 @@ def test_warm_start_bound_does_not_change_the_result(emu, oracle):
     kth = np.where(full, od[:, m - 1], np.inf).astype(np.float32)
     for scale in (1.0, 1.00001, 1.7):
         bounds = np.where(full, kth * np.float32(scale), np.float32(np.inf)).astype(np.float32)
-        for kind in (2, 101, 108, 124):
+        for kind in (2, 101, 108, 124, 200 + 16, 200 + 100000):
             gi, gd, gc, _ = emu_tree_search(emu, src, tgt, radius, m, bounds=bounds, list_kind=kind)
             assert np.array_equal(gc, oc)
             valid = np.arange(m)[None, :] < oc[:, None]
