@@ -224,6 +224,7 @@ struct Engine {
     bool search_queued = false;  // searches after a cloud move go through k_search_q
     size_t search_q_smem_bytes = 0;
     int q_tiles = 1;
+    DevBuf<unsigned char> q_scratch;  // k_search_q's task / candidate queues
     int max_ticks = 0;
     // graph driver
     cudaGraph_t graph = nullptr;
@@ -256,6 +257,7 @@ struct Engine {
         d_pairs.release();
         d_loop.release();
         flush.release();
+        q_scratch.release();
         if (stream) cudaStreamSynchronize(stream);  // the frees above are stream-ordered
         if (own_stream && stream) cudaStreamDestroy(stream);
         if (g_alloc_stream == stream) g_alloc_stream = nullptr;
@@ -690,8 +692,8 @@ static void engine_commit(Engine& E)
     long long max_src = 1;
     int max_eval = 1;
     // The queued search (k_search_q) is opt-in, PPCR_SEARCH_QUEUED=1: on the 1M-point pair it needs a third fewer warp
-    // instructions than k_search (218 M against 331 M, 21 lanes active instead of 13) but its shared-memory queues cost L1
-    // capacity and resident warps, and it ends level: 0.43 ms on a converged pair, 0.69 against 0.61 ms inside the loop.
+    // instructions than k_search (218 M against 331 M, 21 lanes active instead of 13) and is faster on a converged pair
+    // (0.375 against 0.424 ms), but level inside the loop (0.62 against 0.61 ms), where its fallback queries decide.
     // Read at every commit (not cached) so that a test can switch it inside one process.
     const bool queued_wanted = getenv("PPCR_SEARCH_QUEUED") && atoi(getenv("PPCR_SEARCH_QUEUED")) != 0;
     bool queued = queued_wanted && search_variant() == 0 && E.params.max_neighbours <= kSearchQueuedMaxM;
@@ -705,9 +707,6 @@ static void engine_commit(Engine& E)
         max_src = std::max<long long>(max_src, host[p].n_src);
         max_eval = std::max(max_eval, host[p].n_eval_blocks);
     }
-    E.d_pairs.reserve(np);
-    CK(cudaMemcpyAsync(E.d_pairs.p, host.data(), sizeof(PairDev) * np, cudaMemcpyHostToDevice, E.stream));
-    CK(cudaStreamSynchronize(E.stream));
     E.search_smem = static_cast<size_t>(search_cap(E.params.max_neighbours)) * kSearchThreads * sizeof(unsigned long long);
     if (const char* pad = getenv("PPCR_SEARCH_PAD_SMEM")) E.search_smem += static_cast<size_t>(atoi(pad));  // occupancy experiments
     E.eval_smem = E.opts.exact_weights ? kEvalSmem : eval_fast_smem(max_m);
@@ -770,6 +769,13 @@ static void engine_commit(Engine& E)
             E.graph_ready = false;
         }
     }
+    if (E.search_queued) {  // one slab of queues per block of k_search_q's grid
+        E.q_scratch.reserve(static_cast<size_t>(E.q_tiles) * np * search_q_scratch_per_block());
+        for (int p = 0; p < np; ++p) E.pairs[p].dev.q_scratch = host[p].q_scratch = E.q_scratch.p;
+    }
+    E.d_pairs.reserve(np);
+    CK(cudaMemcpyAsync(E.d_pairs.p, host.data(), sizeof(PairDev) * np, cudaMemcpyHostToDevice, E.stream));
+    CK(cudaStreamSynchronize(E.stream));
     // generous device-side cap: n_iter outer iterations, each at most ~64 LM evaluations in practice
     const long long cap = (static_cast<long long>(E.params.n_iter) + 2) * 256 + 64;
     E.max_ticks = static_cast<int>(std::min<long long>(cap, INT_MAX / 2));

@@ -71,6 +71,7 @@ struct PairDev {
     int m;          // result capacity = min(max_neighbours, n_tgt)
     int search_cap; // slots per query in the search kernel's shared-memory column (CollectList: > m)
     int search_queued;  // 1: searches that follow a cloud move are k_search_q's, k_search only does the first of an align()
+    unsigned char* q_scratch;  // k_search_q's task / candidate queues: one slab per block of its grid (all pairs share the pointer)
     float r2f;      // float(radius * radius): strict membership bound (FLANN)
     int* nbr_pos;   // [m][n_pad] slot-major association: positions in tgt_sorted
     const int* inv_perm;  // [n_tgt] original index -> position in tgt_sorted
@@ -515,11 +516,14 @@ constexpr int kQNodeBits = 25;                   // task = query slot << 25 | no
 constexpr uint32_t kQLowMask = (1u << kQNodeBits) - 1u;
 // a candidate is named by 16 bits: task index << 5 | offset in the task's leaf (leaves hold at most 32 points, except
 // finest-level cells full of near-duplicates: a query that meets one falls back)
+// The two queues of a block live in GLOBAL memory (a scratch slab per resident block, 20 KB, L2 resident, accessed with
+// .cg loads / stores so that they do not displace the tree from L1): in shared memory they limited the kernel to 6 blocks
+// per SM and left the walk 50 KB of L1.  Shared memory keeps the queries, the counters and the heap columns.
 PPCR_HD constexpr size_t search_q_smem(int m)
 {
-    return static_cast<size_t>(kSearchThreads) * (16u + 4u) + 4u * kQTaskCap + 2u * kSearchThreads * kQCand +
-           8u * static_cast<size_t>(kSearchThreads) * static_cast<size_t>(m);
+    return static_cast<size_t>(kSearchThreads) * (16u + 4u) + 8u * static_cast<size_t>(kSearchThreads) * static_cast<size_t>(m);
 }
+PPCR_HD constexpr size_t search_q_scratch_per_block() { return 4u * kQTaskCap + 2u * kSearchThreads * kQCand; }
 
 struct QEmit {  // phase A -> task queue
     uint32_t* tasks;
@@ -529,7 +533,7 @@ struct QEmit {  // phase A -> task queue
     __device__ __forceinline__ bool operator()(int node)
     {
         if (++mine > kQTaskPerQuery) return false;
-        tasks[atomicAdd(n_tasks, 1)] = (slot << kQNodeBits) | static_cast<uint32_t>(node);
+        __stcg(tasks + atomicAdd(n_tasks, 1), (slot << kQNodeBits) | static_cast<uint32_t>(node));
         return true;
     }
 };
@@ -546,7 +550,7 @@ struct QPush {  // phase B -> candidate list of one query (slot-major: entry c o
         }
         int c = atomicAdd(cnt, __popc(pass));  // room for every survivor of the leaf at once
         while (pass && c < kQCand) {
-            cand[c++ * kSearchThreads] = static_cast<unsigned short>((task << 5) | static_cast<uint32_t>(lowest_bit(pass)));
+            __stcg(cand + c++ * kSearchThreads, static_cast<unsigned short>((task << 5) | static_cast<uint32_t>(lowest_bit(pass))));
             pass &= pass - 1;
         }
     }
@@ -556,8 +560,8 @@ struct QCand {  // phase C: candidate c of one query -> position in the sorted t
     const uint32_t* tasks;
     __device__ __forceinline__ int operator()(int c) const
     {
-        const uint32_t v = cand[c * kSearchThreads];
-        return static_cast<int>((tasks[v >> 5] & kQLowMask) + (v & 31u));
+        const uint32_t v = __ldcg(cand + c * kSearchThreads);
+        return static_cast<int>((__ldcg(tasks + (v >> 5)) & kQLowMask) + (v & 31u));
     }
 };
 
@@ -569,9 +573,10 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
     if (st->phase != PH_SEARCH || st->apply_dT == 0 || !P.search_queued) return;
     float4* s_q = reinterpret_cast<float4*>(s_raw);                       // query, .w = its pruning bound
     int* s_cnt = reinterpret_cast<int*>(s_q + kSearchThreads);            // candidates pushed per query
-    uint32_t* s_tasks = reinterpret_cast<uint32_t*>(s_cnt + kSearchThreads);
+    unsigned long long* s_heap = reinterpret_cast<unsigned long long*>(s_cnt + kSearchThreads);
+    uint32_t* s_tasks = reinterpret_cast<uint32_t*>(P.q_scratch + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) *
+                                                                       search_q_scratch_per_block());  // this block's slab
     unsigned short* s_cand = reinterpret_cast<unsigned short*>(s_tasks + kQTaskCap);
-    unsigned long long* s_heap = reinterpret_cast<unsigned long long*>(s_cand + kSearchThreads * kQCand);
     __shared__ double s_T[12];
     __shared__ int s_chunk, s_ntasks;
     if (threadIdx.x < 12) s_T[threadIdx.x] = st->dT[threadIdx.x];
@@ -652,12 +657,12 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
         // ---- B: every queued leaf against its query ----
         const int n_tasks = s_ntasks;
         for (int t = threadIdx.x; t < n_tasks; t += kSearchThreads) {
-            const uint32_t task = s_tasks[t];
+            const uint32_t task = __ldcg(s_tasks + t);
             const uint32_t ql = task >> kQNodeBits;
             const float4 qq = s_q[ql];
             const int node = static_cast<int>(task & kQLowMask);
             const int begin = __ldg(&nodes[node].begin);
-            s_tasks[t] = (task & ~kQLowMask) | static_cast<uint32_t>(begin);  // phase C turns candidates back into positions with it
+            __stcg(s_tasks + t, (task & ~kQLowMask) | static_cast<uint32_t>(begin));  // phase C turns candidates back into positions with it
             QPush push{s_cand + ql, s_cnt + ql, static_cast<uint32_t>(t), begin};
             leaf_candidates(nodes, tgt_sorted, node, qq.x, qq.y, qq.z, qq.w, r2f, push);
         }
