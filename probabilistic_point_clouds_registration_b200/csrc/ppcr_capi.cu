@@ -691,11 +691,11 @@ static void engine_commit(Engine& E)
     int max_m = 1;
     long long max_src = 1;
     int max_eval = 1;
-    // The queued search (k_search_q) is opt-in, PPCR_SEARCH_QUEUED=1: on the 1M-point pair it needs a third fewer warp
-    // instructions than k_search (218 M against 331 M, 21 lanes active instead of 13) and is faster on a converged pair
-    // (0.375 against 0.424 ms), but level inside the loop (0.62 against 0.61 ms), where its fallback queries decide.
+    // The queued search (k_search_q) does every search that follows a cloud move whenever its queues fit (the heap columns in
+    // shared memory grow with m; a task names a node in 25 bits): on the 1M-point pair 0.29 against 0.42 ms on a converged
+    // pair, 0.50 against 0.61 ms inside the loop.  PPCR_SEARCH_QUEUED=0 switches it off (k_search then does every search).
     // Read at every commit (not cached) so that a test can switch it inside one process.
-    const bool queued_wanted = getenv("PPCR_SEARCH_QUEUED") && atoi(getenv("PPCR_SEARCH_QUEUED")) != 0;
+    const bool queued_wanted = !(getenv("PPCR_SEARCH_QUEUED") && atoi(getenv("PPCR_SEARCH_QUEUED")) == 0);
     bool queued = queued_wanted && search_variant() == 0 && E.params.max_neighbours <= kSearchQueuedMaxM;
     for (int p = 0; p < np; ++p)
         queued = queued && E.pairs[p].dev.tree.n_nodes_cap < (1 << kQNodeBits) && E.pairs[p].dev.n_tgt < (1 << kQNodeBits);

@@ -501,7 +501,7 @@ __global__ void PPCR_SEARCH_BOUNDS k_search(const PairDev* __restrict__ pairs)
 // updates).  Every search but the first of an align() knows a tight pruning bound per query BEFORE it starts -- the
 // distance of the farthest of last iteration's neighbours to the moved query -- so the walk does not need the heap to prune.
 // That allows the three kinds of work to be separated and each to be done by all threads of the block at the same time,
-// for whichever query it belongs to, through queues in shared memory:
+// for whichever query it belongs to, through two queues per block:
 //   A  (thread per query)   move the query, bound from the previous neighbours, walk the octree with that fixed bound and
 //                           push every leaf within it as a task (query slot, node) on the block's task queue
 //   B  (thread per task)    test the leaf's points against its query; survivors' positions go to the query's candidate list
@@ -509,21 +509,21 @@ __global__ void PPCR_SEARCH_BOUNDS k_search(const PairDev* __restrict__ pairs)
 // A query whose tasks or candidates overflow the queues (no useful bound: a row that had fewer than m neighbours in a dense
 // region) is searched by tree_search with the heap, as in k_search.  Results are bit-identical to k_search's: same distance
 // arithmetic, same strict radius test, same (distance, index) order.
-constexpr int kQTaskPerQuery = 16;               // leaves one query may queue; beyond that it is searched by tree_search
-constexpr int kQTaskCap = kSearchThreads * kQTaskPerQuery;  // leaf tasks per block of 128 queries: the queue cannot overflow
-constexpr int kQCand = 48;                       // candidates per query
-constexpr int kQNodeBits = 25;                   // task = query slot << 25 | node index (phase A), | first position (from phase B on)
+constexpr int kQTaskPerQuery = 64;               // leaves one query may queue; beyond that it is searched by tree_search
+constexpr int kQTaskCap = 8192;                  // leaf tasks per block of 128 queries (64 per query on average)
+constexpr int kQCand = 64;                       // candidate positions per query
+constexpr int kQNodeBits = 25;                   // task = query slot << 25 | node index
 constexpr uint32_t kQLowMask = (1u << kQNodeBits) - 1u;
-// a candidate is named by 16 bits: task index << 5 | offset in the task's leaf (leaves hold at most 32 points, except
-// finest-level cells full of near-duplicates: a query that meets one falls back)
-// The two queues of a block live in GLOBAL memory (a scratch slab per resident block, 20 KB, L2 resident, accessed with
-// .cg loads / stores so that they do not displace the tree from L1): in shared memory they limited the kernel to 6 blocks
-// per SM and left the walk 50 KB of L1.  Shared memory keeps the queries, the counters and the heap columns.
+// The two queues of a block live in GLOBAL memory (a scratch slab per resident block, L2 resident, accessed with .cg
+// loads / stores so that they do not displace the tree from L1): in shared memory they limited the kernel to 6 blocks per
+// SM and left the walk 50 KB of L1.  That also makes them cheap to size for the expensive queries -- the ones half a
+// metre off a dense surface, whose bound touches 30-40 leaves -- so that those go through the queues like all others
+// instead of falling back.  Shared memory keeps the queries, the counters and the heap columns.
 PPCR_HD constexpr size_t search_q_smem(int m)
 {
     return static_cast<size_t>(kSearchThreads) * (16u + 4u) + 8u * static_cast<size_t>(kSearchThreads) * static_cast<size_t>(m);
 }
-PPCR_HD constexpr size_t search_q_scratch_per_block() { return 4u * kQTaskCap + 2u * kSearchThreads * kQCand; }
+PPCR_HD constexpr size_t search_q_scratch_per_block() { return 4u * kQTaskCap + 4u * kSearchThreads * kQCand; }
 
 struct QEmit {  // phase A -> task queue
     uint32_t* tasks;
@@ -533,36 +533,27 @@ struct QEmit {  // phase A -> task queue
     __device__ __forceinline__ bool operator()(int node)
     {
         if (++mine > kQTaskPerQuery) return false;
-        __stcg(tasks + atomicAdd(n_tasks, 1), (slot << kQNodeBits) | static_cast<uint32_t>(node));
+        const int t = atomicAdd(n_tasks, 1);
+        if (t >= kQTaskCap) return false;
+        __stcg(tasks + t, (slot << kQNodeBits) | static_cast<uint32_t>(node));
         return true;
     }
 };
 struct QPush {  // phase B -> candidate list of one query (slot-major: entry c of query ql at [c * 128 + ql])
-    unsigned short* cand;
+    uint32_t* cand;
     int* cnt;
-    uint32_t task;   // index of the task in the queue
-    int begin;       // first position of its leaf
     __device__ __forceinline__ void operator()(int j0, uint32_t pass)
     {
-        if (j0 != begin) {  // the second 32 points of an oversized leaf: not nameable, the query falls back
-            atomicAdd(cnt, 2 * kQCand);
-            return;
-        }
-        int c = atomicAdd(cnt, __popc(pass));  // room for every survivor of the leaf at once
+        int c = atomicAdd(cnt, __popc(pass));  // room for every survivor of the group at once
         while (pass && c < kQCand) {
-            __stcg(cand + c++ * kSearchThreads, static_cast<unsigned short>((task << 5) | static_cast<uint32_t>(lowest_bit(pass))));
+            __stcg(cand + c++ * kSearchThreads, static_cast<uint32_t>(j0 + lowest_bit(pass)));
             pass &= pass - 1;
         }
     }
 };
 struct QCand {  // phase C: candidate c of one query -> position in the sorted target
-    const unsigned short* cand;
-    const uint32_t* tasks;
-    __device__ __forceinline__ int operator()(int c) const
-    {
-        const uint32_t v = __ldcg(cand + c * kSearchThreads);
-        return static_cast<int>((__ldcg(tasks + (v >> 5)) & kQLowMask) + (v & 31u));
-    }
+    const uint32_t* cand;
+    __device__ __forceinline__ int operator()(int c) const { return static_cast<int>(__ldcg(cand + c * kSearchThreads)); }
 };
 
 __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __restrict__ pairs)
@@ -576,7 +567,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
     unsigned long long* s_heap = reinterpret_cast<unsigned long long*>(s_cnt + kSearchThreads);
     uint32_t* s_tasks = reinterpret_cast<uint32_t*>(P.q_scratch + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) *
                                                                        search_q_scratch_per_block());  // this block's slab
-    unsigned short* s_cand = reinterpret_cast<unsigned short*>(s_tasks + kQTaskCap);
+    uint32_t* s_cand = s_tasks + kQTaskCap;
     __shared__ double s_T[12];
     __shared__ int s_chunk, s_ntasks;
     if (threadIdx.x < 12) s_T[threadIdx.x] = st->dT[threadIdx.x];
@@ -655,16 +646,13 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
         __syncthreads();
         PPCR_Q_MARK(0)
         // ---- B: every queued leaf against its query ----
-        const int n_tasks = s_ntasks;
+        const int n_tasks = min(s_ntasks, kQTaskCap);
         for (int t = threadIdx.x; t < n_tasks; t += kSearchThreads) {
             const uint32_t task = __ldcg(s_tasks + t);
             const uint32_t ql = task >> kQNodeBits;
             const float4 qq = s_q[ql];
-            const int node = static_cast<int>(task & kQLowMask);
-            const int begin = __ldg(&nodes[node].begin);
-            __stcg(s_tasks + t, (task & ~kQLowMask) | static_cast<uint32_t>(begin));  // phase C turns candidates back into positions with it
-            QPush push{s_cand + ql, s_cnt + ql, static_cast<uint32_t>(t), begin};
-            leaf_candidates(nodes, tgt_sorted, node, qq.x, qq.y, qq.z, qq.w, r2f, push);
+            QPush push{s_cand + ql, s_cnt + ql};
+            leaf_candidates(nodes, tgt_sorted, static_cast<int>(task & kQLowMask), qq.x, qq.y, qq.z, qq.w, r2f, push);
         }
         __syncthreads();
         PPCR_Q_MARK(1)
@@ -689,7 +677,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
             float kth = kInf;
             if (!fallback) {
                 unsigned long long kk;
-                const QCand at{s_cand + threadIdx.x, s_tasks};
+                const QCand at{s_cand + threadIdx.x};
                 const int n = select_candidates<kSearchThreads>(tgt_sorted, at, n_c, m, q.x, q.y, q.z, s_heap + threadIdx.x, &kk);
                 for (int s = 0; s < n; ++s) search_store(out, i, cnt++, s_heap[threadIdx.x + s * kSearchThreads]);
                 if (kk != kKeyInf) kth = key_d2(kk);
