@@ -2,8 +2,8 @@
 //
 //   tree build      k_bbox, k_tree_keys, (radix sort), k_tree_gather, k_tree_root, k_tree_split_level
 //                                                                     (replaces the kd-tree build, registration.cc:66-67)
-//   radius search   k_search<CAP>                                     (replaces the radiusSearch loop, :72-81, and the
-//                                                                      CSR assembly, :69-83)
+//   radius search   k_search (first search of an align()),            (replaces the radiusSearch loop, :72-81, and the
+//                   k_search_q (every search after a cloud move)       CSR assembly, :69-83)
 //   weights + J^TWJ k_eval<FAST>                                      (WeightUpdaterCallback, ProbabilisticWeights,
 //                                                                      ErrorTerm + Ceres' Jacobian evaluation)
 //   LM controller   k_controller                                      (ceres::Solve's trust-region loop, pose
