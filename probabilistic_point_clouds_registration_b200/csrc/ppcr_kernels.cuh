@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
                 }
                 bound0 = fminf(r2f, far2);
             }
-            s_q[threadIdx.x] = make_float4(q.x, q.y, q.z, bound0);
+            s_q[threadIdx.x] = make_float4(q.x, q.y, q.z, candidate_limit(bound0, r2f));
             QEmit emit{s_tasks, &s_ntasks, threadIdx.x, 0};
             fallback = !tree_collect_leaves(geom, nodes, q.x, q.y, q.z, bound0, emit, stack);
         }
@@ -652,7 +652,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
             const uint32_t ql = task >> kQNodeBits;
             const float4 qq = s_q[ql];
             QPush push{s_cand + ql, s_cnt + ql};
-            leaf_candidates(nodes, tgt_sorted, static_cast<int>(task & kQLowMask), qq.x, qq.y, qq.z, qq.w, r2f, push);
+            leaf_candidates(nodes, tgt_sorted, static_cast<int>(task & kQLowMask), qq.x, qq.y, qq.z, qq.w, push);
         }
         __syncthreads();
         PPCR_Q_MARK(1)

@@ -733,32 +733,47 @@ PPCR_HD bool tree_collect_leaves(const TreeGeom& g, const TreeNode* __restrict__
     return ok;
 }
 
-// Second phase: the points of one emitted leaf against one query.  Every point of the leaf that passes the same two tests
-// a candidate passes in tree_search -- d2 <= bound_d2 and d2 < r2f (strict) -- is reported, 32 points at a time:
-// push(first position, survivor bit mask).  Two passes like tree_search's leaf scan: the point loop only sets bits, so
-// the caller reserves room for all survivors of the group with ONE atomic instead of one per survivor.
+// Second phase: the points of one emitted leaf against one query.  Every point of the leaf with d2 <= limit_d2 is reported,
+// 32 points at a time: push(first position, survivor bit mask).  limit_d2 folds the two tests a candidate passes in
+// tree_search -- d2 <= bound and d2 < r2f (strict) -- into one comparison: candidate_limit(bound, r2f).  Two passes like
+// tree_search's leaf scan: the point loop only sets bits, so the caller reserves room for all survivors of the group
+// with ONE atomic instead of one per survivor.
+PPCR_HD float candidate_limit(float bound_d2, float r2f)
+{
+    if (bound_d2 < r2f) return bound_d2;
+    // the largest float below r2f (r2f > 0: a squared radius): d2 <= it  <=>  d2 < r2f
+    return r2f > 0.f ? bits_float(float_bits(r2f) - 1u) : -1.f;
+}
+
 template <class Push>
 PPCR_HD void leaf_candidates(const TreeNode* __restrict__ nodes, const float4* __restrict__ pts, int node, float qx, float qy,
-                             float qz, float bound_d2, float r2f, Push& push)
+                             float qz, float limit_d2, Push& push)
 {
-    const TreeNode n = load_node(nodes + node);
+    struct Range {
+        int begin, end;
+    };
+#if defined(__CUDA_ARCH__)
+    const int2 be = __ldg(reinterpret_cast<const int2*>(&nodes[node].begin));  // only the range of the leaf is needed
+    const Range n{be.x, be.y};
+#else
+    const Range n{nodes[node].begin, nodes[node].end};
+#endif
     PPCR_STAT(leaves, 1);
     PPCR_STAT(points, n.end - n.begin);
     const int last = n.end - 1;
     for (int j0 = n.begin; j0 < n.end; j0 += 32) {
         const int stop = n.end - j0 < 32 ? n.end - j0 : 32;
         uint32_t pass = 0;
-        // four independent loads in flight per thread (the index is clamped, the surplus results are discarded)
+        // four independent loads in flight per thread; past the end the index is clamped and the bits masked off below
         for (int t = 0; t < stop; t += 4) {
             float4 p[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) p[u] = load_point(pts + (j0 + t + u < last ? j0 + t + u : last));
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float d2 = dist2_exact(qx, qy, qz, p[u].x, p[u].y, p[u].z);
-                if (t + u < stop && d2 <= bound_d2 && d2 < r2f) pass |= 1u << (t + u);
-            }
+            for (int u = 0; u < 4; ++u)
+                if (dist2_exact(qx, qy, qz, p[u].x, p[u].y, p[u].z) <= limit_d2) pass |= 1u << ((t + u) & 31);
         }
+        if (stop < 32) pass &= (1u << stop) - 1u;
         if (pass) push(j0, pass);
     }
 }

@@ -325,7 +325,7 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
             auto push = [&](int j0, uint32_t pass) {
                 for (; pass; pass &= pass - 1) cand.push_back(static_cast<uint32_t>(j0 + lowest_bit(pass)));
             };
-            for (int node : leaves) leaf_candidates(nodes.data(), pts.data(), node, q[0], q[1], q[2], b0, r2f, push);
+            for (int node : leaves) leaf_candidates(nodes.data(), pts.data(), node, q[0], q[1], q[2], candidate_limit(b0, r2f), push);
             if (static_cast<int>(cand.size()) <= qcap) {
                 unsigned long long kth = 0;
                 auto at = [&](int c) { return static_cast<int>(cand[static_cast<size_t>(c)]); };

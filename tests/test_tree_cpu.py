@@ -57,8 +57,9 @@ def test_lattice_with_exact_ties(emu, oracle, m):
     _check(emu, oracle, pts, pts, 0.75, m, leaf_cap=4, list_kind=101)
     _check(emu, oracle, pts, pts, 0.75, m, leaf_cap=4, list_kind=112)
     _check(emu, oracle, pts, pts, 0.75, m, leaf_cap=4, list_kind=200 + 100000)
-    gi, gd, gc, _ = emu_tree_search(emu, pts, pts, 0.5, m)
-    assert np.all(gc == 1) and np.array_equal(gi[:, 0], np.arange(400))
+    for kind in (2, 200 + 100000):  # a neighbour at exactly the radius is outside (strict), for the heap walk and the queued phases
+        gi, gd, gc, _ = emu_tree_search(emu, pts, pts, 0.5, m, list_kind=kind)
+        assert np.all(gc == 1) and np.array_equal(gi[:, 0], np.arange(400))
 
 
 def test_edge_cases(emu, oracle):
