@@ -579,7 +579,8 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
         note_launches(1);
     }
     tr.mark("voxel filters + tag");
-    const int leaf_cap = E.opts.leaf_capacity > 0 ? E.opts.leaf_capacity : kDefaultLeafCap;
+    static const int env_leaf = getenv("PPCR_LEAF_CAP") ? atoi(getenv("PPCR_LEAF_CAP")) : 0;  // tuning
+    const int leaf_cap = E.opts.leaf_capacity > 0 ? E.opts.leaf_capacity : env_leaf > 0 ? env_leaf : kDefaultLeafCap;
     if (P.n_tgt > 0) {
         build_target_tree(E, P, leaf_cap);
         tr.mark("target tree");
@@ -702,6 +703,7 @@ static void engine_commit(Engine& E)
     E.search_queued = queued;
     for (int p = 0; p < np; ++p) {
         E.pairs[p].dev.search_queued = queued ? 1 : 0;
+        E.pairs[p].dev.q_heavy = getenv("PPCR_Q_HEAVY") ? static_cast<float>(atof(getenv("PPCR_Q_HEAVY"))) : 0.75f;  // (tuning)
         host[p] = E.pairs[p].dev;
         max_m = std::max(max_m, host[p].m);
         max_src = std::max<long long>(max_src, host[p].n_src);

@@ -71,6 +71,7 @@ struct PairDev {
     int m;          // result capacity = min(max_neighbours, n_tgt)
     int search_cap; // slots per query in the search kernel's shared-memory column (CollectList: > m)
     int search_queued;  // 1: searches that follow a cloud move are k_search_q's, k_search only does the first of an align()
+    float q_heavy;             // k_search_q: a query expecting more than q_heavy * kQCand candidates counts as heavy
     unsigned char* q_scratch;  // k_search_q's task / candidate queues: one slab per block of its grid (all pairs share the pointer)
     float r2f;      // float(radius * radius): strict membership bound (FLANN)
     int* nbr_pos;   // [m][n_pad] slot-major association: positions in tgt_sorted
@@ -572,6 +573,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
     __shared__ int s_chunk, s_ntasks;
     if (threadIdx.x < 12) s_T[threadIdx.x] = st->dT[threadIdx.x];
     const int m = P.m;
+    const float heavy_factor = P.q_heavy;
     const int n_src = P.n_src;
     const float r2f = P.r2f;
     const TreeGeom geom = P.tree;
@@ -608,7 +610,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
         // ---- A: the query, its bound, its leaves ----
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
         float bound0 = r2f;
-        bool fallback = false;
+        bool fallback = false, heavy = false;
         if (valid) {
             q = src[i];
             const double x = q.x, y = q.y, z = q.z;
@@ -638,7 +640,32 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
                     far2 = fmaxf(far2, dist2_exact(nx, ny, nz, t.x, t.y, t.z));
                 }
                 bound0 = fminf(r2f, far2);
+                // On a surface the targets within the bound number about m (bound / previous m-th distance)^2: a query is
+                // "heavy" when that would fill most of its candidate list.  It happens when the cloud moves by more than
+                // the neighbour spacing (the 10M-point pair: spacing 1 cm, increments of 2 cm).
+                heavy = static_cast<float>(m) * far2 > heavy_factor * static_cast<float>(kQCand) * prev;
             }
+        }
+        // A chunk made mostly of heavy queries is searched the way k_search does it -- every thread walks with its heap and
+        // lets the bound shrink as candidates arrive -- because the fixed bound would push them all through the fallback.
+        if (__syncthreads_count(heavy) * 2 > kSearchThreads) {
+            if (valid) {
+                HeapList<kSearchThreads, 0> L;
+                L.k = s_heap + threadIdx.x;
+                L.init(m);
+                tree_search(geom, nodes, tgt_sorted, q.x, q.y, q.z, r2f, bound0, L, stack);
+                int cnt = 0;
+                for (int s = 0; s < m; ++s) {
+                    const unsigned long long key = L.k[s * kSearchThreads];
+                    if (key != kKeyInf) search_store(out, i, cnt++, key);
+                }
+                nbr_cnt[i] = cnt;
+                nbr_kth[i] = L.kth_key() != kKeyInf ? key_d2(L.kth_key()) : kInf;
+                cnt_total += cnt;
+            }
+            continue;
+        }
+        if (valid) {
             s_q[threadIdx.x] = make_float4(q.x, q.y, q.z, candidate_limit(bound0, r2f));
             QEmit emit{s_tasks, &s_ntasks, threadIdx.x, 0};
             fallback = !tree_collect_leaves(geom, nodes, q.x, q.y, q.z, bound0, emit, stack);

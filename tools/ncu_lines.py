@@ -45,7 +45,9 @@ for ln in dis:
     if m:
         line_of[int(m.group(1), 16)] = cur
 
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+# a capture may hold several kernels (the search launches k_search and k_search_q back to back): NCU_KERNEL=<regex> picks one
+sel = ["--kernel-name", "regex:" + os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else []
+raw = subprocess.run(["ncu", "-i", rep, *sel, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]
