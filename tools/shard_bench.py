@@ -58,6 +58,7 @@ if rank == 0:
     corr = sum(s["n_correspondences"] for s in stats)
     evals = sum(s["lm_iterations"] + 1 for s in stats)
     ms = 1e3 * float(np.mean(times))
+    print("SHARD_BENCH reps (ms):", " ".join(f"{1e3 * t:.1f}" for t in times))
     print(f"SHARD_BENCH n_gpus={world} n_src={len(src)} n_tgt={len(tgt)} outer={len(stats)} evals={evals} "
           f"correspondences={corr} ms={ms:.1f} (min {1e3 * min(times):.1f}) corr_per_s={corr / (ms * 1e-3):.3e} gen_s={gen_s:.0f}")
 if world > 1:
