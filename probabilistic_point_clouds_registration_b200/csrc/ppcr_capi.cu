@@ -703,6 +703,7 @@ static void engine_commit(Engine& E)
     E.search_queued = queued;
     for (int p = 0; p < np; ++p) {
         E.pairs[p].dev.search_queued = queued ? 1 : 0;
+        E.pairs[p].dev.q_cand = getenv("PPCR_Q_CAND") ? atoi(getenv("PPCR_Q_CAND")) : search_q_cand(E.params.max_neighbours);
         E.pairs[p].dev.q_heavy = getenv("PPCR_Q_HEAVY") ? static_cast<float>(atof(getenv("PPCR_Q_HEAVY"))) : 0.75f;  // (tuning)
         host[p] = E.pairs[p].dev;
         max_m = std::max(max_m, host[p].m);
@@ -772,7 +773,7 @@ static void engine_commit(Engine& E)
         }
     }
     if (E.search_queued) {  // one slab of queues per block of k_search_q's grid
-        E.q_scratch.reserve(static_cast<size_t>(E.q_tiles) * np * search_q_scratch_per_block());
+        E.q_scratch.reserve(static_cast<size_t>(E.q_tiles) * np * search_q_scratch_per_block(E.pairs[0].dev.q_cand));
         for (int p = 0; p < np; ++p) E.pairs[p].dev.q_scratch = host[p].q_scratch = E.q_scratch.p;
     }
     E.d_pairs.reserve(np);

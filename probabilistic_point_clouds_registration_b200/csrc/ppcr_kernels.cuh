@@ -71,7 +71,8 @@ struct PairDev {
     int m;          // result capacity = min(max_neighbours, n_tgt)
     int search_cap; // slots per query in the search kernel's shared-memory column (CollectList: > m)
     int search_queued;  // 1: searches that follow a cloud move are k_search_q's, k_search only does the first of an align()
-    float q_heavy;             // k_search_q: a query expecting more than q_heavy * kQCand candidates counts as heavy
+    int q_cand;                // k_search_q: candidate positions per query (search_q_cand(max_neighbours))
+    float q_heavy;             // k_search_q: a query expecting more than q_heavy * q_cand candidates counts as heavy
     unsigned char* q_scratch;  // k_search_q's task / candidate queues: one slab per block of its grid (all pairs share the pointer)
     float r2f;      // float(radius * radius): strict membership bound (FLANN)
     int* nbr_pos;   // [m][n_pad] slot-major association: positions in tgt_sorted
@@ -512,7 +513,9 @@ __global__ void PPCR_SEARCH_BOUNDS k_search(const PairDev* __restrict__ pairs)
 // arithmetic, same strict radius test, same (distance, index) order.
 constexpr int kQTaskPerQuery = 64;               // leaves one query may queue; beyond that it is searched by tree_search
 constexpr int kQTaskCap = 8192;                  // leaf tasks per block of 128 queries (64 per query on average)
-constexpr int kQCand = 64;                       // candidate positions per query
+// candidate positions per query.  128 for max_neighbours = 20 was tried: one 120k-point pair 6.2 -> 6.0 ms, but a batch of them
+// 403 -> 344 pairs/s (the slabs of six lanes crowd L2), so 64 for every m; PPCR_Q_CAND overrides it (tuning)
+PPCR_HD constexpr int search_q_cand(int /*max_nn*/) { return 64; }
 constexpr int kQNodeBits = 25;                   // task = query slot << 25 | node index
 constexpr uint32_t kQLowMask = (1u << kQNodeBits) - 1u;
 // The two queues of a block live in GLOBAL memory (a scratch slab per resident block, L2 resident, accessed with .cg
@@ -524,7 +527,7 @@ PPCR_HD constexpr size_t search_q_smem(int m)
 {
     return static_cast<size_t>(kSearchThreads) * (16u + 4u) + 8u * static_cast<size_t>(kSearchThreads) * static_cast<size_t>(m);
 }
-PPCR_HD constexpr size_t search_q_scratch_per_block() { return 4u * kQTaskCap + 4u * kSearchThreads * kQCand; }
+PPCR_HD constexpr size_t search_q_scratch_per_block(int q_cand) { return 4u * kQTaskCap + 4u * kSearchThreads * static_cast<size_t>(q_cand); }
 
 struct QEmit {  // phase A -> task queue
     uint32_t* tasks;
@@ -543,10 +546,11 @@ struct QEmit {  // phase A -> task queue
 struct QPush {  // phase B -> candidate list of one query (slot-major: entry c of query ql at [c * 128 + ql])
     uint32_t* cand;
     int* cnt;
+    int cap;
     __device__ __forceinline__ void operator()(int j0, uint32_t pass)
     {
         int c = atomicAdd(cnt, __popc(pass));  // room for every survivor of the group at once
-        while (pass && c < kQCand) {
+        while (pass && c < cap) {
             __stcg(cand + c++ * kSearchThreads, static_cast<uint32_t>(j0 + lowest_bit(pass)));
             pass &= pass - 1;
         }
@@ -567,12 +571,13 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
     int* s_cnt = reinterpret_cast<int*>(s_q + kSearchThreads);            // candidates pushed per query
     unsigned long long* s_heap = reinterpret_cast<unsigned long long*>(s_cnt + kSearchThreads);
     uint32_t* s_tasks = reinterpret_cast<uint32_t*>(P.q_scratch + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) *
-                                                                       search_q_scratch_per_block());  // this block's slab
+                                                                       search_q_scratch_per_block(P.q_cand));  // this block's slab
     uint32_t* s_cand = s_tasks + kQTaskCap;
     __shared__ double s_T[12];
     __shared__ int s_chunk, s_ntasks;
     if (threadIdx.x < 12) s_T[threadIdx.x] = st->dT[threadIdx.x];
     const int m = P.m;
+    const int q_cand = P.q_cand;
     const float heavy_factor = P.q_heavy;
     const int n_src = P.n_src;
     const float r2f = P.r2f;
@@ -643,7 +648,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
                 // On a surface the targets within the bound number about m (bound / previous m-th distance)^2: a query is
                 // "heavy" when that would fill most of its candidate list.  It happens when the cloud moves by more than
                 // the neighbour spacing (the 10M-point pair: spacing 1 cm, increments of 2 cm).
-                heavy = static_cast<float>(m) * far2 > heavy_factor * static_cast<float>(kQCand) * prev;
+                heavy = static_cast<float>(m) * far2 > heavy_factor * static_cast<float>(q_cand) * prev;
             }
         }
         // A chunk made mostly of heavy queries is searched the way k_search does it -- every thread walks with its heap and
@@ -678,7 +683,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
             const uint32_t task = __ldcg(s_tasks + t);
             const uint32_t ql = task >> kQNodeBits;
             const float4 qq = s_q[ql];
-            QPush push{s_cand + ql, s_cnt + ql};
+            QPush push{s_cand + ql, s_cnt + ql, q_cand};
             leaf_candidates(nodes, tgt_sorted, static_cast<int>(task & kQLowMask), qq.x, qq.y, qq.z, qq.w, push);
         }
         __syncthreads();
@@ -699,7 +704,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
 #if defined(PPCR_Q_PROFILE)
             n_fall_task += fallback ? 1 : 0;
 #endif
-            if (n_c > kQCand) fallback = true;
+            if (n_c > q_cand) fallback = true;
             int cnt = 0;
             float kth = kInf;
             if (!fallback) {
