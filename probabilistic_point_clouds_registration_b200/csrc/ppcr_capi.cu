@@ -615,7 +615,8 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     CK(cudaMemsetAsync(P.nbr_cnt.p, 0, static_cast<size_t>(D.n_pad) * sizeof(int), st));
     {
         const bool fast = !E.opts.exact_weights;
-        const int per_sm = fast ? kEvalFastBlocks : E.eval_blocks_per_sm;
+        // (the asynchronous-gather variant stages the target points too: 64 KB of shared memory per block at m = 10, three blocks per SM)
+        const int per_sm = fast ? (eval_async(E.params.max_neighbours) ? std::min(kEvalFastBlocks, kEvalAsyncBlocks) : kEvalFastBlocks) : E.eval_blocks_per_sm;
         D.n_eval_blocks = std::max(1, std::min(ceil_div(std::max(D.n_src, 1), eval_threads(fast)), per_sm * std::max(g_sm_count, 1)));
     }
     D.n_eval_groups = ceil_div(D.n_eval_blocks, kFoldGroup);
@@ -712,7 +713,7 @@ static void engine_commit(Engine& E)
     }
     E.search_smem = static_cast<size_t>(search_cap(E.params.max_neighbours)) * kSearchThreads * sizeof(unsigned long long);
     if (const char* pad = getenv("PPCR_SEARCH_PAD_SMEM")) E.search_smem += static_cast<size_t>(atoi(pad));  // occupancy experiments
-    E.eval_smem = E.opts.exact_weights ? kEvalSmem : eval_fast_smem(max_m);
+    E.eval_smem = E.opts.exact_weights ? kEvalSmem : eval_fast_smem(E.params.max_neighbours);
     {
         // the opt-in shared-memory sizes are per function and process wide: only ever raise them (handles of several host
         // threads, e.g. the lanes of ppcr_align_batch, launch the same kernels with different sizes)
@@ -822,7 +823,7 @@ static void launch_evalctl(Engine& E, bool use_cond, int probe = 0)
 {
     const int np = static_cast<int>(E.pairs.size());
     dim3 grid(E.max_eval_blocks, np);
-    const int flags = (use_cond ? 1 : 0) | probe;
+    const int flags = (use_cond ? 1 : 0) | probe | ((!E.opts.exact_weights && eval_async(E.params.max_neighbours)) ? 8 : 0);
     if (!E.opts.exact_weights)
         k_evalctl<true><<<grid, kEvalFastThreads, E.eval_smem, E.stream>>>(E.d_pairs.p, np, E.d_loop.p, E.cond, E.cond_search, flags, E.max_ticks);
     else

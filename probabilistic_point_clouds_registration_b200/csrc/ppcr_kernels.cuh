@@ -760,7 +760,23 @@ PPCR_HD constexpr int eval_threads(bool fast) { return fast ? kEvalFastThreads :
 
 // one staged tile of the fast evaluation: [m][128] positions, [128] counts, [128] source points
 PPCR_HD constexpr size_t eval_stage_bytes(int m) { return static_cast<size_t>(kEvalFastThreads) * (4u * static_cast<size_t>(m) + 20u); }
-PPCR_HD constexpr size_t eval_fast_smem(int m) { return kEvalStages * eval_stage_bytes(m) + 16u * kEvalStages; }
+// Build-time experiment (-DPPCR_EVAL_ASYNC=1): up to kEvalAsyncMaxM neighbours per row the gathered target points are staged too,
+// two buffers of [m][128] float4 filled by per-thread asynchronous copies (cp.async) one tile ahead of the arithmetic.
+#ifndef PPCR_EVAL_ASYNC
+#define PPCR_EVAL_ASYNC 0  // measured on the 1M-point pair: 81 us per evaluation against 63 (three blocks per SM, and the 16-byte copies take the same L1 path as the loads they replace)
+#endif
+constexpr int kEvalAsyncMaxM = PPCR_EVAL_ASYNC ? 12 : 0;
+#ifndef PPCR_EVAL_ASYNC_BLOCKS
+#define PPCR_EVAL_ASYNC_BLOCKS 3
+#endif
+constexpr int kEvalAsyncBlocks = PPCR_EVAL_ASYNC_BLOCKS;  // resident blocks per SM that fit with the point buffers at m = 10..12
+PPCR_HD constexpr bool eval_async(int m) { return m <= kEvalAsyncMaxM; }
+PPCR_HD constexpr size_t eval_points_bytes(int m) { return static_cast<size_t>(kEvalFastThreads) * 16u * static_cast<size_t>(m); }
+PPCR_HD constexpr size_t eval_fast_smem(int m)
+{
+    // (the stages are a multiple of 16 bytes; the barriers sit behind the point buffers)
+    return kEvalStages * eval_stage_bytes(m) + (eval_async(m) ? 2u * eval_points_bytes(m) : 0u) + 16u * kEvalStages;
+}
 
 // ---- asynchronous bulk copies (TMA, 1-D) completing on an mbarrier ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -916,7 +932,15 @@ struct EvalStage {
     uint32_t bar0;         // shared-space address of the first mbarrier
     size_t stage_bytes;
     int m;
+    float4* points;        // two buffers of [m][128] gathered target points (asynchronous variant), else null
 };
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_global)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_global) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // called by the whole first warp: lane 0 arms the barrier, then the lanes issue the m + 2 copies between them
 __device__ __forceinline__ void eval_issue_tile(const PairDev& P, const EvalStage& S, int stage, int tile)
@@ -936,7 +960,7 @@ __device__ __forceinline__ void eval_issue_tile(const PairDev& P, const EvalStag
     if (lane == ((S.m + 1) & 31)) bulk_g2s(dst + seg * S.m + seg, P.src + row0, kEvalFastThreads * 16u, bar);
 }
 
-template <int WM, bool SAME>
+template <int WM, bool SAME, bool ASYNC>
 __device__ __forceinline__ void eval_rows_fast(const PairDev& P, const EvalStage& S, const Pose& pe, const Pose& pw,
                                                const WeightCfg& wc, double* __restrict__ racc)
 {
@@ -945,12 +969,36 @@ __device__ __forceinline__ void eval_rows_fast(const PairDev& P, const EvalStage
     const int tile_step = P.n_eval_blocks;
     const float4* __restrict__ table = P.tgt_sorted;
     const int n_src = P.n_src;
+    // ASYNC: this thread's row of tile `t` (staged in stage slot `jt % kEvalStages`, once its barrier has completed) names its
+    // target points; fetch them into point buffer `jt & 1` without waiting.  Every thread only ever reads the points it
+    // fetched itself, so completion is the thread's own cp.async group, no block-wide barrier.
+    auto fetch_points = [&](int t, int jt) {
+        if (t < n_tiles) {
+            const int st = jt % kEvalStages;
+            while (!mbar_try_wait(S.bar0 + 8u * st, static_cast<uint32_t>(jt / kEvalStages) & 1u)) {
+            }
+            const unsigned char* nb = S.base + st * S.stage_bytes;
+            const int* n_pos = reinterpret_cast<const int*>(nb) + threadIdx.x;
+            int n_cnt = reinterpret_cast<const int*>(nb + static_cast<size_t>(kEvalFastThreads) * 4u * S.m)[threadIdx.x];
+            if (t * kEvalFastThreads + static_cast<int>(threadIdx.x) >= n_src) n_cnt = 0;
+            float4* dst = S.points + static_cast<size_t>(jt & 1) * kEvalFastThreads * S.m + threadIdx.x;
+            for (int k = 0; k < n_cnt; ++k) cp_async16(dst + k * kEvalFastThreads, table + n_pos[k * kEvalFastThreads]);
+        }
+        cp_async_commit();  // (an empty group when there is no such tile: the group count stays in step)
+    };
     int j = 0;
+    if (ASYNC) fetch_points(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < n_tiles; tile += tile_step, ++j) {
         const int stage = j % kEvalStages;
         const uint32_t parity = static_cast<uint32_t>(j / kEvalStages) & 1u;
-        while (!mbar_try_wait(S.bar0 + 8u * stage, parity)) {
+        if (ASYNC) {
+            fetch_points(tile + tile_step, j + 1);
+            cp_async_wait_1();  // everything but the group just committed has landed: this tile's points are here
+        } else {
+            while (!mbar_try_wait(S.bar0 + 8u * stage, parity)) {
+            }
         }
+        const float4* s_pts = ASYNC ? S.points + static_cast<size_t>(j & 1) * kEvalFastThreads * S.m + threadIdx.x : nullptr;
         const unsigned char* sb = S.base + stage * S.stage_bytes;
         const int* s_pos = reinterpret_cast<const int*>(sb) + threadIdx.x;
         int cnt = reinterpret_cast<const int*>(sb + static_cast<size_t>(kEvalFastThreads) * 4u * S.m)[threadIdx.x];
@@ -974,7 +1022,8 @@ __device__ __forceinline__ void eval_rows_fast(const PairDev& P, const EvalStage
             for (; k0 + kU <= cnt; k0 += kU) {
                 float4 y[kU];
 #pragma unroll
-                for (int u = 0; u < kU; ++u) y[u] = __ldg(table + s_pos[(k0 + u) * kEvalFastThreads]);
+                for (int u = 0; u < kU; ++u)
+                    y[u] = ASYNC ? s_pts[(k0 + u) * kEvalFastThreads] : __ldg(table + s_pos[(k0 + u) * kEvalFastThreads]);
 #pragma unroll
                 for (int u = 0; u < kU; ++u) rowf_add_t<WM, SAME>(&row, wc, y[u].x, y[u].y, y[u].z, he, dw);
             }
@@ -982,7 +1031,8 @@ __device__ __forceinline__ void eval_rows_fast(const PairDev& P, const EvalStage
                 float4 y[kU - 1];
 #pragma unroll
                 for (int u = 0; u < kU - 1; ++u)
-                    if (k0 + u < cnt) y[u] = __ldg(table + s_pos[(k0 + u) * kEvalFastThreads]);
+                    if (k0 + u < cnt)
+                        y[u] = ASYNC ? s_pts[(k0 + u) * kEvalFastThreads] : __ldg(table + s_pos[(k0 + u) * kEvalFastThreads]);
 #pragma unroll
                 for (int u = 0; u < kU - 1; ++u)
                     if (k0 + u < cnt) rowf_add_t<WM, SAME>(&row, wc, y[u].x, y[u].y, y[u].z, he, dw);
@@ -1028,7 +1078,9 @@ __global__ void __launch_bounds__(eval_threads(kFast), kFast ? kEvalFastBlocks :
         stg.m = P.m;
         stg.stage_bytes = eval_stage_bytes(stg.m);
         stg.base = s_dyn;
-        stg.bar0 = smem_u32(s_dyn + kEvalStages * stg.stage_bytes);
+        // the asynchronous variant needs the smem the host sized for the engine's max_neighbours: use it when this pair's m fits
+        stg.points = (eval_async(stg.m) && (use_cond & 8)) ? reinterpret_cast<float4*>(s_dyn + kEvalStages * stg.stage_bytes) : nullptr;
+        stg.bar0 = smem_u32(s_dyn + kEvalStages * stg.stage_bytes + (stg.points ? 2u * eval_points_bytes(stg.m) : 0u));
         if (threadIdx.x < 32) {
             if (threadIdx.x == 0) {
                 for (int k = 0; k < kEvalStages; ++k) mbar_init(stg.bar0 + 8u * k, 1);
@@ -1062,16 +1114,28 @@ __global__ void __launch_bounds__(eval_threads(kFast), kFast ? kEvalFastBlocks :
         for (int k = 0; k < 12; ++k)
             same = same && (reinterpret_cast<const double*>(&s_pe)[k] == reinterpret_cast<const double*>(&s_pw)[k]);
         // one instantiation of the row loop per (weight model, same pose): both are uniform over the launch
+        // ... and one per gather variant (uniform too: it follows from m)
+#if PPCR_EVAL_ASYNC
+#define PPCR_ROWS(WM, SAME)                                                     \
+    if (stg.points) eval_rows_fast<WM, SAME, true>(P, stg, pe, pw, wc, racc);   \
+    else eval_rows_fast<WM, SAME, false>(P, stg, pe, pw, wc, racc);             \
+    break;
+#else
+#define PPCR_ROWS(WM, SAME)                                      \
+    eval_rows_fast<WM, SAME, false>(P, stg, pe, pw, wc, racc);   \
+    break;
+#endif
         switch (weight_mode(wc) * 2 + (same ? 1 : 0)) {
-            case WM_T_H4 * 2: eval_rows_fast<WM_T_H4, false>(P, stg, pe, pw, wc, racc); break;
-            case WM_T_H4 * 2 + 1: eval_rows_fast<WM_T_H4, true>(P, stg, pe, pw, wc, racc); break;
-            case WM_T_INT * 2: eval_rows_fast<WM_T_INT, false>(P, stg, pe, pw, wc, racc); break;
-            case WM_T_INT * 2 + 1: eval_rows_fast<WM_T_INT, true>(P, stg, pe, pw, wc, racc); break;
-            case WM_T_REAL * 2: eval_rows_fast<WM_T_REAL, false>(P, stg, pe, pw, wc, racc); break;
-            case WM_T_REAL * 2 + 1: eval_rows_fast<WM_T_REAL, true>(P, stg, pe, pw, wc, racc); break;
-            case WM_GAUSS * 2: eval_rows_fast<WM_GAUSS, false>(P, stg, pe, pw, wc, racc); break;
-            default: eval_rows_fast<WM_GAUSS, true>(P, stg, pe, pw, wc, racc); break;
+            case WM_T_H4 * 2: PPCR_ROWS(WM_T_H4, false)
+            case WM_T_H4 * 2 + 1: PPCR_ROWS(WM_T_H4, true)
+            case WM_T_INT * 2: PPCR_ROWS(WM_T_INT, false)
+            case WM_T_INT * 2 + 1: PPCR_ROWS(WM_T_INT, true)
+            case WM_T_REAL * 2: PPCR_ROWS(WM_T_REAL, false)
+            case WM_T_REAL * 2 + 1: PPCR_ROWS(WM_T_REAL, true)
+            case WM_GAUSS * 2: PPCR_ROWS(WM_GAUSS, false)
+            default: PPCR_ROWS(WM_GAUSS, true)
         }
+#undef PPCR_ROWS
     } else {
         // float64 path: the 24 accumulators of a thread live in shared memory (one column per thread, conflict-free)
         double* acc = reinterpret_cast<double*>(s_dyn) + threadIdx.x;
