@@ -130,13 +130,21 @@ def _moved_search_rows(capi, src, tgt, n_iter, **kw):
     return cloud, idx, cnt, n_done
 
 
-@pytest.mark.parametrize("queued", [0, 1])
+# the queued kernel's three ways through a chunk: queues (default), every chunk walked with heaps (threshold 0), and
+# queues with a candidate list so short that most queries overflow it and fall back one by one
+QUEUED_MODES = {"off": {"PPCR_SEARCH_QUEUED": "0"}, "queues": {"PPCR_SEARCH_QUEUED": "1"},
+                "all_heavy": {"PPCR_SEARCH_QUEUED": "1", "PPCR_Q_HEAVY": "0"},
+                "overflow": {"PPCR_SEARCH_QUEUED": "1", "PPCR_Q_HEAVY": "1e9", "PPCR_Q_CAND": "12"}}
+
+
+@pytest.mark.parametrize("mode", sorted(QUEUED_MODES))
 @pytest.mark.parametrize("radius,m", [(0.5, 10), (1.5, 20), (3.0, 5)])
-def test_searches_after_a_cloud_move(capi, oracle, monkeypatch, queued, radius, m):
+def test_searches_after_a_cloud_move(capi, oracle, monkeypatch, mode, radius, m):
     """Every search of an align() but the first is fused with the cloud move and pruned by a bound taken from the previous
     association (the farthest previous neighbour of the moved query).  Its rows must still be exactly the m nearest
-    in-radius targets of the moved cloud -- for the default kernel and for the queued variant (PPCR_SEARCH_QUEUED=1)."""
-    monkeypatch.setenv("PPCR_SEARCH_QUEUED", str(queued))
+    in-radius targets of the moved cloud -- for k_search and for every path through the queued kernel."""
+    for k, v in QUEUED_MODES[mode].items():
+        monkeypatch.setenv(k, v)
     src, tgt, _ = synth.lidar_pair(23, 32, 700, yaw_deg=1.0, trans=(0.2, 0.05, 0.0))
     for n_iter in (2, 4):
         cloud, idx, cnt, n_done = _moved_search_rows(capi, src, tgt, n_iter, max_neighbours=m, radius=radius, dof=5.0)
