@@ -167,6 +167,15 @@ ppcr_status ppcr_iteration_solve(const float* src_xyzw, int64_t n_src, const flo
                                  const ppcr_params* params, const ppcr_options* options /* may be NULL */,
                                  double function_tolerance, double* out_pose, double* out_T, ppcr_iter_stats* stats);
 
+/* The reference's per-iteration diagnostics on the DEVICE (src/prob_point_cloud_registration.cc:110-122,132-135 with
+ * calculateMSE, include/.../utilities.hpp:16-26): replays the increments of outer iterations [first, first + count) of a
+ * finished ppcr_align on a full-resolution cloud -- x <- float(dT x) in place, like :110 -- and returns per iteration the mean
+ * Euclidean distance of the moved cloud to the ground truth (mse_gt, "MSE w.r.t. ground truth"; gt_xyzw may be NULL) and to
+ * its previous position (mse_prev, the report's mse_prev_iter).  cloud_xyzw (n points, host) comes back moved by all of them.
+ * One pass over the cloud per iteration, sums in a fixed order. */
+ppcr_status ppcr_replay_metrics(ppcr_handle* h, float* cloud_xyzw, const float* gt_xyzw, int64_t n, int32_t first, int32_t count,
+                                double* mse_gt, double* mse_prev);
+
 /* pcl::transformPointCloud(cloud, cloud, Affine3d) at :110-112: double math, float store, in place. */
 ppcr_status ppcr_transform(float* xyzw, int64_t n, const double* T4x4_rowmajor);
 

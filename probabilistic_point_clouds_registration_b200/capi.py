@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = [
     "ppcr_iteration_stats",
     "ppcr_filtered_source", "ppcr_filtered_target", "ppcr_association", "ppcr_get_stage_times", "ppcr_time_kernel",
     "ppcr_voxel_filter", "ppcr_radius_search", "ppcr_weights_normal_eq", "ppcr_iteration_solve", "ppcr_transform",
+    "ppcr_replay_metrics",
     "ppcr_align_batch", "ppcr_shard_export", "ppcr_shard_connect",
 ]
 
@@ -127,6 +128,7 @@ def lib():
         L.ppcr_weights_normal_eq.argtypes = [vp, i64, vp, i64, vp, vp, i32, f64, i32, vp, vp, i32, vp, vp]
         L.ppcr_iteration_solve.argtypes = [vp, i64, vp, i64, vp, vp, i32, C.POINTER(Params), C.POINTER(Options), f64, vp, vp, vp]
         L.ppcr_transform.argtypes = [vp, i64, vp]
+        L.ppcr_replay_metrics.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
         L.ppcr_align_batch.argtypes = [C.POINTER(PairDesc), i32, C.POINTER(Params), C.POINTER(Options), i32, vp, vp, vp]
         L.ppcr_shard_export.argtypes = [vp, i32, i32, vp]
         L.ppcr_shard_connect.argtypes = [vp, vp]
@@ -242,6 +244,19 @@ class Registration:
         cap = C.c_int32(n.value)
         _check(lib().ppcr_increment_history(self._h, hist.ctypes.data, C.byref(cap)))
         return hist[:n.value].reshape(n.value, 4, 4)
+
+    def replay_metrics(self, cloud, ground_truth=None, first=0, count=None):
+        """Per-iteration diagnostics of the reference on the device (registration.cc:110-122): moves `cloud` ([N,4] float32)
+        by the increments of outer iterations [first, first + count) and returns (moved cloud, mean distance to the ground
+        truth per iteration, mean distance to the previous position per iteration)."""
+        cloud = np.ascontiguousarray(cloud, dtype=np.float32).copy()
+        gt = None if ground_truth is None else np.ascontiguousarray(ground_truth, dtype=np.float32)
+        if count is None:
+            count = len(self.iteration_stats()) - first
+        mse_gt, mse_prev = np.zeros(max(count, 1)), np.zeros(max(count, 1))
+        _check(lib().ppcr_replay_metrics(self._h, cloud.ctypes.data, None if gt is None else gt.ctypes.data, len(cloud),
+                                         int(first), int(count), mse_gt.ctypes.data, mse_prev.ctypes.data))
+        return cloud, mse_gt[:count], mse_prev[:count]
 
     def transformation(self) -> np.ndarray:
         h = self.transformation_history()

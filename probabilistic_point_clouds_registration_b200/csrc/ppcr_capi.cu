@@ -1619,6 +1619,57 @@ ppcr_status ppcr_transform(float* xyzw, int64_t n, const double* T)
     });
 }
 
+ppcr_status ppcr_replay_metrics(ppcr_handle* h, float* cloud_xyzw, const float* gt_xyzw, int64_t n, int32_t first, int32_t count,
+                                double* mse_gt, double* mse_prev)
+{
+    if (!h || (n > 0 && !cloud_xyzw) || n < 0 || first < 0 || count < 0) return fail(PPCR_ERR_INVALID, "bad argument");
+    return guarded([&] {
+        Engine& E = h->eng;
+        use_engine(E);
+        int32_t n_hist = 0;
+        {
+            const PairState s = download_state(E, 0);
+            n_hist = s.current_iteration;
+        }
+        if (first + count > n_hist) throw StatusError{PPCR_ERR_INVALID, "replay range exceeds the outer iterations run"};
+        if (count == 0 || n == 0) return;
+        if (n > INT_MAX) throw StatusError{PPCR_ERR_INVALID, "cloud too large"};
+        std::vector<double> inc(static_cast<size_t>(n_hist) * 16);
+        int32_t cap = n_hist;
+        if (ppcr_increment_history(h, inc.data(), &cap) != PPCR_OK) throw StatusError{PPCR_ERR_CUDA, ppcr_last_error()};
+        use_engine(E);
+        cudaStream_t st = E.stream;
+        const int blocks = std::min(ceil_div(n, kReplayThreads), 8 * std::max(g_sm_count, 1));
+        DevBuf<float4> d_cloud, d_gt;
+        DevBuf<double> d_T, d_partial, d_out;
+        d_cloud.reserve(n);
+        if (gt_xyzw) d_gt.reserve(n);
+        d_T.reserve(static_cast<size_t>(count) * 16);
+        d_partial.reserve(static_cast<size_t>(blocks) * 2);
+        d_out.reserve(static_cast<size_t>(count) * 2);
+        CK(cudaMemcpyAsync(d_cloud.p, cloud_xyzw, static_cast<size_t>(n) * 16, cudaMemcpyHostToDevice, st));
+        if (gt_xyzw) CK(cudaMemcpyAsync(d_gt.p, gt_xyzw, static_cast<size_t>(n) * 16, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_T.p, inc.data() + static_cast<size_t>(first) * 16, static_cast<size_t>(count) * 16 * sizeof(double),
+                           cudaMemcpyHostToDevice, st));
+        for (int k = 0; k < count; ++k) {
+            k_replay_step<<<blocks, kReplayThreads, 0, st>>>(d_cloud.p, gt_xyzw ? d_gt.p : nullptr, static_cast<int>(n),
+                                                             d_T.p + static_cast<size_t>(k) * 16, d_partial.p);
+            k_replay_fold<<<1, 32, 0, st>>>(d_partial.p, blocks, static_cast<int>(n), d_out.p + 2 * k);
+        }
+        CK(cudaGetLastError());
+        note_launches(2 * count);
+        std::vector<double> out(static_cast<size_t>(count) * 2);
+        CK(cudaMemcpyAsync(out.data(), d_out.p, out.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(cloud_xyzw, d_cloud.p, static_cast<size_t>(n) * 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int k = 0; k < count; ++k) {
+            if (mse_gt) mse_gt[k] = gt_xyzw ? out[2 * k] : 0.0;
+            if (mse_prev) mse_prev[k] = out[2 * k + 1];
+        }
+        d_cloud.release(); d_gt.release(); d_T.release(); d_partial.release(); d_out.release();
+    });
+}
+
 // ---- batch ---------------------------------------------------------------------------------------------------
 
 ppcr_status ppcr_align_batch(const ppcr_pair* pairs, int32_t n_pairs, const ppcr_params* params,

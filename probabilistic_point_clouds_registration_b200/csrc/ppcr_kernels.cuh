@@ -1456,6 +1456,67 @@ __global__ void k_transform_plain(float4* __restrict__ pts, int n, const double*
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// replay of the per-iteration diagnostics (registration.cc:110-122, utilities.hpp:16-26)
+// ------------------------------------------------------------------------------------------------------------
+//
+// One outer iteration of the reference's bookkeeping on a full-resolution cloud: x <- float(dT x) in place, and in the same
+// pass the two "MSE" figures -- really mean Euclidean distances, evaluated in float32 like calculateMSE -- of the moved
+// cloud to the ground truth and to where it was before the move.  Per-block sums in double; k_replay_fold adds them in
+// block order, so the figures do not depend on scheduling.
+constexpr int kReplayThreads = 256;
+
+__device__ __forceinline__ float replay_distance(const float4& a, const float4& b)
+{
+    const float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
+    return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+}
+
+__global__ void __launch_bounds__(kReplayThreads) k_replay_step(float4* __restrict__ pts, const float4* __restrict__ gt, int n,
+                                                                const double* __restrict__ Tm, double* __restrict__ partial)
+{
+    __shared__ double T[12];
+    __shared__ double s_red[2][kReplayThreads / 32];
+    if (threadIdx.x < 12) T[threadIdx.x] = Tm[threadIdx.x];
+    __syncthreads();
+    double sum_gt = 0.0, sum_prev = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 old = pts[i];
+        float4 p = old;
+        const double x = p.x, y = p.y, z = p.z;
+        p.x = transform_row(T, x, y, z);
+        p.y = transform_row(T + 4, x, y, z);
+        p.z = transform_row(T + 8, x, y, z);
+        pts[i] = p;
+        sum_prev += static_cast<double>(replay_distance(p, old));
+        if (gt) sum_gt += static_cast<double>(replay_distance(p, gt[i]));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sum_gt += __shfl_xor_sync(kFull, sum_gt, o);
+        sum_prev += __shfl_xor_sync(kFull, sum_prev, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_red[0][threadIdx.x >> 5] = sum_gt;
+        s_red[1][threadIdx.x >> 5] = sum_prev;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double v = 0.0;
+        for (int w = 0; w < kReplayThreads / 32; ++w) v += s_red[threadIdx.x][w];
+        partial[2 * blockIdx.x + threadIdx.x] = v;
+    }
+}
+
+// out[0] = mean distance to the ground truth, out[1] = to the previous position
+__global__ void k_replay_fold(const double* __restrict__ partial, int n_blocks, int n, double* __restrict__ out)
+{
+    if (threadIdx.x < 2) {
+        double v = 0.0;
+        for (int b = 0; b < n_blocks; ++b) v += partial[2 * b + threadIdx.x];
+        out[threadIdx.x] = v / static_cast<double>(n);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // voxel filter (pcl::VoxelGrid default settings): key, sort by key (radix sort, host side), segmented mean
 // ------------------------------------------------------------------------------------------------------------
 

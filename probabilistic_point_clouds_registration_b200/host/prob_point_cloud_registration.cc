@@ -127,32 +127,40 @@ void ProbPointCloudRegistration::align()
     int32_t n = 0;
     check(ppcr_history(handle_, nullptr, &n), "ppcr_history");
     if (n > reported_iterations_) {
-        std::vector<double> poses(static_cast<std::size_t>(n) * 16), incs(static_cast<std::size_t>(n) * 16);
+        std::vector<double> poses(static_cast<std::size_t>(n) * 16);
         std::vector<ppcr_iter_stats> stats(static_cast<std::size_t>(n));
         int32_t cap = n;
         check(ppcr_history(handle_, poses.data(), &cap), "ppcr_history");
         cap = n;
-        check(ppcr_increment_history(handle_, incs.data(), &cap), "ppcr_increment_history");
-        cap = n;
         check(ppcr_iteration_stats(handle_, stats.data(), &cap), "ppcr_iteration_stats");
         const bool replay = ground_truth_ || parameters_.summary;
+        // The per-iteration diagnostics (:110-122): the full-resolution source copy follows the same increments as the
+        // registered cloud, and its mean distance to the ground truth / to its previous position is taken after each.  One
+        // device pass per iteration over the cloud (ppcr_replay_metrics) instead of a host loop per iteration.
+        std::vector<double> mse_gt(static_cast<std::size_t>(n)), mse_prev(static_cast<std::size_t>(n));
+        if (replay && !source_cloud_->empty()) {
+            const int first = reported_iterations_;
+            // (a ground truth of another size: let calculateMSE fail the way the reference's does, on .at())
+            if (ground_truth_ && ground_truth_cloud_->size() != source_cloud_->size()) (void)calculateMSE(source_cloud_, ground_truth_cloud_);
+            check(ppcr_replay_metrics(handle_, reinterpret_cast<float*>(source_cloud_->points.data()),
+                                      ground_truth_ ? reinterpret_cast<const float*>(ground_truth_cloud_->points.data()) : nullptr,
+                                      static_cast<int64_t>(source_cloud_->size()), first, n - first, mse_gt.data() + first,
+                                      mse_prev.data() + first),
+                  "ppcr_replay_metrics");
+            if (parameters_.summary) *prev_source_cloud_ = *source_cloud_;
+        }
         for (int it = reported_iterations_; it < n; ++it) {
             const Eigen::Affine3d current_trans = to_affine(&poses[16 * static_cast<std::size_t>(it)]);
             transformation_history_.push_back(current_trans);
             output_stream_ << "Outer iteration " << it << ": " << stats[it].n_correspondences << " correspondences, "
                            << stats[it].lm_iterations << " LM iterations (" << stats[it].num_successful_steps
                            << " successful), cost " << stats[it].initial_cost << " -> " << stats[it].final_cost << "\n";
-            if (replay) {
-                // the full-resolution source copy follows the same increments as the registered cloud (:110)
-                pcl::transformPointCloud(*source_cloud_, *source_cloud_, to_affine(&incs[16 * static_cast<std::size_t>(it)]));
-            }
             if (ground_truth_) {
-                mse_ground_truth_ = calculateMSE(source_cloud_, ground_truth_cloud_);
+                mse_ground_truth_ = mse_gt[static_cast<std::size_t>(it)];
                 output_stream_ << "MSE w.r.t. ground truth: " << mse_ground_truth_ << "\n";
             }
             if (parameters_.summary) {
-                mse_prev_it_ = calculateMSE(source_cloud_, prev_source_cloud_);
-                *prev_source_cloud_ = *source_cloud_;
+                mse_prev_it_ = mse_prev[static_cast<std::size_t>(it)];
                 const Eigen::Vector3d rpy = current_trans.rotation().eulerAngles(0, 1, 2);
                 report_ << it << ", " << stats[it].num_successful_steps << ", " << stats[it].initial_cost << ", "
                         << stats[it].final_cost << ", " << current_trans.translation().x() << ", "

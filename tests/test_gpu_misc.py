@@ -56,3 +56,36 @@ def test_target_is_filtered_and_source_copy_is_moved(capi):
         reg.align()
         after = reg.filtered_source()
     assert len(before) == len(src) and not np.array_equal(before, after)
+
+
+def test_replay_metrics_match_a_host_replay(capi):
+    """ppcr_replay_metrics = the reference's per-iteration bookkeeping (registration.cc:110-122 with calculateMSE,
+    utilities.hpp:16-26) on the device: the cloud moved by every increment like pcl::transformPointCloud (bit-exact), and
+    the two mean distances after each move (float32 distances, summed in double)."""
+    src, tgt, T = synth.config1_plane_sphere(seed=5, n_plane=1500, n_sphere=1500)
+    gt = synth.apply_T_like_pcl(src, T)
+    with capi.Registration(src, tgt, capi.make_params(max_neighbours=10, radius=1.0)) as reg:
+        reg.align()
+        inc = reg.increment_history()
+        moved, mse_gt, mse_prev = reg.replay_metrics(src, gt)
+        half = len(inc) // 2
+        part1, g1, p1 = reg.replay_metrics(src, gt, first=0, count=half)
+        part2, g2, p2 = reg.replay_metrics(part1, None, first=half)
+    assert len(inc) >= 3 and len(mse_gt) == len(inc)
+    cur = src.copy()
+    for k, Tk in enumerate(inc):
+        new = synth.apply_T_like_pcl(cur, Tk)
+
+        def mean_dist(a, b):
+            d = a[:, :3] - b[:, :3]
+            return float(np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]).astype(np.float64).mean())
+
+        np.testing.assert_allclose(mse_gt[k], mean_dist(new, gt), rtol=1e-12)
+        np.testing.assert_allclose(mse_prev[k], mean_dist(new, cur), rtol=1e-12)
+        cur = new
+    assert np.array_equal(moved[:, :3], cur[:, :3])
+    # a replay in two parts continues where the first stopped; without a ground truth that column is zero
+    assert np.array_equal(part2[:, :3], moved[:, :3])
+    assert np.array_equal(np.concatenate([g1, g2]), np.concatenate([mse_gt[:half], np.zeros(len(inc) - half)]))
+    assert np.array_equal(np.concatenate([p1, p2]), mse_prev)
+    assert mse_gt[-1] < mse_gt[0]
