@@ -681,55 +681,74 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
 // come within the bound; testing their points is somebody else's work.  Same start-node descent, same box lower bounds
 // and the same pruning threshold as tree_search: a leaf tree_search would scan under this bound is always emitted.
 // `stack` must hold kTreeStack ints.  Returns false when emit refused a leaf (queue full): the caller falls back.
+// The deepest node whose subtree holds every target within bound_d2 of q (the start of the walk; see tree_search).
+// Returns its index and whether it is a leaf; -1 when no target can lie within the bound.
+PPCR_HD int tree_start_node(const TreeGeom& g, const TreeNode* __restrict__ nodes, float qx, float qy, float qz, float bound_d2,
+                            bool* is_leaf)
+{
+    TreeNode n = load_node(nodes);
+    if (n.end <= n.begin) return -1;
+    int at = 0;
+    const float rho = sqrtf(bound_d2) * 1.00001f + 2.0f * g.slack;
+    const float lox = qx - rho, hix = qx + rho, loy = qy - rho, hiy = qy + rho, loz = qz - rho, hiz = qz + rho;
+    bool leaf = n.child < 0;
+    while (!leaf) {
+        int oct;
+        if (lox >= n.cx) oct = 1;
+        else if (hix < n.cx) oct = 0;
+        else break;
+        if (loy >= n.cy) oct |= 2;
+        else if (!(hiy < n.cy)) break;
+        if (loz >= n.cz) oct |= 4;
+        else if (!(hiz < n.cz)) break;
+        if (!((n.mask >> oct) & 1)) return -1;  // the only octant the ball touches is empty
+        at = n.child + oct;
+        leaf = ((n.mask >> (16 + oct)) & 1) != 0;
+        if (!leaf) n = load_node(nodes + at);
+    }
+    *is_leaf = leaf;
+    return at;
+}
+
+// Opens inner node `node` for query q: every non-empty child whose box comes within the pruning threshold is handed to
+// leaf(child) or inner(child).  Same lower bounds as tree_search.
+template <class Leaf, class Inner>
+PPCR_HD void tree_open_node(const TreeGeom& g, const TreeNode* __restrict__ nodes, int node, float qx, float qy, float qz, float thr,
+                            Leaf& leaf, Inner& inner)
+{
+    const TreeNode n = load_node(nodes + node);
+    PPCR_STAT(opens, 1);
+    const float ch = n.half * 0.5f;
+    const float hi = ch + g.slack;
+    const float gx[2] = {axis_gap2(qx, n.cx - ch, hi), axis_gap2(qx, n.cx + ch, hi)};
+    const float gy[2] = {axis_gap2(qy, n.cy - ch, hi), axis_gap2(qy, n.cy + ch, hi)};
+    const float gz[2] = {axis_gap2(qz, n.cz - ch, hi), axis_gap2(qz, n.cz + ch, hi)};
+    const int mask = n.mask;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float lb = gx[c & 1] + gy[(c >> 1) & 1] + gz[(c >> 2) & 1];
+        if (((mask >> c) & 1) && !(lb > thr)) {
+            if ((mask >> (16 + c)) & 1) leaf(n.child + c);
+            else inner(n.child + c);
+        }
+    }
+}
+
 template <class Emit>
 PPCR_HD bool tree_collect_leaves(const TreeGeom& g, const TreeNode* __restrict__ nodes, float qx, float qy, float qz,
                                  float bound_d2, Emit& emit, int* stack)
 {
     const float thr = prune_threshold(bound_d2);
+    bool is_leaf = false;
+    const int at = tree_start_node(g, nodes, qx, qy, qz, bound_d2, &is_leaf);
+    if (at < 0) return true;
+    if (is_leaf) return emit(at);
     int sp = 0;
-    {
-        TreeNode n = load_node(nodes);
-        if (n.end <= n.begin) return true;
-        int at = 0;
-        const float rho = sqrtf(bound_d2) * 1.00001f + 2.0f * g.slack;
-        const float lox = qx - rho, hix = qx + rho, loy = qy - rho, hiy = qy + rho, loz = qz - rho, hiz = qz + rho;
-        bool leaf = n.child < 0;
-        while (!leaf) {
-            int oct;
-            if (lox >= n.cx) oct = 1;
-            else if (hix < n.cx) oct = 0;
-            else break;
-            if (loy >= n.cy) oct |= 2;
-            else if (!(hiy < n.cy)) break;
-            if (loz >= n.cz) oct |= 4;
-            else if (!(hiz < n.cz)) break;
-            if (!((n.mask >> oct) & 1)) return true;  // the only octant the ball touches is empty
-            at = n.child + oct;
-            leaf = ((n.mask >> (16 + oct)) & 1) != 0;
-            if (!leaf) n = load_node(nodes + at);
-        }
-        if (leaf) return emit(at);
-        stack[sp++] = at;
-    }
+    stack[sp++] = at;
     bool ok = true;
-    while (sp > 0) {
-        const TreeNode n = load_node(nodes + stack[--sp]);
-        PPCR_STAT(opens, 1);
-        const float ch = n.half * 0.5f;
-        const float hi = ch + g.slack;
-        const float gx[2] = {axis_gap2(qx, n.cx - ch, hi), axis_gap2(qx, n.cx + ch, hi)};
-        const float gy[2] = {axis_gap2(qy, n.cy - ch, hi), axis_gap2(qy, n.cy + ch, hi)};
-        const float gz[2] = {axis_gap2(qz, n.cz - ch, hi), axis_gap2(qz, n.cz + ch, hi)};
-        const int mask = n.mask;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float lb = gx[c & 1] + gy[(c >> 1) & 1] + gz[(c >> 2) & 1];
-            if (((mask >> c) & 1) && !(lb > thr)) {
-                if ((mask >> (16 + c)) & 1) ok = emit(n.child + c) && ok;
-                else stack[sp++] = n.child + c;
-            }
-        }
-    }
+    auto leaf = [&](int child) { ok = emit(child) && ok; };
+    auto inner = [&](int child) { stack[sp++] = child; };
+    while (sp > 0) tree_open_node(g, nodes, stack[--sp], qx, qy, qz, thr, leaf, inner);
     return ok;
 }
 
