@@ -507,10 +507,11 @@ __global__ void PPCR_SEARCH_BOUNDS k_search(const PairDev* __restrict__ pairs)
 //   A  (thread per query)   move the query, bound from the previous neighbours, walk the octree with that fixed bound and
 //                           push every leaf within it as a task (query slot, node) on the block's task queue
 //   B  (thread per task)    test the leaf's points against its query; survivors' positions go to the query's candidate list
-//   C  (thread per query)   the m best of the candidates: build a heap of the first m, stream the rest through its root
-// A query whose tasks or candidates overflow the queues (no useful bound: a row that had fewer than m neighbours in a dense
-// region) is searched by tree_search with the heap, as in k_search.  Results are bit-identical to k_search's: same distance
-// arithmetic, same strict radius test, same (distance, index) order.
+//   C  (thread per query)   the m best of the candidates: build a heap of the first m, stream the rest through its root,
+//                           heap-sort them into (distance, index) order (a row must not depend on who pushed first)
+// A query whose tasks or candidates overflow the queues is searched by tree_search with the heap, as in k_search; a chunk in
+// which most queries expect to (the cloud moved by more than the neighbour spacing) is walked with heaps as a whole.  The
+// neighbour sets are identical to k_search's: same distance arithmetic, same strict radius test, same (distance, index) order.
 constexpr int kQTaskPerQuery = 64;               // leaves one query may queue; beyond that it is searched by tree_search
 constexpr int kQTaskCap = 8192;                  // leaf tasks per block of 128 queries (64 per query on average)
 // candidate positions per query.  128 for max_neighbours = 20 was tried: one 120k-point pair 6.2 -> 6.0 ms, but a batch of them
