@@ -535,12 +535,15 @@ struct QEmit {  // phase A -> task queue
     int* n_tasks;
     uint32_t slot;
     int mine;
-    __device__ __forceinline__ bool operator()(int node)
+    // the leaf children `first + c`, c a set bit of mask, of one opened node: one reservation for all of them
+    __device__ __forceinline__ bool operator()(int first, int mask)
     {
-        if (++mine > kQTaskPerQuery) return false;
-        const int t = atomicAdd(n_tasks, 1);
-        if (t >= kQTaskCap) return false;
-        __stcg(tasks + t, (slot << kQNodeBits) | static_cast<uint32_t>(node));
+        const int n = __popc(mask);
+        mine += n;
+        if (mine > kQTaskPerQuery) return false;
+        int t = atomicAdd(n_tasks, n);
+        if (t + n > kQTaskCap) return false;
+        for (; mask; mask &= mask - 1) __stcg(tasks + t++, (slot << kQNodeBits) | static_cast<uint32_t>(first + lowest_bit(mask)));
         return true;
     }
 };

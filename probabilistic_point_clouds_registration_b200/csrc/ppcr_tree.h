@@ -676,11 +676,6 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
 
 // ---- traversal with a fixed bound: which leaves can hold a target within bound_d2 of q ------------------------------
 //
-// First phase of the queued search kernel (k_search_q): the pruning bound is known up front (the search kernel's warm
-// bound) and does not change during the walk, so the walk only has to NAME the leaves -- emit(node index) -- whose boxes
-// come within the bound; testing their points is somebody else's work.  Same start-node descent, same box lower bounds
-// and the same pruning threshold as tree_search: a leaf tree_search would scan under this bound is always emitted.
-// `stack` must hold kTreeStack ints.  Returns false when emit refused a leaf (queue full): the caller falls back.
 // The deepest node whose subtree holds every target within bound_d2 of q (the start of the walk; see tree_search).
 // Returns its index and whether it is a leaf; -1 when no target can lie within the bound.
 PPCR_HD int tree_start_node(const TreeGeom& g, const TreeNode* __restrict__ nodes, float qx, float qy, float qz, float bound_d2,
@@ -710,11 +705,12 @@ PPCR_HD int tree_start_node(const TreeGeom& g, const TreeNode* __restrict__ node
     return at;
 }
 
-// Opens inner node `node` for query q: every non-empty child whose box comes within the pruning threshold is handed to
-// leaf(child) or inner(child).  Same lower bounds as tree_search.
-template <class Leaf, class Inner>
+// Opens inner node `node` for query q: the non-empty children whose boxes come within the pruning threshold are handed on --
+// the inner ones one by one, inner(child), the leaves together, leaves(first child, bit mask of the leaf children), so that a
+// consumer that queues them needs one reservation per node.  Same lower bounds as tree_search.
+template <class Leaves, class Inner>
 PPCR_HD void tree_open_node(const TreeGeom& g, const TreeNode* __restrict__ nodes, int node, float qx, float qy, float qz, float thr,
-                            Leaf& leaf, Inner& inner)
+                            Leaves& leaves, Inner& inner)
 {
     const TreeNode n = load_node(nodes + node);
     PPCR_STAT(opens, 1);
@@ -724,16 +720,24 @@ PPCR_HD void tree_open_node(const TreeGeom& g, const TreeNode* __restrict__ node
     const float gy[2] = {axis_gap2(qy, n.cy - ch, hi), axis_gap2(qy, n.cy + ch, hi)};
     const float gz[2] = {axis_gap2(qz, n.cz - ch, hi), axis_gap2(qz, n.cz + ch, hi)};
     const int mask = n.mask;
+    int leaf_mask = 0;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const float lb = gx[c & 1] + gy[(c >> 1) & 1] + gz[(c >> 2) & 1];
         if (((mask >> c) & 1) && !(lb > thr)) {
-            if ((mask >> (16 + c)) & 1) leaf(n.child + c);
+            if ((mask >> (16 + c)) & 1) leaf_mask |= 1 << c;
             else inner(n.child + c);
         }
     }
+    if (leaf_mask) leaves(n.child, leaf_mask);
 }
 
+// First phase of the queued search kernel (k_search_q): the pruning bound is known up front (the search kernel's warm
+// bound) and does not change during the walk, so the walk only has to NAME the leaves whose boxes -- emit(first, mask):
+// the nodes first + c for every set bit c of mask, the leaf children of one opened node together --
+// come within the bound; testing their points is somebody else's work.  Same start-node descent, same box lower bounds
+// and the same pruning threshold as tree_search: a leaf tree_search would scan under this bound is always emitted.
+// `stack` must hold kTreeStack ints.  Returns false when emit refused a leaf (queue full): the caller falls back.
 template <class Emit>
 PPCR_HD bool tree_collect_leaves(const TreeGeom& g, const TreeNode* __restrict__ nodes, float qx, float qy, float qz,
                                  float bound_d2, Emit& emit, int* stack)
@@ -742,13 +746,13 @@ PPCR_HD bool tree_collect_leaves(const TreeGeom& g, const TreeNode* __restrict__
     bool is_leaf = false;
     const int at = tree_start_node(g, nodes, qx, qy, qz, bound_d2, &is_leaf);
     if (at < 0) return true;
-    if (is_leaf) return emit(at);
+    if (is_leaf) return emit(at, 1);
     int sp = 0;
     stack[sp++] = at;
     bool ok = true;
-    auto leaf = [&](int child) { ok = emit(child) && ok; };
+    auto leaves = [&](int first, int mask) { ok = emit(first, mask) && ok; };
     auto inner = [&](int child) { stack[sp++] = child; };
-    while (sp > 0) tree_open_node(g, nodes, stack[--sp], qx, qy, qz, thr, leaf, inner);
+    while (sp > 0) tree_open_node(g, nodes, stack[--sp], qx, qy, qz, thr, leaves, inner);
     return ok;
 }
 

@@ -320,7 +320,11 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
             std::vector<int> leaves;
             std::vector<uint32_t> cand;
             const float b0 = bound0 < r2f ? bound0 : r2f;
-            auto emit = [&](int node) { leaves.push_back(node); return true; };
+            auto emit = [&](int first, int mask) {
+                for (int c = 0; c < 8; ++c)
+                    if ((mask >> c) & 1) leaves.push_back(first + c);
+                return true;
+            };
             tree_collect_leaves(g, nodes.data(), q[0], q[1], q[2], b0, emit, stack);
             auto push = [&](int j0, uint32_t pass) {
                 for (; pass; pass &= pass - 1) cand.push_back(static_cast<uint32_t>(j0 + lowest_bit(pass)));
