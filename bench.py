@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c1|c5] [--impl ours|reference]
 
 A "step" is one registration of one synthetic scan pair: ProbPointCloudRegistration constructor + align() to the
-reference's own stopping rule (src/prob_point_cloud_registration.cc:15-158) -- grid build, then per outer
+reference's own stopping rule (src/prob_point_cloud_registration.cc:15-158) -- octree build, then per outer
 iteration radius search -> weights + normal equations per LM iteration -> pose update -> cloud move -> convergence
 test, all on the device.  The default workload is BASELINE.json configs[2], the 1M-point pair the metric is quoted
 on ("c3": -m 10 -r 0.5 -d 5).  With N > 1 every rank registers its own pair of the same shape (independent scan
@@ -15,8 +15,10 @@ pairs, data-parallel, no data-path collective): weak scaling.
           outside the timed intervals.
   e2e     the same metric through the public C ABI with HOST buffers (pinned): H2D of both clouds, the whole
           registration and the D2H of the pose history / statistics inside the timed region (wall clock).
-  roofline  the dominant kernel re-run in isolation with CUDA events (ppcr_time_kernel, L2 flushed between
-          launches): algorithmic bytes / average launch time vs MEASURED_PEAKS.json's HBM copy number.
+  roofline  the dominant kernel's algorithmic bytes / its average launch duration measured LIVE inside one
+          registration (host-stepped driver, every launch bracketed by CUDA events on the handle's stream) vs
+          MEASURED_PEAKS.json's HBM copy number; isolated re-runs (ppcr_time_kernel, L2 flushed between launches) of
+          the first search, a search after a cloud move and the evaluation are reported beside it.
   cpu_baseline  the CPU oracle (a restatement of the reference; the reference itself needs PCL/Ceres which are not
           installable here) on a bounded sample of the same workload, all host cores.
 
