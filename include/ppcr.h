@@ -179,6 +179,27 @@ ppcr_status ppcr_replay_metrics(ppcr_handle* h, float* cloud_xyzw, const float* 
 /* pcl::transformPointCloud(cloud, cloud, Affine3d) at :110-112: double math, float store, in place. */
 ppcr_status ppcr_transform(float* xyzw, int64_t n, const double* T4x4_rowmajor);
 
+/* The closest-point metric helpers of include/prob_point_cloud_registration/utilities.hpp:28-234 in one call.  Each of them
+ * builds a kd-tree on cloud2, takes nearestKSearch(k = 1) of every cloud1 point -- a SQUARED distance, float -- and reduces
+ * that vector; here: one octree build, one 1-NN search, one radix sort, one reduction pass.  The reference's "median" is its
+ * own index rule on the sorted vector (element (n+1)/2 for odd n, mean of n/2 and n/2+1 for even n; NaN where that reads out
+ * of bounds, which is undefined behaviour in the reference); the robust variants keep the entries within
+ * [median / f, median * f] (f = 3, or `factor`) and return DBL_MAX when fewer than 10 remain. */
+typedef struct ppcr_closest_metrics {
+    double average_closest_distance;           /* averageClosestDistance          :28-46  */
+    double sum_squared_error;                  /* sumSquaredError                 :48-65  */
+    double robust_sum_squared_error;           /* robustSumSquaredError           :67-101 */
+    double robust_sum_squared_error_factor;    /* robustSumSquaredError(.., factor) :103-138 */
+    double robust_averaged_sum_squared_error;  /* robustAveragedSumSquaredError   :140-175 */
+    double median_closest_distance;            /* medianClosestDistance           :177-199 */
+    double robust_median_closest_distance;     /* robustMedianClosestDistance     :201-234 */
+    int64_t n_filtered, n_filtered_factor;     /* entries inside the two windows */
+} ppcr_closest_metrics;
+/* cloud1 / cloud2: host pointers unless options->input_on_device; options may be NULL.  out_d2 (may be NULL, host): the n1
+ * squared distances in cloud1's order. */
+ppcr_status ppcr_closest_point_metrics(const float* cloud1_xyzw, int64_t n1, const float* cloud2_xyzw, int64_t n2,
+                                       double factor, const ppcr_options* options, ppcr_closest_metrics* out, float* out_d2);
+
 /* ---- batch of independent pairs (new surface; no reference counterpart) -------------------------------- */
 
 typedef struct ppcr_pair {

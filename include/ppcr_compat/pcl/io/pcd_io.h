@@ -5,7 +5,9 @@
 //   savePCDFile : ASCII by default, like pcl::io::savePCDFile(name, cloud, binary_mode = false).
 #ifndef PPCR_COMPAT_PCL_PCD_IO_H
 #define PPCR_COMPAT_PCL_PCD_IO_H
+#include <cmath>
 #include <cstdint>
+#include <exception>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -122,9 +124,18 @@ int loadPCDFile(const std::string& file_name, PointCloud<PointT>& cloud)
         }
     }
     if (fields.empty() || data_kind.empty()) return -1;
-    if (!have_points) n_points = width * height;
+    if (!have_points) {
+        if (height != 0 && width > std::numeric_limits<std::size_t>::max() / height) return -1;
+        n_points = width * height;
+    }
+    // Header values come from the file: nothing below may index or allocate on their say-so alone.
+    constexpr std::size_t kMaxRecord = std::size_t(1) << 20, kMaxPoints = std::size_t(1) << 31;
+    if (n_points > kMaxPoints) return -1;
     int ix = -1, iy = -1, iz = -1, offset = 0;
     for (std::size_t k = 0; k < fields.size(); ++k) {
+        if (fields[k].size != 1 && fields[k].size != 2 && fields[k].size != 4 && fields[k].size != 8) return -1;
+        if (fields[k].count < 1 || static_cast<std::size_t>(fields[k].count) > kMaxRecord) return -1;
+        if (static_cast<std::size_t>(offset) + static_cast<std::size_t>(fields[k].size) * fields[k].count > kMaxRecord) return -1;
         fields[k].offset = offset;
         offset += fields[k].size * fields[k].count;
         if (fields[k].name == "x") ix = static_cast<int>(k);
@@ -133,10 +144,34 @@ int loadPCDFile(const std::string& file_name, PointCloud<PointT>& cloud)
     }
     if (ix < 0 || iy < 0 || iz < 0) return -1;
     const std::size_t record = static_cast<std::size_t>(offset);
-    cloud.points.assign(n_points, PointT());
+    if (data_kind != "ascii") {
+        // a binary body holds record * n_points bytes (at most that, compressed): a POINTS value the file cannot back is rejected
+        // before anything is allocated for it
+        const std::streampos body = f.tellg();
+        f.seekg(0, std::ios::end);
+        const std::streampos end = f.tellg();
+        f.seekg(body);
+        if (body < 0 || end < body) return -1;
+        const std::size_t left = static_cast<std::size_t>(end - body);
+        if (data_kind == "binary" && (record == 0 || n_points > left / record)) return -1;
+        if (data_kind == "binary_compressed" && left < 8) return -1;
+    }
+    try {
+        cloud.points.assign(n_points, PointT());
+    } catch (const std::exception&) {
+        return -1;
+    }
     cloud.width = static_cast<std::uint32_t>(width ? width : n_points);
     cloud.height = static_cast<std::uint32_t>(height);
     cloud.is_dense = true;
+    // like PCL's reader: a cloud holding a non-finite coordinate is flagged, so that filters and the search skip those points
+    auto flag_density = [&cloud]() {
+        for (const auto& p : cloud.points)
+            if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) {
+                cloud.is_dense = false;
+                return;
+            }
+    };
     if (data_kind == "ascii") {
         for (std::size_t i = 0; i < n_points; ++i) {
             if (!std::getline(f, line)) return -1;
@@ -162,9 +197,15 @@ int loadPCDFile(const std::string& file_name, PointCloud<PointT>& cloud)
                     if (static_cast<int>(k) == iz) cloud.points[i].z = v;
                 }
         }
+        flag_density();
         return 0;
     }
-    std::vector<unsigned char> raw(record * n_points);
+    std::vector<unsigned char> raw;
+    try {
+        raw.resize(record * n_points);
+    } catch (const std::exception&) {
+        return -1;
+    }
     if (data_kind == "binary") {
         f.read(reinterpret_cast<char*>(raw.data()), static_cast<std::streamsize>(raw.size()));
         if (static_cast<std::size_t>(f.gcount()) != raw.size()) return -1;
@@ -174,6 +215,7 @@ int loadPCDFile(const std::string& file_name, PointCloud<PointT>& cloud)
             cloud.points[i].y = detail::read_as_float(p + fields[iy].offset, fields[iy]);
             cloud.points[i].z = detail::read_as_float(p + fields[iz].offset, fields[iz]);
         }
+        flag_density();
         return 0;
     }
     if (data_kind == "binary_compressed") {
@@ -181,6 +223,13 @@ int loadPCDFile(const std::string& file_name, PointCloud<PointT>& cloud)
         f.read(reinterpret_cast<char*>(&comp), 4);
         f.read(reinterpret_cast<char*>(&uncomp), 4);
         if (!f || uncomp != raw.size()) return -1;
+        {
+            const std::streampos at = f.tellg();
+            f.seekg(0, std::ios::end);
+            const std::streampos end = f.tellg();
+            f.seekg(at);
+            if (at < 0 || end < at || static_cast<std::size_t>(end - at) < comp) return -1;
+        }
         std::vector<unsigned char> packed(comp);
         f.read(reinterpret_cast<char*>(packed.data()), comp);
         if (static_cast<std::size_t>(f.gcount()) != comp) return -1;
@@ -199,6 +248,7 @@ int loadPCDFile(const std::string& file_name, PointCloud<PointT>& cloud)
             }
             base += fsz * n_points;
         }
+        flag_density();
         return 0;
     }
     return -1;

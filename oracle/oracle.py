@@ -52,7 +52,7 @@ class SolveSummary(C.Structure):
         ("num_iterations", C.c_int32),
         ("num_successful_steps", C.c_int32),
         ("termination", C.c_int32),
-        ("pad", C.c_int32),
+        ("num_nonmonotonic_steps", C.c_int32),
     ]
 
 
@@ -80,8 +80,7 @@ def build(force: bool = False) -> str:
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
-            build()
+        build()  # (re)compiles only when the library is missing or older than its sources
         L = C.CDLL(_LIB_PATH)
         fp = C.POINTER(C.c_float)
         dp = C.POINTER(C.c_double)
@@ -107,6 +106,12 @@ def lib():
         L.oracle_align.argtypes = [fp, C.c_int64, fp, C.c_int64, C.POINTER(OracleParams), C.POINTER(SolverOptions),
                                    C.c_int32, dp, C.POINTER(IterStats), C.c_int32, fp, lp, lp]
         L.oracle_max_threads.restype = C.c_int32
+        L.oracle_closest_metrics.restype = C.c_int32
+        L.oracle_closest_metrics.argtypes = [fp, C.c_int64, fp, C.c_int64, C.c_double, dp, fp]
+        L.oracle_normal_eq.restype = None
+        L.oracle_normal_eq.argtypes = [fp, fp, C.c_int64, lp, ip, C.c_double, dp, dp, dp]
+        L.oracle_nonmonotonic_steps.restype = C.c_int64
+        L.oracle_nonmonotonic_steps.argtypes = [C.c_int32]
         _lib = L
     return _lib
 
@@ -152,6 +157,11 @@ def make_options(function_tolerance=1e-5, max_num_iterations=2**31 - 1, inner_ki
 
 def max_threads() -> int:
     return int(lib().oracle_max_threads())
+
+
+def nonmonotonic_steps(reset=False) -> int:
+    """Accepted non-monotonic LM steps over every solve since the last reset."""
+    return int(lib().oracle_nonmonotonic_steps(int(bool(reset))))
 
 
 def radius_search(src, tgt, radius, max_nn, use_grid=False, num_threads=0, cap=None):
@@ -233,6 +243,38 @@ def voxel_grid(cloud, leaf):
     if n < 0:
         return out, True
     return out[:n].copy(), False
+
+
+CLOSEST_METRIC_NAMES = ("average_closest_distance", "sum_squared_error", "robust_sum_squared_error",
+                        "robust_sum_squared_error_factor", "robust_averaged_sum_squared_error", "median_closest_distance",
+                        "robust_median_closest_distance", "n_filtered", "n_filtered_factor")
+
+
+def closest_metrics(cloud1, cloud2, factor=3.0):
+    """utilities.hpp:28-234 in one call: dict of the seven helpers' return values (+ the two window counts) and the
+    per-point squared 1-NN distances."""
+    a, b = _f32(cloud1), _f32(cloud2)
+    out = np.zeros(9)
+    d2 = np.zeros(len(a), dtype=np.float32)
+    rc = lib().oracle_closest_metrics(_ptr(a, C.c_float), len(a), _ptr(b, C.c_float), len(b), float(factor),
+                                      _ptr(out, C.c_double), _ptr(d2, C.c_float))
+    if rc != 0:
+        raise ValueError("empty cloud")
+    return dict(zip(CLOSEST_METRIC_NAMES, out.tolist())), d2
+
+
+def normal_eq(src, tgt, row_ptr, col_idx, dof, pose_w, pose_e):
+    """J^T W J (upper triangle, 28), J^T W r (7), cost of one evaluation at pose_e with weights refreshed at pose_w."""
+    src, tgt = _f32(src), _f32(tgt)
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    col_idx = np.ascontiguousarray(col_idx, dtype=np.int32)
+    xw = np.ascontiguousarray(pose_w, dtype=np.float64)
+    xe = np.ascontiguousarray(pose_e, dtype=np.float64)
+    out = np.zeros(36)
+    lib().oracle_normal_eq(_ptr(src, C.c_float), _ptr(tgt, C.c_float), len(row_ptr) - 1, _ptr(row_ptr, C.c_int64),
+                           _ptr(col_idx, C.c_int32), float(dof), _ptr(xw, C.c_double), _ptr(xe, C.c_double),
+                           _ptr(out, C.c_double))
+    return out
 
 
 def calculate_mse(a, b):

@@ -15,6 +15,7 @@
 #include "ppcr_oracle.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -67,33 +68,38 @@ inline bool di_less(const DistIndex& a, const DistIndex& b)
     return a.d2 < b.d2 || (a.d2 == b.d2 && a.idx < b.idx);
 }
 
-// Bounded result set with FLANN KNNRadiusResultSet semantics: strict d2 < worst, where worst starts at
-// the squared radius and becomes the largest kept d2 once the set is full.  Candidates are offered in
-// ascending index order per cell and the set is kept as a max-heap on (d2, idx); the result therefore
-// equals "the m smallest by (d2, idx)" except for exact float ties at the m-th boundary.
+// Bounded result set: the members are the points with d2 < r2 (strict, FLANN), and when more than `capacity` qualify the
+// capacity smallest under the lexicographic order (d2, index) -- the tie rule BASELINE.json's north_star states
+// ("distance, then index tiebreak"), which makes the result a pure function of the two clouds.  FLANN's own
+// KNNRadiusResultSet drops a candidate whose d2 EQUALS the current worst whatever its index, so on an exact float tie at
+// the m-th boundary its answer depends on the order its tree happens to visit the points in; there is no reference-held
+// vector for that case (radius search unpinned), and an order-dependent rule cannot be restated without the
+// tree.  Both the brute-force and the grid path below, and the CUDA kernels, use the pure rule.
 struct ResultSet {
     std::vector<DistIndex> heap;
     size_t capacity;
-    float worst;
-    void reset(size_t cap, float r2)
+    float r2;
+    void reset(size_t cap, float r2f)
     {
         heap.clear();
         capacity = cap;
-        worst = r2;
+        r2 = r2f;
     }
     inline void offer(float d2, int32_t idx)
     {
-        if (!(d2 < worst)) return;
+        if (!(d2 < r2)) return;
+        const DistIndex cand{d2, idx};
         if (heap.size() == capacity) {
-            // equal-distance lower-index candidate is rejected by the test above, like FLANN
+            if (!di_less(cand, heap.front())) return;
             std::pop_heap(heap.begin(), heap.end(), di_less);
-            heap.back() = {d2, idx};
+            heap.back() = cand;
         } else {
-            heap.push_back({d2, idx});
+            heap.push_back(cand);
         }
         std::push_heap(heap.begin(), heap.end(), di_less);
-        if (heap.size() == capacity) worst = heap.front().d2;
     }
+    // largest kept d2 once the set is full (nothing farther can enter), the squared radius before that
+    float worst_d2() const { return heap.size() == capacity ? heap.front().d2 : r2; }
     bool full() const { return heap.size() == capacity; }
     void sorted(std::vector<DistIndex>& out)
     {
@@ -214,7 +220,7 @@ void grid_query(const CpuGrid& g, const float* tgt, const float* q, float /*r2f*
         if (rs.full()) {
             // every point not yet scanned is farther than s*h along some axis (minus rounding slack)
             double covered = static_cast<double>(s) * g.h * (1.0 - 1e-5);
-            if (static_cast<double>(rs.worst) < covered * covered) break;
+            if (static_cast<double>(rs.worst_d2()) < covered * covered) break;
         }
     }
 }
@@ -724,6 +730,8 @@ struct StepEvaluator {  // non-monotonic acceptance, Conn-Gould-Toint alg. 10.1.
     }
 };
 
+static std::atomic<long long> g_nonmonotonic_total{0};  // accepted non-monotonic steps since the last reset (test probe)
+
 template <typename Problem>
 void minimise(Problem& prob, double x[kNumParams], const oracle_solver_options& opt, oracle_solve_summary* sum)
 {
@@ -754,7 +762,7 @@ void minimise(Problem& prob, double x[kNumParams], const oracle_solver_options& 
     StepEvaluator ev(x_cost, kMaxNonmonotonic);
     double radius = kInitialRadius, decrease_factor = 2.0;
     bool reuse_diagonal = false, step_ok = true;
-    int iteration = 0, invalid = 0, successful = 0;
+    int iteration = 0, invalid = 0, successful = 0, nonmonotonic_accepted = 0;
     int termination = 4;
 
     for (;;) {
@@ -764,9 +772,16 @@ void minimise(Problem& prob, double x[kNumParams], const oracle_solver_options& 
             if (x_cost < minimum_cost) {
                 minimum_cost = x_cost;
                 std::copy(x, x + kNumParams, best_x);
+            } else {
+                ++nonmonotonic_accepted;  // an accepted step that did not lower the minimum: parameters_ stays behind x
+                if (trace) std::fprintf(stderr, "  [oracle lm] it %d accepted non-monotonic step: x_cost %.12g >= minimum %.12g\n", iteration, x_cost, minimum_cost);
             }
         }
-        prob.callback(x);  // update_state_every_iteration: the callback sees the current iterate
+        // [CERES] update_state_every_iteration is a StateUpdatingCallback that runs ahead of the user callbacks and copies the
+        // minimiser's `parameters_` into the user's arrays -- and `parameters_` is only overwritten when x_cost < minimum_cost
+        // (the lines above).  After an accepted NON-monotonic step the WeightUpdaterCallback (weight_updater_callback.hpp:42-51
+        // reads rotation_ / translation_) therefore sees the lowest-cost iterate, not x.
+        prob.callback(best_x);
         if (iteration >= opt.max_num_iterations) { termination = 4; break; }
         if (step_ok && grad_max <= kGradTol) { termination = 2; break; }
         if (radius < kMinRadius) { termination = 3; break; }
@@ -842,6 +857,8 @@ void minimise(Problem& prob, double x[kNumParams], const oracle_solver_options& 
     sum->num_iterations = iteration;
     sum->num_successful_steps = successful;
     sum->termination = termination;
+    sum->num_nonmonotonic_steps = nonmonotonic_accepted;
+    g_nonmonotonic_total += nonmonotonic_accepted;
 }
 
 // iteration.hpp:59-67 + [EIGEN]: normalise q, rotation matrix, [R | t] as a row-major 4x4
@@ -1016,11 +1033,120 @@ int64_t radius_search(const float* src, int64_t n_src, const float* tgt, int64_t
     return total;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// utilities.hpp:28-234 -- the closest-point metric helpers (1-nearest-neighbour distances of cloud1 in cloud2)
+// ---------------------------------------------------------------------------------------------
+
+// [PCL/FLANN] KdTreeFLANN::nearestKSearch(cloud, i, 1, idx, dist): dist[0] is the SQUARED distance (float, L2_Simple
+// arithmetic) to the nearest point of the tree's cloud.  Exact search: brute force returns the same value.
+static void closest_sq_distances(const float* c1, int64_t n1, const float* c2, int64_t n2, std::vector<float>& out)
+{
+    out.assign(static_cast<size_t>(n1), 0.f);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n1; ++i) {
+        float best = std::numeric_limits<float>::infinity();
+        for (int64_t j = 0; j < n2; ++j) best = std::min(best, dist2_f32(c1 + 4 * i, c2 + 4 * j));
+        out[static_cast<size_t>(i)] = best;
+    }
+}
+
+// The reference's "median" of a SORTED vector (utilities.hpp:84-89 and five more copies): element (n + 1) / 2 when n is odd,
+// the mean of elements n / 2 and n / 2 + 1 when n is even -- one position above the textbook median, and out of bounds for
+// n = 1 and n = 2 (undefined behaviour in the reference; NaN here).  T = double for the vector<double> helpers (the addition
+// happens in double), float for the vector<float> ones (the two floats are added in float, then divided by 2.0 in double).
+template <typename T>
+static double reference_median(const std::vector<T>& v)
+{
+    const size_t n = v.size();
+    if (n % 2 != 0) {
+        const size_t k = (n + 1) / 2;
+        return k < n ? static_cast<double>(v[k]) : std::numeric_limits<double>::quiet_NaN();
+    }
+    const size_t a = n / 2, b = n / 2 + 1;
+    if (b >= n) return std::numeric_limits<double>::quiet_NaN();
+    return (v[a] + v[b]) / 2.0;
+}
+
+
 }  // namespace
 
 extern "C" {
 
+int32_t oracle_closest_metrics(const float* c1, int64_t n1, const float* c2, int64_t n2, double factor, double* out,
+                                          float* out_d2)
+{
+    if (n1 < 1 || n2 < 1) return -1;
+    std::vector<float> d;
+    closest_sq_distances(c1, n1, c2, n2, d);
+    if (out_d2) std::copy(d.begin(), d.end(), out_d2);
+    // averageClosestDistance :28-46 and sumSquaredError :48-65: float distances added to a double in point order
+    double sum = 0;
+    for (float v : d) sum += v;
+    out[0] = sum / static_cast<double>(n1);
+    out[1] = sum;
+    // robustSumSquaredError :67-101 / (factor) :103-138 / robustAveragedSumSquaredError :140-175: vector<double>, sorted
+    std::vector<double> all(d.begin(), d.end());
+    std::sort(all.begin(), all.end());
+    const double med = reference_median(all);
+    auto robust = [&](double f, double* s_out, int64_t* n_out) {
+        double s = 0;
+        int64_t nf = 0;
+        for (double v : all)
+            if (v <= med * f && v >= med / f) {
+                s += v;
+                ++nf;
+            }
+        *s_out = s;
+        *n_out = nf;
+    };
+    double s3, sf;
+    int64_t n3, nf;
+    robust(3.0, &s3, &n3);
+    robust(factor, &sf, &nf);
+    const double big = std::numeric_limits<double>::max();
+    out[2] = n3 < 10 ? big : s3;
+    out[3] = nf < 10 ? big : sf;
+    out[4] = n3 < 10 ? big : s3 / static_cast<double>(n3);
+    // medianClosestDistance :177-199 and robustMedianClosestDistance :201-234: vector<float>, sorted
+    std::vector<float> fs(d);
+    std::sort(fs.begin(), fs.end());
+    const double medf = reference_median(fs);
+    out[5] = medf;
+    std::vector<float> filt;
+    for (float v : fs)
+        if (v <= medf * 3 && v >= medf / 3.0) filt.push_back(v);
+    out[6] = filt.empty() ? std::numeric_limits<double>::quiet_NaN() : reference_median(filt) / static_cast<double>(filt.size());
+    out[7] = static_cast<double>(n3);
+    out[8] = static_cast<double>(nf);
+    return 0;
+}
+
+// H (upper triangle, 28), g (7) and the cost of one Jacobian evaluation at pose x_e with the weights refreshed at pose x_w:
+// what Ceres assembles from the 3K x 7 Jacobian of the problem of iteration.hpp:24-50 (unscaled columns).
+void oracle_normal_eq(const float* src, const float* tgt, int64_t n_rows, const int64_t* row_ptr, const int32_t* col_idx,
+                                 double dof, const double* x_w, const double* x_e, double* out36)
+{
+    Association A{src, tgt, n_rows, row_ptr, col_idx};
+    NormalEqProblem prob(A, dof, 1);
+    prob.callback(x_w);
+    const double cost = prob.evaluate_full(x_e);
+    int o = 0;
+    for (int r = 0; r < kNumParams; ++r)
+        for (int c = r; c < kNumParams; ++c) out36[o++] = prob.H[r][c];
+    for (int r = 0; r < kNumParams; ++r) out36[o++] = prob.g[r];
+    out36[o] = cost;
+}
+
+
 int32_t oracle_max_threads(void) { return resolve_threads(0); }
+
+int64_t oracle_nonmonotonic_steps(int32_t reset)
+{
+    const long long v = g_nonmonotonic_total.load();
+    if (reset) g_nonmonotonic_total.store(0);
+    return v;
+}
 
 int64_t oracle_radius_search(const float* src, int64_t n_src, const float* tgt, int64_t n_tgt, double radius,
                              int32_t max_nn, int32_t cap, int32_t use_grid, int32_t num_threads, int32_t* out_idx,

@@ -57,7 +57,7 @@ typedef struct oracle_solve_summary {
     int32_t num_successful_steps; /* includes iteration zero, like Ceres */
     int32_t termination;          /* 0 function tol, 1 parameter tol, 2 gradient tol, 3 min radius,
                                      4 max iterations, 5 no residuals, 6 too many invalid steps */
-    int32_t pad;
+    int32_t num_nonmonotonic_steps; /* accepted steps that did not lower the minimum cost (use_nonmonotonic_steps) */
 } oracle_solve_summary;
 
 typedef struct oracle_iter_stats {
@@ -114,7 +114,24 @@ int32_t oracle_align(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw
 /* calculateMSE (utilities.hpp:16-26): mean Euclidean distance between same-sized clouds. */
 double oracle_calculate_mse(const float* a_xyzw, const float* b_xyzw, int64_t n);
 
+/* The closest-point metric helpers of utilities.hpp:28-234 in one call (1-NN squared distances of cloud1 in cloud2, brute
+ * force).  out[9]: 0 averageClosestDistance, 1 sumSquaredError, 2 robustSumSquaredError, 3 robustSumSquaredError(factor),
+ * 4 robustAveragedSumSquaredError, 5 medianClosestDistance, 6 robustMedianClosestDistance, 7 / 8 the number of distances
+ * inside the [median / 3, median * 3] and [median / factor, median * factor] windows.  out_d2 (may be NULL): the n1
+ * squared distances.  Returns -1 when a cloud is empty (the reference reads out of bounds there). */
+int32_t oracle_closest_metrics(const float* c1_xyzw, int64_t n1, const float* c2_xyzw, int64_t n2, double factor,
+                               double* out9, float* out_d2);
+
+/* Upper triangle of J^T W J (28, row-major), J^T W r (7) and the cost (1) of the problem of iteration.hpp:24-50 evaluated at
+ * x_e = (w,x,y,z,tx,ty,tz) with the weights refreshed at x_w (WeightUpdaterCallback), analytic Jacobian rows in float64. */
+void oracle_normal_eq(const float* src_xyzw, const float* tgt_xyzw, int64_t n_rows, const int64_t* row_ptr,
+                      const int32_t* col_idx, double dof, const double* x_w, const double* x_e, double* out36);
+
 int32_t oracle_max_threads(void);
+
+/* Accepted non-monotonic LM steps over every solve since the last reset (tests: proves a scenario exercises the
+ * "callback sees the lowest-cost iterate" rule of update_state_every_iteration). */
+int64_t oracle_nonmonotonic_steps(int32_t reset);
 
 #ifdef __cplusplus
 }

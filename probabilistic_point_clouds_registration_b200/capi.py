@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "ppcr_iteration_stats",
     "ppcr_filtered_source", "ppcr_filtered_target", "ppcr_association", "ppcr_get_stage_times", "ppcr_time_kernel",
     "ppcr_voxel_filter", "ppcr_radius_search", "ppcr_weights_normal_eq", "ppcr_iteration_solve", "ppcr_transform",
-    "ppcr_replay_metrics",
+    "ppcr_replay_metrics", "ppcr_closest_point_metrics",
     "ppcr_align_batch", "ppcr_shard_export", "ppcr_shard_connect",
 ]
 
@@ -87,6 +87,17 @@ class StageTimes(C.Structure):
     ]
 
 
+class ClosestMetrics(C.Structure):
+    """ppcr_closest_metrics: the seven closest-point helpers of utilities.hpp:28-234."""
+
+    _fields_ = [
+        ("average_closest_distance", C.c_double), ("sum_squared_error", C.c_double),
+        ("robust_sum_squared_error", C.c_double), ("robust_sum_squared_error_factor", C.c_double),
+        ("robust_averaged_sum_squared_error", C.c_double), ("median_closest_distance", C.c_double),
+        ("robust_median_closest_distance", C.c_double), ("n_filtered", C.c_int64), ("n_filtered_factor", C.c_int64),
+    ]
+
+
 class PairDesc(C.Structure):
     _fields_ = [("src", C.c_void_p), ("n_src", C.c_int64), ("tgt", C.c_void_p), ("n_tgt", C.c_int64)]
 
@@ -129,6 +140,7 @@ def lib():
         L.ppcr_iteration_solve.argtypes = [vp, i64, vp, i64, vp, vp, i32, C.POINTER(Params), C.POINTER(Options), f64, vp, vp, vp]
         L.ppcr_transform.argtypes = [vp, i64, vp]
         L.ppcr_replay_metrics.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
+        L.ppcr_closest_point_metrics.argtypes = [vp, i64, vp, i64, f64, C.POINTER(Options), C.POINTER(ClosestMetrics), vp]
         L.ppcr_align_batch.argtypes = [C.POINTER(PairDesc), i32, C.POINTER(Params), C.POINTER(Options), i32, vp, vp, vp]
         L.ppcr_shard_export.argtypes = [vp, i32, i32, vp]
         L.ppcr_shard_connect.argtypes = [vp, vp]
@@ -368,6 +380,18 @@ def transform(cloud, T):
     T = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
     _check(lib().ppcr_transform(out.ctypes.data, len(out), T.ctypes.data))
     return out
+
+
+def closest_point_metrics(cloud1, cloud2, factor=3.0, options: Options | None = None, want_distances=True):
+    """utilities.hpp:28-234: dict of the seven helpers' values (+ window counts), and the squared 1-NN distance of every
+    cloud1 point in cloud2 (cloud1's order)."""
+    a, b = _cloud(cloud1), _cloud(cloud2)
+    out = ClosestMetrics()
+    d2 = np.zeros(max(len(a), 1), dtype=np.float32) if want_distances else None
+    _check(lib().ppcr_closest_point_metrics(a.ctypes.data, len(a), b.ctypes.data, len(b), float(factor),
+                                            C.byref(options) if options is not None else None, C.byref(out),
+                                            d2.ctypes.data if d2 is not None else None))
+    return {name: getattr(out, name) for name, _ in ClosestMetrics._fields_}, (d2[:len(a)] if d2 is not None else None)
 
 
 def align_batch(pairs, params: Params, options: Options | None = None, slots=0):

@@ -419,7 +419,9 @@ static void build_target_tree(Engine& E, Pair& P, int leaf_cap)
     const Bbox bb = cloud_bbox(P.tgt_raw.p, n, P, st);
     for (int k = 0; k < 3; ++k)
         if (!std::isfinite(bb.lo[k]) || !std::isfinite(bb.hi[k]))
-            throw StatusError{PPCR_ERR_INVALID, "target cloud contains non-finite coordinates"};
+            throw StatusError{PPCR_ERR_INVALID, "target cloud contains non-finite coordinates (pcl::KdTreeFLANN leaves such points out "
+                                                "of its tree when the cloud is flagged !is_dense: the C++ class does, the C ABI takes "
+                                                "finite targets)"};
     const TreeGeom g = make_tree_geom(bb, leaf_cap, n);
     morton_sort(P, P.tgt_raw.p, n, g, st);
     P.tgt_sorted.reserve(n);
@@ -473,6 +475,10 @@ static int64_t voxel_filter_device(const float4* in, int64_t n, double leaf_d, D
     const float leaf = static_cast<float>(leaf_d);
     const float inv = 1.0f / leaf;
     const Bbox bb = cloud_bbox(in, static_cast<int>(n), scratch, st);
+    for (int k = 0; k < 3; ++k)
+        if (!std::isfinite(bb.lo[k]) || !std::isfinite(bb.hi[k]))
+            throw StatusError{PPCR_ERR_INVALID, "a cloud to be voxel-filtered contains non-finite coordinates (PCL drops them when "
+                                                "the cloud is flagged !is_dense: the C++ class does, the C ABI takes finite clouds)"};
     int64_t d[3];
     VoxelGeom vg{};
     vg.inv_leaf = inv;
@@ -653,6 +659,7 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     state_init(&hs, &c);
     CK(cudaMemcpyAsync(P.cfg.p, &c, sizeof(c), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(P.state.p, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
+    D.dump_w = nullptr;
     D.mailbox = nullptr;
     D.rank = 0;
     D.world = 1;
@@ -982,6 +989,7 @@ static void use_engine(Engine& E)
     CK(cudaSetDevice(E.device));
     g_alloc_stream = E.stream;
     g_launch_sink = &E.times.total_launches;
+    E.h_active = pinned_flag();  // the CALLING thread's pinned word (the handle may have been created on another thread)
 }
 
 static PairState download_state(Engine& E, int p)
@@ -1517,15 +1525,20 @@ ppcr_status ppcr_weights_normal_eq(const float* src, int64_t n_src, const float*
         pose7_to_state(pose_e, &s.pose_e);
         pose7_to_state(pose_w, &s.pose_w);
         CK(cudaMemcpyAsync(E.pairs[0].state.p, &s, sizeof(s), cudaMemcpyHostToDevice, E.stream));
-        if (weights) {  // before the evaluation: its controller tail advances the scratch state
-            const PairDev& D = E.pairs[0].dev;
-            DevBuf<double> dw;
-            const size_t plane = static_cast<size_t>(D.m) * D.n_pad;
+        // The weights come out of the evaluation kernel itself (PairDev::dump_w): the same staged loop, row statistics and
+        // weight terms that produce the moments, not a separate test kernel.
+        DevBuf<double> dw;
+        const size_t plane = static_cast<size_t>(E.pairs[0].dev.m) * E.pairs[0].dev.n_pad;
+        if (weights) {
             dw.reserve(plane);
             CK(cudaMemsetAsync(dw.p, 0, plane * sizeof(double), E.stream));
-            if (fast_weights) k_dump_weights<true><<<ceil_div(std::max(D.n_src, 1), 128), 128, 0, E.stream>>>(E.d_pairs.p, dw.p);
-            else k_dump_weights<false><<<ceil_div(std::max(D.n_src, 1), 128), 128, 0, E.stream>>>(E.d_pairs.p, dw.p);
-            CK(cudaGetLastError());
+            E.pairs[0].dev.dump_w = dw.p;
+            engine_commit(E);  // republish the PairDev
+        }
+        launch_evalctl(E, false);  // its controller tail runs on a scratch state; only the partial sums are used
+        CK(cudaGetLastError());
+        if (weights) {
+            const PairDev& D = E.pairs[0].dev;
             std::vector<double> hw(plane);
             CK(cudaMemcpyAsync(hw.data(), dw.p, plane * sizeof(double), cudaMemcpyDeviceToHost, E.stream));
             CK(cudaStreamSynchronize(E.stream));
@@ -1537,8 +1550,6 @@ ppcr_status ppcr_weights_normal_eq(const float* src, int64_t n_src, const float*
             }
             dw.release();
         }
-        launch_evalctl(E, false);  // its controller tail runs on a scratch state; only the partial sums are used
-        CK(cudaGetLastError());
         double S[kNSum];
         reduce_partials_like_controller(E, 0, S);
         Expanded ev;
@@ -1670,6 +1681,85 @@ ppcr_status ppcr_replay_metrics(ppcr_handle* h, float* cloud_xyzw, const float* 
     });
 }
 
+// ---- closest-point metrics ------------------------------------------------------------------------------------
+
+ppcr_status ppcr_closest_point_metrics(const float* cloud1, int64_t n1, const float* cloud2, int64_t n2, double factor,
+                                       const ppcr_options* options, ppcr_closest_metrics* out, float* out_d2)
+{
+    if (!cloud1 || !cloud2 || !out || n1 < 1 || n2 < 1 || !(factor > 0.0))
+        return fail(PPCR_ERR_INVALID, "bad argument (both clouds need at least one point: the reference reads out of bounds otherwise)");
+    return guarded([&] {
+        ppcr_params prm;
+        ppcr_default_params(&prm);
+        prm.max_neighbours = 1;       // nearestKSearch(k = 1)
+        prm.radius = 1.8e19;          // no radius: float(r * r) is the largest squared distance a float cloud can produce
+        ppcr_options opt;
+        ppcr_default_options(&opt);
+        if (options) opt = *options;
+        Engine E;
+        engine_init(E, prm, &opt);
+        E.pairs.resize(1);
+        Pair& P = E.pairs[0];
+        P.want_d2 = true;
+        pair_setup(E, P, cloud1, n1, cloud2, n2, opt.input_on_device != 0);
+        engine_commit(E);
+        cudaStream_t st = E.stream;
+        const int n = static_cast<int>(n1);
+        {   // the queries must be finite too (the target was checked by the tree build)
+            const Bbox bb = cloud_bbox(P.src.p, n, P, st);
+            for (int k = 0; k < 3; ++k)
+                if (!std::isfinite(bb.lo[k]) || !std::isfinite(bb.hi[k]))
+                    throw StatusError{PPCR_ERR_INVALID, "cloud1 contains non-finite coordinates"};
+        }
+        set_phase(E, 0, PH_SEARCH);
+        launch_search(E);
+        note_launches(1);
+        CK(cudaGetLastError());
+        // m = 1: the distance plane is one float per query (device order = Morton order of cloud1)
+        DevBuf<float> sorted;
+        DevBuf<unsigned char> tmp;
+        DevBuf<double> partial, d_out;
+        DevBuf<ClosestPlan> plan;
+        sorted.reserve(n);
+        size_t tmp_bytes = 0;
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, P.nbr_d2.p, sorted.p, n, 0, 32, st));
+        tmp.reserve(tmp_bytes);
+        CK(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, P.nbr_d2.p, sorted.p, n, 0, 32, st));
+        const int blocks = std::min(ceil_div(n, kClosestThreads), 8 * std::max(g_sm_count, 1));
+        partial.reserve(static_cast<size_t>(blocks) * 3);
+        d_out.reserve(9);
+        plan.reserve(1);
+        k_closest_plan<<<1, 32, 0, st>>>(sorted.p, n, factor, plan.p);
+        k_closest_reduce<<<blocks, kClosestThreads, 0, st>>>(sorted.p, n, plan.p, partial.p);
+        k_closest_fold<<<1, 32, 0, st>>>(partial.p, blocks, n, plan.p, d_out.p);
+        CK(cudaGetLastError());
+        note_launches(3 + 6);
+        double h[9];
+        CK(cudaMemcpyAsync(h, d_out.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        std::vector<float> h_d2;
+        std::vector<int> order;
+        if (out_d2) {
+            h_d2.resize(static_cast<size_t>(n));
+            CK(cudaMemcpyAsync(h_d2.data(), P.nbr_d2.p, static_cast<size_t>(n) * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        if (out_d2) {
+            order = source_order(E, 0);
+            for (int j = 0; j < n; ++j) out_d2[order[static_cast<size_t>(j)]] = h_d2[static_cast<size_t>(j)];
+        }
+        out->average_closest_distance = h[0];
+        out->sum_squared_error = h[1];
+        out->robust_sum_squared_error = h[2];
+        out->robust_sum_squared_error_factor = h[3];
+        out->robust_averaged_sum_squared_error = h[4];
+        out->median_closest_distance = h[5];
+        out->robust_median_closest_distance = h[6];
+        out->n_filtered = static_cast<int64_t>(h[7]);
+        out->n_filtered_factor = static_cast<int64_t>(h[8]);
+        sorted.release(); tmp.release(); partial.release(); d_out.release(); plan.release();
+    });
+}
+
 // ---- batch ---------------------------------------------------------------------------------------------------
 
 ppcr_status ppcr_align_batch(const ppcr_pair* pairs, int32_t n_pairs, const ppcr_params* params,
@@ -1721,9 +1811,16 @@ ppcr_status ppcr_align_batch(const ppcr_pair* pairs, int32_t n_pairs, const ppcr
             } catch (const StatusError& e) {
                 std::lock_guard<std::mutex> lock(err_mutex);
                 if (first_error.code == PPCR_OK) first_error = e;
+            } catch (const CudaError& e) {  // CK() throws this plain struct: it must not leave the thread
+                const ppcr_status code = translate(e);  // (message lands in this lane thread's g_last_error)
+                std::lock_guard<std::mutex> lock(err_mutex);
+                if (first_error.code == PPCR_OK) first_error = StatusError{code, g_last_error};
             } catch (const std::exception& e) {
                 std::lock_guard<std::mutex> lock(err_mutex);
                 if (first_error.code == PPCR_OK) first_error = StatusError{PPCR_ERR_CUDA, e.what()};
+            } catch (...) {
+                std::lock_guard<std::mutex> lock(err_mutex);
+                if (first_error.code == PPCR_OK) first_error = StatusError{PPCR_ERR_CUDA, "unknown failure in a batch lane"};
             }
         };
         if (lanes == 1) {

@@ -91,6 +91,7 @@ struct PairDev {
     double* history;
     IterStats* stats;
     WeightCfg wcfg;
+    double* dump_w;  // parity dumps only (ppcr_weights_normal_eq), normally null: [m][n_pad] weights written by the evaluation itself
     // sharded mode: mailbox exchange of the moment vector between ranks
     double* mailbox;          // [world][kMailDoubles] on THIS device, written by the peers
     double* peer_mailbox[8];  // the same buffer on every rank (peer-mapped), indexed by rank
@@ -340,6 +341,10 @@ __device__ __forceinline__ float transform_row(const double* T, double x, double
     return __double2float_rn(acc);
 }
 
+// A query with a non-finite coordinate has no neighbours (every distance comparison fails, as in FLANN); it must not walk
+// the tree either: its box tests cannot prune anything.
+__device__ __forceinline__ bool finite_query(const float4& q) { return isfinite(q.x) && isfinite(q.y) && isfinite(q.z); }
+
 struct SearchOut {  // where a query's results go (copied out of the PairDev once per block)
     int* __restrict__ nbr_pos;
     float* __restrict__ nbr_d2;
@@ -474,6 +479,11 @@ __global__ void PPCR_SEARCH_BOUNDS k_search(const PairDev* __restrict__ pairs)
         }
         int cnt = 0;
         float kth = __int_as_float(0x7f800000);
+        if (!finite_query(q)) {
+            nbr_cnt[i] = 0;
+            nbr_kth[i] = kth;
+            continue;
+        }
         typename SearchList<VAR>::type L;
         L.k = s_heap + threadIdx.x;
         L.init(m, cap);
@@ -619,7 +629,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
         // ---- A: the query, its bound, its leaves ----
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
         float bound0 = r2f;
-        bool fallback = false, heavy = false;
+        bool fallback = false, heavy = false, dead = false;  // dead: a non-finite query, no neighbours
         if (valid) {
             q = src[i];
             const double x = q.x, y = q.y, z = q.z;
@@ -630,7 +640,8 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
             q.y = ny;
             q.z = nz;
             src[i] = q;
-            if (prev < kInf) {  // a saturated row: the farthest of its previous neighbours bounds the new m-th distance
+            dead = !finite_query(q);
+            if (prev < kInf && !dead) {  // a saturated row: the farthest of its previous neighbours bounds the new m-th distance
                 const int* __restrict__ pp = out.nbr_pos + i;
                 float far2 = 0.f;
                 int k = 0;
@@ -658,7 +669,10 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
         // A chunk made mostly of heavy queries is searched the way k_search does it -- every thread walks with its heap and
         // lets the bound shrink as candidates arrive -- because the fixed bound would push them all through the fallback.
         if (__syncthreads_count(heavy) * 2 > kSearchThreads) {
-            if (valid) {
+            if (dead) {
+                nbr_cnt[i] = 0;
+                nbr_kth[i] = kInf;
+            } else if (valid) {
                 HeapList<kSearchThreads, 0> L;
                 L.k = s_heap + threadIdx.x;
                 L.init(m);
@@ -674,7 +688,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
             }
             continue;
         }
-        if (valid) {
+        if (valid && !dead) {
             s_q[threadIdx.x] = make_float4(q.x, q.y, q.z, candidate_limit(bound0, r2f));
             QEmit emit{s_tasks, &s_ntasks, threadIdx.x, 0};
             fallback = !tree_collect_leaves(geom, nodes, q.x, q.y, q.z, bound0, emit, stack);
@@ -1042,6 +1056,31 @@ __device__ __forceinline__ void eval_rows_fast(const PairDev& P, const EvalStage
                     if (k0 + u < cnt) rowf_add_t<WM, SAME>(&row, wc, y[u].x, y[u].y, y[u].z, he, dw);
             }
             rowf_end_s<1>(&row, sx, sy, sz, racc);
+            if (!ASYNC && P.dump_w) {
+                // Parity dump (ppcr_weights_normal_eq): the weight of every correspondence of this row, from the row statistics
+                // just folded into the moments and the same staged positions, residual arithmetic and weight terms.
+                double* __restrict__ o = P.dump_w + static_cast<size_t>(tile) * kEvalFastThreads + threadIdx.x;
+                for (int k = 0; k < cnt; ++k) {
+                    const float4 y = __ldg(table + s_pos[k * kEvalFastThreads]);
+                    float wx = residual_hl(y.x, he.hi[0], he.lo[0]), wy = residual_hl(y.y, he.hi[1], he.lo[1]),
+                          wz = residual_hl(y.z, he.hi[2], he.lo[2]);
+                    if (!SAME) {
+                        wx += dw[0];
+                        wy += dw[1];
+                        wz += dw[2];
+                    }
+                    const float r2w = wx * wx + wy * wy + wz * wz;
+                    float w;
+                    if (WM == WM_GAUSS) {
+                        w = f_exp(-0.5f * r2w - row.m) / row.a0;
+                    } else {
+                        float u, ue;
+                        t_terms<WM>(wc, r2w, &u, &ue);
+                        w = ue / row.a0;
+                    }
+                    o[static_cast<size_t>(k) * P.n_pad] = static_cast<double>(w);
+                }
+            }
         }
         __syncthreads();  // every thread is done with this stage: refill it with the tile kEvalStages ahead
         if (threadIdx.x < 32) {
@@ -1163,6 +1202,13 @@ __global__ void __launch_bounds__(eval_threads(kFast), kFast ? kEvalFastBlocks :
                 row_add<false>(&row, wc, y.x, y.y, y.z, pte, ptw);
             }
             row_end_s<kEvalThreads>(&row, sx, sy, sz, acc);
+            if (P.dump_w) {  // parity dump: the weights this row entered the moments with
+                for (int k = 0; k < cnt; ++k) {
+                    const size_t o = static_cast<size_t>(k) * n_pad + i;
+                    const float4 y = __ldg(P.tgt_sorted + __ldg(P.nbr_pos + o));
+                    P.dump_w[o] = finished_weight<false>(&row, wc, y.x, y.y, y.z, ptw);
+                }
+            }
         }
 #pragma unroll
         for (int k = 0; k < kNSum; ++k) racc[k] = acc[k * kEvalThreads];
@@ -1357,52 +1403,6 @@ __global__ void __launch_bounds__(eval_threads(kFast), kFast ? kEvalFastBlocks :
     }
 }
 
-// weights of the current association at pose_w, written slot-major (parity dumps only)
-template <bool kFast>
-__global__ void k_dump_weights(const PairDev* __restrict__ pairs, double* __restrict__ out)
-{
-    const PairDev& P = pairs[0];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_src) return;
-    const int cnt = P.nbr_cnt[i];
-    if (cnt == 0) return;
-    const Pose pw = P.state->pose_w;
-    const float4 sp = P.src[i];
-    double ptw[3];
-    apply_pose(pw, sp.x, sp.y, sp.z, ptw);
-    const size_t n_pad = P.n_pad;
-    if constexpr (kFast) {
-        PointHL hw;
-        split_point(ptw, &hw);
-        RowAccF row;
-        rowf_begin(&row);
-        for (int k = 0; k < cnt; ++k) {
-            const size_t o = static_cast<size_t>(k) * n_pad + i;
-            const float zero[3] = {0.f, 0.f, 0.f};
-            const float4 y = P.tgt_sorted[P.nbr_pos[o]];
-            rowf_add(&row, P.wcfg, y.x, y.y, y.z, hw, zero, true);
-        }
-        for (int k = 0; k < cnt; ++k) {
-            const size_t o = static_cast<size_t>(k) * n_pad + i;
-            const float4 y = P.tgt_sorted[P.nbr_pos[o]];
-            out[o] = rowf_finished_weight(&row, P.wcfg, y.x, y.y, y.z, hw);
-        }
-    } else {
-        RowAcc row;
-        row_begin(&row);
-        for (int k = 0; k < cnt; ++k) {
-            const size_t o = static_cast<size_t>(k) * n_pad + i;
-            const float4 y = P.tgt_sorted[P.nbr_pos[o]];
-            row_add<false>(&row, P.wcfg, y.x, y.y, y.z, ptw, ptw);
-        }
-        for (int k = 0; k < cnt; ++k) {
-            const size_t o = static_cast<size_t>(k) * n_pad + i;
-            const float4 y = P.tgt_sorted[P.nbr_pos[o]];
-            out[o] = finished_weight<false>(&row, P.wcfg, y.x, y.y, y.z, ptw);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // align() entry and exit
 // ------------------------------------------------------------------------------------------------------------
@@ -1571,6 +1571,126 @@ __global__ void k_voxel_mean(const float4* __restrict__ pts, const unsigned* __r
     }
     const float cnt = static_cast<float>(k - i);
     out[slot[i]] = make_float4(__fdiv_rn(cx, cnt), __fdiv_rn(cy, cnt), __fdiv_rn(cz, cnt), 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// closest-point metrics (utilities.hpp:28-234): statistics of the squared 1-NN distances of one cloud in another
+// ------------------------------------------------------------------------------------------------------------
+//
+// The seven helpers of the reference differ only in what they do with the vector of nearestKSearch(k = 1) distances: its
+// sum, its "median" (the reference's own index rule, one position above the textbook one), and the sum / count / median
+// of the entries inside a window [median / f, median * f].  The search is k_search with m = 1 and no radius; the vector is
+// sorted once (radix sort), k_closest_plan finds the medians and the windows -- contiguous index ranges of the sorted
+// vector -- by binary search, k_closest_reduce adds up the three ranges per block in double, k_closest_fold adds the block
+// sums in block order (fixed order: run-to-run identical) and writes the nine results.
+
+struct ClosestPlan {
+    double med_d;      // "median" of the distances as a vector<double> (robustSumSquaredError family)
+    double med_f;      // ... as a vector<float>: the two middle floats are added in float32 (medianClosestDistance family)
+    double robust_med; // robustMedianClosestDistance
+    int lo3, hi3;      // [lo3, hi3): entries with med_d / 3 <= v <= med_d * 3
+    int lof, hif;      // the same with the caller's factor
+    int pad[2];
+};
+
+__device__ __forceinline__ double closest_median(const float* __restrict__ v, int n, bool add_in_float)
+{
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    if (n % 2 != 0) {
+        const int k = (n + 1) / 2;
+        return k < n ? static_cast<double>(v[k]) : nan;  // (out of bounds in the reference for n = 1)
+    }
+    const int a = n / 2, b = n / 2 + 1;
+    if (b >= n) return nan;
+    if (add_in_float) return static_cast<double>(__fadd_rn(v[a], v[b])) / 2.0;
+    return (static_cast<double>(v[a]) + static_cast<double>(v[b])) / 2.0;
+}
+
+// first index in [0, n) whose entry is >= lo (as doubles) / first index whose entry is > hi; NaN bounds give empty ranges
+__device__ __forceinline__ void closest_window(const float* __restrict__ v, int n, double lo, double hi, int* first, int* last)
+{
+    int a = 0, b = n;
+    while (a < b) {
+        const int mid = a + ((b - a) >> 1);
+        if (static_cast<double>(v[mid]) >= lo) b = mid; else a = mid + 1;
+    }
+    *first = a;
+    int c = 0, d = n;
+    while (c < d) {
+        const int mid = c + ((d - c) >> 1);
+        if (static_cast<double>(v[mid]) <= hi) c = mid + 1; else d = mid;
+    }
+    *last = c;
+    if (!(lo == lo) || !(hi == hi) || *last < *first) *first = *last = 0;
+}
+
+__global__ void k_closest_plan(const float* __restrict__ sorted, int n, double factor, ClosestPlan* __restrict__ plan)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    ClosestPlan p{};
+    p.med_d = closest_median(sorted, n, false);
+    p.med_f = closest_median(sorted, n, true);
+    closest_window(sorted, n, p.med_d / 3, p.med_d * 3, &p.lo3, &p.hi3);
+    closest_window(sorted, n, p.med_d / factor, p.med_d * factor, &p.lof, &p.hif);
+    int a = 0, b = 0;
+    closest_window(sorted, n, p.med_f / 3.0, p.med_f * 3, &a, &b);
+    const int nf = b - a;
+    p.robust_med = nf > 0 ? closest_median(sorted + a, nf, true) / static_cast<double>(nf) : __longlong_as_double(0x7ff8000000000000ll);
+    *plan = p;
+}
+
+constexpr int kClosestThreads = 256;
+
+__global__ void __launch_bounds__(kClosestThreads) k_closest_reduce(const float* __restrict__ sorted, int n,
+                                                                    const ClosestPlan* __restrict__ plan, double* __restrict__ partial)
+{
+    __shared__ double s_red[3][kClosestThreads / 32];
+    const ClosestPlan p = *plan;
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double v = static_cast<double>(sorted[i]);
+        s[0] += v;
+        if (i >= p.lo3 && i < p.hi3) s[1] += v;
+        if (i >= p.lof && i < p.hif) s[2] += v;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(kFull, s[k], o);
+        if ((threadIdx.x & 31) == 0) s_red[k][threadIdx.x >> 5] = s[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double v = 0.0;
+        for (int w = 0; w < kClosestThreads / 32; ++w) v += s_red[threadIdx.x][w];
+        partial[3 * blockIdx.x + threadIdx.x] = v;
+    }
+}
+
+// out[9]: average, sum, robust sum (3), robust sum (factor), robust averaged sum, median, robust median, window counts
+__global__ void k_closest_fold(const double* __restrict__ partial, int n_blocks, int n, const ClosestPlan* __restrict__ plan,
+                               double* __restrict__ out)
+{
+    __shared__ double s_sum[3];
+    if (threadIdx.x < 3) {
+        double v = 0.0;
+        for (int b = 0; b < n_blocks; ++b) v += partial[3 * b + threadIdx.x];
+        s_sum[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const ClosestPlan p = *plan;
+        const double big = 1.7976931348623157e308;  // std::numeric_limits<double>::max(), the helpers' "too few points"
+        const int n3 = p.hi3 - p.lo3, nf = p.hif - p.lof;
+        out[0] = s_sum[0] / static_cast<double>(n);
+        out[1] = s_sum[0];
+        out[2] = n3 < 10 ? big : s_sum[1];
+        out[3] = nf < 10 ? big : s_sum[2];
+        out[4] = n3 < 10 ? big : s_sum[1] / static_cast<double>(n3);
+        out[5] = p.med_f;
+        out[6] = p.robust_med;
+        out[7] = static_cast<double>(n3);
+        out[8] = static_cast<double>(nf);
+    }
 }
 
 // L2 flush helper for benchmarks

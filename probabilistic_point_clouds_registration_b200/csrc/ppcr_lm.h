@@ -79,7 +79,7 @@ struct PairState {
     // ---- inner LM (one ceres::Solve) ----
     double x[kNP], cand[kNP], best_x[kNP];
     Pose pose_e;  // pose the NEXT eval computes residuals at (the candidate)
-    Pose pose_w;  // pose the NEXT eval refreshes the weights at (the current iterate)
+    Pose pose_w;  // pose the NEXT eval refreshes the weights at (the lowest-cost iterate so far: what Ceres shows the callback)
     double Hs[kNP * kNP], gs[kNP];  // column-scaled J^T W J and J^T W r of the current iterate
     double scale[kNP], diag[kNP], step[kNP];
     double x_cost, x_norm, grad_max, minimum_cost, min_iter_cost, initial_cost;
@@ -331,8 +331,10 @@ PPCR_HD bool step_prepare(PairState* s, const Config* cfg, double* D)
             for (int p = 0; p < kNP; ++p) s->best_x[p] = s->x[p];
         }
     }
-    // the IterationCallback refreshes the weights at the current iterate: the next eval does it on the fly
-    pose_from_x(s->x, &s->pose_w);
+    // The IterationCallback refreshes the weights at the state Ceres exposes to it: with update_state_every_iteration that is
+    // the minimiser's `parameters_`, which only follows x when x_cost < minimum_cost (above) -- after an accepted
+    // non-monotonic step it is still the lowest-cost iterate.  The next eval refreshes the weights there on the fly.
+    pose_from_x(s->best_x, &s->pose_w);
     if (s->iteration >= cfg->max_lm_iterations) { s->termination = TERM_MAX_ITER; return false; }
     if (s->step_ok && s->grad_max <= kGradTol) { s->termination = TERM_GRADIENT_TOL; return false; }
     if (s->radius < kMinRadius) { s->termination = TERM_MIN_RADIUS; return false; }

@@ -46,6 +46,19 @@ ppcr_params to_c(const ProbPointCloudRegistrationParams& p)
     return c;
 }
 
+// The finite points of a cloud that is flagged !is_dense, in order.  PCL's own stages drop the others: VoxelGrid skips
+// non-finite points when the input is not dense, and KdTreeFLANN leaves them out of the tree it builds
+// (registration.cc:27-30,37-40,66-67).  The C ABI takes finite clouds only.
+bool finite_points(const pcl::PointCloud<pcl::PointXYZ>& cloud, std::vector<pcl::PointXYZ>* out)
+{
+    if (cloud.is_dense) return false;
+    out->clear();
+    out->reserve(cloud.size());
+    for (const auto& p : cloud.points)
+        if (std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z)) out->push_back(p);
+    return out->size() != cloud.size();
+}
+
 Eigen::Affine3d to_affine(const double* T)
 {
     Eigen::Affine3d A;
@@ -99,9 +112,20 @@ void ProbPointCloudRegistration::init()
     const ppcr_params cp = to_c(parameters_);
     const float* src = source_cloud_->empty() ? nullptr : reinterpret_cast<const float*>(source_cloud_->points.data());
     const float* tgt = target_cloud_->empty() ? nullptr : reinterpret_cast<const float*>(target_cloud_->points.data());
-    check(ppcr_create(src, static_cast<int64_t>(source_cloud_->size()), tgt, static_cast<int64_t>(target_cloud_->size()),
-                      &cp, &handle_),
-          "ppcr_create");
+    int64_t n_src = static_cast<int64_t>(source_cloud_->size()), n_tgt = static_cast<int64_t>(target_cloud_->size());
+    // Clouds flagged !is_dense (e.g. organised depth-sensor PCDs): the target's non-finite points never reach the search
+    // structure, and a voxel-filtered source loses them in the filter.  An unfiltered source keeps them, as in the reference;
+    // such a point finds no neighbour (every comparison with NaN fails) and contributes nothing.
+    std::vector<pcl::PointXYZ> finite_src, finite_tgt;
+    if (finite_points(*target_cloud_, &finite_tgt)) {
+        tgt = finite_tgt.empty() ? nullptr : reinterpret_cast<const float*>(finite_tgt.data());
+        n_tgt = static_cast<int64_t>(finite_tgt.size());
+    }
+    if (parameters_.source_filter_size > 0 && finite_points(*source_cloud_, &finite_src)) {
+        src = finite_src.empty() ? nullptr : reinterpret_cast<const float*>(finite_src.data());
+        n_src = static_cast<int64_t>(finite_src.size());
+    }
+    check(ppcr_create(src, n_src, tgt, n_tgt, &cp, &handle_), "ppcr_create");
     if (parameters_.target_filter_size > 0) {
         // the reference runs pcl::VoxelGrid on the caller's target cloud in place (registration.cc:34-41)
         int64_t n = 0;

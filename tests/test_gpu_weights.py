@@ -80,6 +80,28 @@ def test_normal_equations_match_host_logic(capi, emu, oracle, dof):
     assert np.max(np.abs(nf - ref)) / scale < 2e-6
 
 
+@pytest.mark.parametrize("dof", [5.0, np.inf])
+def test_normal_equations_match_oracle(capi, oracle, dof):
+    """J^T W J, J^T W r and the cost against the ORACLE's own assembly (analytic Jacobian rows per correspondence, float64,
+    oracle/ppcr_oracle.cpp NormalEqProblem) -- not against a CPU build of the product's headers.  The kernel reaches the same
+    36 numbers through 24 source-point moments; they agree to rounding."""
+    src, tgt, _ = synth.config1_plane_sphere(seed=6, n_plane=2000, n_sphere=1000)
+    idx, _, cnt, _ = oracle.radius_search(src, tgt, 1.0, 20)
+    row_ptr, col = csr_from_rows(idx, cnt)
+    pose_w = np.array([1.0, 0.01, 0.02, -0.01, 0.01, 0.0, 0.02])
+    pose_e = np.array([0.98, 0.03, -0.02, 0.05, 0.03, -0.04, 0.01])
+    ref = oracle.normal_eq(src, tgt, row_ptr, col, dof, pose_w, pose_e)
+    scale_h, scale_g = np.abs(ref[:28]).max(), np.abs(ref[28:35]).max()
+    _, ne = capi.weights_normal_eq(src, tgt, idx, cnt, dof, pose_w, pose_e, want_weights=False)
+    assert np.max(np.abs(ne[:28] - ref[:28])) / scale_h < 1e-11
+    assert np.max(np.abs(ne[28:35] - ref[28:35])) / scale_g < 1e-10  # (the gradient is a sum of cancelling terms)
+    assert abs(ne[35] - ref[35]) / ref[35] < 1e-12
+    _, nf = capi.weights_normal_eq(src, tgt, idx, cnt, dof, pose_w, pose_e, want_weights=False, fast_weights=True)
+    assert np.max(np.abs(nf[:28] - ref[:28])) / scale_h < 2e-6
+    assert np.max(np.abs(nf[28:35] - ref[28:35])) / scale_g < 2e-5
+    assert abs(nf[35] - ref[35]) / ref[35] < 2e-6
+
+
 def test_rows_without_neighbours_contribute_nothing(capi):
     src, tgt, idx, cnt = _golden_fixture()
     cnt0 = np.array([0, 4], dtype=np.int32)

@@ -10,8 +10,14 @@ from probabilistic_point_clouds_registration_b200 import synth
 @pytest.mark.parametrize("dof,radius,kind", [(5.0, 1.0, 0), (np.inf, 1.0, 0), (5.0, 3.0, 1)])
 def test_controller_follows_the_restated_ceres_path(emu, oracle, dof, radius, kind):
     src, tgt, _ = synth.config1_plane_sphere(n_plane=700, n_sphere=500)
+    oracle.nonmonotonic_steps(reset=True)
     ref = oracle.align(src, tgt, oracle.make_params(max_neighbours=20, dof=dof, radius=radius),
                        oracle.make_options(inner_kind=kind), use_grid=False)
+    # Every one of these runs ACCEPTS non-monotonic steps (the weights are refreshed between the evaluation of x and of the
+    # candidate, so the cost often rises on an accepted step).  After such a step Ceres' update_state_every_iteration hands the
+    # callback its lowest-cost iterate, not x (oracle/ppcr_oracle.cpp minimise(), csrc/ppcr_lm.h step_prepare): the lock-step
+    # comparison below only holds if both sides refresh the weights there.
+    assert oracle.nonmonotonic_steps() > 0
     n, hist, stats, moved = emu_align(emu, src, tgt, 20, dof, radius)
     assert n == ref.n_outer
     for a, b in zip(stats, ref.stats):
