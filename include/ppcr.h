@@ -140,6 +140,11 @@ ppcr_status ppcr_time_kernel(ppcr_handle* h, int32_t which, int32_t reps, int32_
  * *n_out = n and out = in when PCL would refuse the leaf size (index overflow). out must hold n points. */
 ppcr_status ppcr_voxel_filter(const float* xyzw, int64_t n, double leaf, float* out_xyzw, int64_t* n_out);
 
+/* Timing of the same filter (bench.py's roofline entry): `reps` runs between two CUDA events after one warm-up run; the
+ * cloud is a host pointer unless options->input_on_device.  *n_out = filtered size (-1: PCL would refuse the leaf). */
+ppcr_status ppcr_time_voxel_filter(const float* xyzw, int64_t n, double leaf, const ppcr_options* options, int32_t reps,
+                                   float* avg_ms, double* algorithmic_bytes, int64_t* n_out);
+
 /* The radius search loop at :72-81 (pcl::KdTreeFLANN::radiusSearch semantics).
  * out_idx/out_d2: [n_src][max_nn], rows sorted ascending by (d2, index); out_count[n_src].
  * leaf_capacity 0 = default; the result does not depend on it. */

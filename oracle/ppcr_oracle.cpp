@@ -34,9 +34,11 @@ constexpr int kNumParams = 7;  // rotation_[4] + translation_[3]  (iteration.hpp
 int resolve_threads(int requested)
 {
 #ifdef _OPENMP
-    int hw = omp_get_max_threads();
-    if (requested <= 0 || requested > hw) return hw;
-    return requested;
+    // <= 0: OpenMP's own default (honours OMP_NUM_THREADS); an explicit request is only capped by the processors there are,
+    // so that a caller can ask for every core even under a launcher that exports OMP_NUM_THREADS=1 (torchrun does)
+    if (requested <= 0) return omp_get_max_threads();
+    const int procs = omp_get_num_procs();
+    return requested > procs ? procs : requested;
 #else
     (void)requested;
     return 1;

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "ppcr_create_ex", "ppcr_destroy", "ppcr_align", "ppcr_has_converged", "ppcr_history", "ppcr_increment_history",
     "ppcr_iteration_stats",
     "ppcr_filtered_source", "ppcr_filtered_target", "ppcr_association", "ppcr_get_stage_times", "ppcr_time_kernel",
-    "ppcr_voxel_filter", "ppcr_radius_search", "ppcr_weights_normal_eq", "ppcr_iteration_solve", "ppcr_transform",
+    "ppcr_voxel_filter", "ppcr_time_voxel_filter", "ppcr_radius_search", "ppcr_weights_normal_eq", "ppcr_iteration_solve", "ppcr_transform",
     "ppcr_replay_metrics", "ppcr_closest_point_metrics",
     "ppcr_align_batch", "ppcr_shard_export", "ppcr_shard_connect",
 ]
@@ -135,6 +135,7 @@ def lib():
         L.ppcr_get_stage_times.argtypes = [vp, C.POINTER(StageTimes)]
         L.ppcr_time_kernel.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_float), C.POINTER(f64)]
         L.ppcr_voxel_filter.argtypes = [vp, i64, f64, vp, C.POINTER(i64)]
+        L.ppcr_time_voxel_filter.argtypes = [vp, i64, f64, C.POINTER(Options), i32, C.POINTER(C.c_float), C.POINTER(f64), C.POINTER(i64)]
         L.ppcr_radius_search.argtypes = [vp, i64, vp, i64, f64, i32, i32, vp, vp, vp]
         L.ppcr_weights_normal_eq.argtypes = [vp, i64, vp, i64, vp, vp, i32, f64, i32, vp, vp, i32, vp, vp]
         L.ppcr_iteration_solve.argtypes = [vp, i64, vp, i64, vp, vp, i32, C.POINTER(Params), C.POINTER(Options), f64, vp, vp, vp]
@@ -328,6 +329,18 @@ def voxel_filter(cloud, leaf):
     n = C.c_int64(0)
     _check(lib().ppcr_voxel_filter(cloud.ctypes.data, len(cloud), float(leaf), out.ctypes.data, C.byref(n)))
     return out[:n.value].copy()
+
+
+def voxel_filter_timed(cloud_ptr, n, leaf, device=0, reps=3):
+    """Average device time of the voxel filter on a DEVICE-resident cloud; dict for bench.py's roofline.kernels."""
+    opt = make_options(device=device, input_on_device=True)
+    ms, by, k = C.c_float(0), C.c_double(0), C.c_int64(0)
+    _check(lib().ppcr_time_voxel_filter(int(cloud_ptr), int(n), float(leaf), C.byref(opt), int(reps), C.byref(ms), C.byref(by),
+                                        C.byref(k)))
+    if k.value < 0:
+        return None
+    return {"avg_ms": ms.value, "algorithmic_bytes": by.value, "gbs": by.value / (ms.value * 1e-3) / 1e9, "leaf": leaf,
+            "n_in": int(n), "n_out": int(k.value)}
 
 
 def radius_search(src, tgt, radius, max_nn, leaf_capacity=0):

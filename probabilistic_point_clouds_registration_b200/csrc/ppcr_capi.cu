@@ -1469,6 +1469,43 @@ ppcr_status ppcr_voxel_filter(const float* xyzw, int64_t n, double leaf, float* 
     });
 }
 
+ppcr_status ppcr_time_voxel_filter(const float* xyzw, int64_t n, double leaf, const ppcr_options* options, int32_t reps,
+                                   float* avg_ms, double* algorithmic_bytes, int64_t* n_out)
+{
+    if (!xyzw || n < 1 || !(leaf > 0) || reps < 1 || !avg_ms) return fail(PPCR_ERR_INVALID, "bad argument");
+    return guarded([&] {
+        ppcr_params prm;
+        ppcr_default_params(&prm);
+        ppcr_options opt;
+        ppcr_default_options(&opt);
+        if (options) opt = *options;
+        Engine E;
+        engine_init(E, prm, &opt);
+        Pair P;
+        DevBuf<float4> in, out;
+        upload_cloud(in, xyzw, n, opt.input_on_device != 0, E.stream);
+        int64_t k = voxel_filter_device(in.p, n, leaf, out, P, E.stream);  // warm-up (allocations)
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+        CK(cudaEventRecord(a, E.stream));
+        for (int r = 0; r < reps; ++r) k = voxel_filter_device(in.p, n, leaf, out, P, E.stream);
+        CK(cudaEventRecord(b, E.stream));
+        CK(cudaStreamSynchronize(E.stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        *avg_ms = ms / static_cast<float>(reps);
+        if (n_out) *n_out = k;
+        // every input point read once, every centroid written once (the sort's own traffic is not algorithmic)
+        if (algorithmic_bytes) *algorithmic_bytes = 16.0 * static_cast<double>(n) + 16.0 * static_cast<double>(std::max<int64_t>(k, 0));
+        in.release();
+        out.release();
+        P.release();
+    });
+}
+
 ppcr_status ppcr_radius_search(const float* src, int64_t n_src, const float* tgt, int64_t n_tgt, double radius,
                                int32_t max_nn, int32_t leaf_capacity, int32_t* out_idx, float* out_d2, int32_t* out_count)
 {

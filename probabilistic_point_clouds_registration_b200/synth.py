@@ -84,16 +84,16 @@ _HALF = 30.0
 _CEIL = _GROUND_Z + 20.0
 
 
-def _ray_box(o, d, lo, hi):
-    """Slab test, vectorised over rays; returns entry distance (inf if missed)."""
-    with np.errstate(divide="ignore", invalid="ignore"):
-        inv = 1.0 / d
-        t0 = (lo - o) * inv
-        t1 = (hi - o) * inv
-    tmin = np.minimum(t0, t1)
-    tmax = np.maximum(t0, t1)
-    tn = np.nanmax(tmin, axis=1)
-    tf = np.nanmin(tmax, axis=1)
+def _ray_box(o, inv, lo, hi):
+    """Slab test, vectorised over rays (inv = 1 / direction, [N,3]); returns the entry distance (inf if missed).
+    NaN slabs (0 * inf: a ray parallel to a face it starts on) are ignored like nanmax / nanmin would."""
+    tn = tf = None
+    for ax in range(3):
+        t0 = (lo[ax] - o[ax]) * inv[:, ax]
+        t1 = (hi[ax] - o[ax]) * inv[:, ax]
+        a, b = np.minimum(t0, t1), np.maximum(t0, t1)
+        tn = a if tn is None else np.fmax(tn, a)
+        tf = b if tf is None else np.fmin(tf, b)
     hit = (tf >= tn) & (tn > 0.05)
     return np.where(hit, tn, np.inf)
 
@@ -116,10 +116,12 @@ def lidar_scan(rng, n_rings, n_az, pose=None, range_noise=0.02):
         for ax, lim in ((0, _HALF), (0, -_HALF), (1, _HALF), (1, -_HALF), (2, _CEIL)):
             tw = (lim - o[ax]) / d[:, ax]
             t = np.where((tw > 0) & np.isfinite(tw), np.minimum(t, tw), t)
-    for cx, cy, hx, hy, h in _OBSTACLES:
-        lo = np.array([cx - hx, cy - hy, _GROUND_Z])
-        hi = np.array([cx + hx, cy + hy, _GROUND_Z + h])
-        t = np.minimum(t, _ray_box(o[None, :], d, lo[None, :], hi[None, :]))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = 1.0 / d
+        for cx, cy, hx, hy, h in _OBSTACLES:
+            lo = np.array([cx - hx, cy - hy, _GROUND_Z])
+            hi = np.array([cx + hx, cy + hy, _GROUND_Z + h])
+            t = np.minimum(t, _ray_box(o, inv, lo, hi))
     t = t + rng.normal(scale=range_noise, size=t.shape)
     return d_s * t[:, None]
 
