@@ -522,7 +522,14 @@ __global__ void PPCR_SEARCH_BOUNDS k_search(const PairDev* __restrict__ pairs)
 // A query whose tasks or candidates overflow the queues is searched by tree_search with the heap, as in k_search; a chunk in
 // which most queries expect to (the cloud moved by more than the neighbour spacing) is walked with heaps as a whole.  The
 // neighbour sets are identical to k_search's: same distance arithmetic, same strict radius test, same (distance, index) order.
-constexpr int kQTaskPerQuery = 64;               // leaves one query may queue; beyond that it is searched by tree_search
+// Leaves one query may queue before it falls back to tree_search.  It used to be 64, which looked harmless (5.6 leaves per query
+// on average) and was not: while the pose is still off, about one query per few blocks sits 0.4 m from a dense surface and its
+// bound touches 70-300 leaf cubes (a thick shell of small cells, nearly all of them without a point inside the bound).  Such a
+// query then walked that shell ALONE with a heap -- 130 us on one thread with 127 waiting at the barrier -- and the blocks that
+// drew one finished at 540 us when every other block was done at 350: a third of the in-loop search time was that tail
+// (per-block globaltimer stamps, -DPPCR_Q_PROFILE).  Through the task queue the same leaves are 2-3 rounds of phase B for the
+// whole block.  The cap that remains is the block's queue (kQTaskCap).
+constexpr int kQTaskPerQuery = 4096;
 constexpr int kQTaskCap = 8192;                  // leaf tasks per block of 128 queries (64 per query on average)
 // candidate positions per query.  128 for max_neighbours = 20 was tried: one 120k-point pair 6.2 -> 6.0 ms, but a batch of them
 // 403 -> 344 pairs/s (the slabs of six lanes crowd L2), so 64 for every m; PPCR_Q_CAND overrides it (tuning)
@@ -608,6 +615,9 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
     int cnt_total = 0;
 #if defined(PPCR_Q_PROFILE)
     long long t_phase[4] = {0, 0, 0, 0}, t_mark = clock64();
+    unsigned long long g_begin;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_begin));
+    int n_chunks_done = 0, n_heavy_chunks = 0;
     long long n_task_sum = 0, n_fall = 0, n_fall_task = 0;
 #define PPCR_Q_MARK(ph) { const long long now = clock64(); t_phase[ph] += now - t_mark; t_mark = now; }
 #else
@@ -669,6 +679,9 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
         // A chunk made mostly of heavy queries is searched the way k_search does it -- every thread walks with its heap and
         // lets the bound shrink as candidates arrive -- because the fixed bound would push them all through the fallback.
         if (__syncthreads_count(heavy) * 2 > kSearchThreads) {
+#if defined(PPCR_Q_PROFILE)
+            ++n_heavy_chunks;
+#endif
             if (dead) {
                 nbr_cnt[i] = 0;
                 nbr_kth[i] = kInf;
@@ -707,6 +720,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
         __syncthreads();
         PPCR_Q_MARK(1)
 #if defined(PPCR_Q_PROFILE)
+        ++n_chunks_done;
         n_task_sum += n_tasks;
         {
             const int n_cold = __syncthreads_count(valid && bound0 >= r2f);
@@ -732,10 +746,23 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
                 for (int s = 0; s < n; ++s) search_store(out, i, cnt++, s_heap[threadIdx.x + s * kSearchThreads]);
                 if (kk != kKeyInf) kth = key_d2(kk);
             } else {
+                // The list overflowed (or a queue did): this thread searches its query alone, 127 others waiting.  What the list does
+                // hold are DISTINCT targets within the radius, so when there are m of them their m-th smallest distance bounds the
+                // true one -- and it is tight (a sample of a far larger candidate set), where the bound the query came in with was
+                // loose enough to overflow the list.  The walk then opens a handful of leaves instead of the hundreds the loose
+                // bound touches (it was 130 us of a 350 us block; -DPPCR_Q_PROFILE).
+                float bound1 = bound0;
+                const int have = min(n_c, q_cand);
+                if (have >= m) {
+                    unsigned long long kk;
+                    const QCand at{s_cand + threadIdx.x};
+                    select_candidates<kSearchThreads>(tgt_sorted, at, have, m, q.x, q.y, q.z, s_heap + threadIdx.x, &kk);
+                    if (kk != kKeyInf) bound1 = fminf(bound1, key_d2(kk));
+                }
                 HeapList<kSearchThreads, 0> L;
                 L.k = s_heap + threadIdx.x;
                 L.init(m);
-                tree_search(geom, nodes, tgt_sorted, q.x, q.y, q.z, r2f, bound0, L, stack);
+                tree_search(geom, nodes, tgt_sorted, q.x, q.y, q.z, r2f, bound1, L, stack);
                 for (int s = 0; s < m; ++s) {
                     const unsigned long long key = L.k[s * kSearchThreads];
                     if (key != kKeyInf) search_store(out, i, cnt++, key);
@@ -761,9 +788,12 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
     atomicAdd(&s_prof[0], static_cast<int>(n_fall));
     atomicAdd(&s_prof[1], static_cast<int>(n_fall_task));
     __syncthreads();
-    if (threadIdx.x == 0 && (blockIdx.x % 97) == 0)
-        printf("[k_search_q block %d] cycles A %lld B %lld C %lld idle %lld; tasks %lld; fallbacks %d (task-queue overflow %d)\n", blockIdx.x,
-               t_phase[0], t_phase[1], t_phase[2], t_phase[3], n_task_sum, s_prof[0], s_prof[1]);
+    unsigned long long g_end;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+    if (threadIdx.x == 0 && ((blockIdx.x % 197) == 0 || s_prof[0] > 0 || n_heavy_chunks > 0 || (g_end - g_begin) > 450000ull))
+        printf("[k_search_q block %d] cycles A %lld B %lld C %lld idle %lld; tasks %lld; fallbacks %d (task-queue overflow %d); chunks %d heavy %d; "
+               "globaltimer begin %llu end %llu (%.1f us)\n", blockIdx.x, t_phase[0], t_phase[1], t_phase[2], t_phase[3], n_task_sum, s_prof[0],
+               s_prof[1], n_chunks_done, n_heavy_chunks, g_begin % 100000000ull, g_end % 100000000ull, (g_end - g_begin) * 1e-3);
 #endif
     for (int o = 16; o > 0; o >>= 1) cnt_total += __shfl_xor_sync(kFull, cnt_total, o);
     if ((threadIdx.x & 31) == 0 && cnt_total)

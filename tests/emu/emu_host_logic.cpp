@@ -109,6 +109,7 @@ void eval(const Cloud& src, const Cloud& tgt, const std::vector<int>& idx, const
 
 #if defined(PPCR_TREE_STATS)
 static std::vector<float> g_query_cost;
+static std::vector<int> g_query_opens, g_query_leaves;
 #endif
 
 extern "C" {
@@ -262,6 +263,8 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
     std::vector<unsigned long long> buf(static_cast<size_t>(heap_slots(std::max(m, 1))));
 #if defined(PPCR_TREE_STATS)
     g_query_cost.assign(static_cast<size_t>(n_src), 0.f);
+    g_query_opens.assign(static_cast<size_t>(n_src), 0);
+    g_query_leaves.assign(static_cast<size_t>(n_src), 0);
 #endif
     for (int64_t i = 0; i < n_src; ++i) {
         const float* q = src_xyzw + 4 * i;
@@ -272,13 +275,17 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
         struct CostNote {
             const TreeStats& b;
             float& out;
+            int& opens;
+            int& leaves;
             ~CostNote()
             {
+                opens = static_cast<int>(g_tree_stats.opens - b.opens);
+                leaves = static_cast<int>(g_tree_stats.leaves - b.leaves);
                 // rough thread-instruction weights of the search kernel (profiles/): open, scanned point, survivor, insertion
                 out = 120.f * (g_tree_stats.opens - b.opens) + 14.f * (g_tree_stats.points - b.points) +
                       25.f * (g_tree_stats.survivors - b.survivors) + 65.f * (g_tree_stats.inserts - b.inserts) + 300.f;
             }
-        } note{before, g_query_cost[static_cast<size_t>(i)]};
+        } note{before, g_query_cost[static_cast<size_t>(i)], g_query_opens[static_cast<size_t>(i)], g_query_leaves[static_cast<size_t>(i)]};
 #endif
         auto take = [&](const unsigned long long* k, int cap) {
             for (int s2 = 0; s2 < cap; ++s2) {
@@ -339,10 +346,19 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
                 if ((kth != kKeyInf) != (cnt == m) || (cnt == m && kth != *std::max_element(found.begin(), found.end())))
                     return -1;
             } else {
+                // the kernel's overflow path: the qcap candidates the list holds are distinct targets within the radius, so the
+                // m-th smallest of their distances bounds the true one; the heap walk then starts from that (tight) bound
+                float bound1 = bound0;
+                if (qcap >= m) {
+                    unsigned long long kth = 0;
+                    auto at = [&](int c) { return static_cast<int>(cand[static_cast<size_t>(c)]); };
+                    select_candidates<1>(pts.data(), at, qcap, m, q[0], q[1], q[2], buf.data(), &kth);
+                    if (kth != kKeyInf && key_d2(kth) < bound1) bound1 = key_d2(kth);
+                }
                 HeapList<1> L;
                 L.k = buf.data();
                 L.init(m);
-                tree_search(g, nodes.data(), pts.data(), q[0], q[1], q[2], r2f, bound0, L, stack);
+                tree_search(g, nodes.data(), pts.data(), q[0], q[1], q[2], r2f, bound1, L, stack);
                 for (int s2 = L.begin(); s2 < L.end(); ++s2)
                     if (buf[s2] != kKeyInf) found.push_back(buf[s2]);
             }
@@ -401,6 +417,13 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
 void emu_tree_costs(float* out, long long n)
 {
     for (long long i = 0; i < n && i < static_cast<long long>(g_query_cost.size()); ++i) out[i] = g_query_cost[static_cast<size_t>(i)];
+}
+void emu_tree_per_query(int* opens, int* leaves, long long n)
+{
+    for (long long i = 0; i < n && i < static_cast<long long>(g_query_opens.size()); ++i) {
+        opens[i] = g_query_opens[static_cast<size_t>(i)];
+        leaves[i] = g_query_leaves[static_cast<size_t>(i)];
+    }
 }
 void emu_tree_stats(long long* out7, int reset)
 {

@@ -32,9 +32,15 @@ gen_s = time.perf_counter() - t0
 params = capi.make_params(max_neighbours=10, radius=0.5, dof=5.0)
 lo, hi = multi.slice_bounds(len(src), rank, world)
 # clouds resident in HBM, like bench.py's `value`
-d_src = torch.from_numpy(src[lo:hi]).cuda()
+if os.environ.get("SHARD_STRIDED"):
+    mine = np.ascontiguousarray(src[rank::world])
+    lo, hi = 0, len(mine)
+    d_src = torch.from_numpy(mine).cuda()
+else:
+    d_src = torch.from_numpy(src[lo:hi]).cuda()
 d_tgt = torch.from_numpy(tgt).cuda()
-opt = capi.make_options(device=local, input_on_device=True)
+stages = bool(os.environ.get("SHARD_STAGES"))
+opt = capi.make_options(device=local, input_on_device=True, driver=1 if stages else 0, record_stage_times=stages)
 times = []
 for rep in range(reps + 1):
     if world > 1:
@@ -46,8 +52,13 @@ for rep in range(reps + 1):
         reg.align()
         stats = reg.iteration_stats()
         hist = reg.transformation_history()
+        if stages:
+            lt = reg.stage_times()
+            print(f"[rank {rank}] rep {rep}: search {lt.search_ms:.1f} ms in {lt.search_launches} launches, eval {lt.eval_ms:.1f} ms in "
+                  f"{lt.eval_launches} launches, K local {sum(s['n_correspondences'] for s in stats)}", flush=True)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    print(f"[rank {rank}] rep {rep}: {1e3 * dt:.1f} ms", flush=True)
     if world > 1:
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
