@@ -221,15 +221,24 @@ ppcr_status ppcr_align_batch(const ppcr_pair* pairs, int32_t n_pairs, const ppcr
                              const ppcr_options* options, int32_t slots, double* out_T, int32_t* out_n_outer,
                              int64_t* out_corr);
 
+/* The same over several GPUs of one process (device_ids[], n_dev): `slots` lanes on EVERY listed device, all
+ * drawing pairs from one counter -- no exchange between devices, results land in the caller's arrays by pair index.  Pair buffers
+ * must be host pointers when n_dev > 1 (options->device and options->stream are ignored then). */
+ppcr_status ppcr_align_batch_devices(const ppcr_pair* pairs, int32_t n_pairs, const ppcr_params* params,
+                                     const ppcr_options* options, const int32_t* device_ids, int32_t n_dev, int32_t slots,
+                                     double* out_T, int32_t* out_n_outer, int64_t* out_corr);
+
 /* ---- one pair sharded over several GPUs (new surface) --------------------------------------------------- */
 
 /* Every rank passes ITS slice of the source and the whole target.  The per-iteration exchange is a 32-double
  * all-reduce written straight into the peers' mailboxes over NVLink from inside the reduction kernel.
- * Call order on every rank: ppcr_create_ex -> ppcr_shard_export -> (exchange the 64-byte tokens out of band,
- * e.g. torch.distributed.all_gather) -> ppcr_shard_connect -> ppcr_align. */
-#define PPCR_SHARD_TOKEN_BYTES 64
+ * Call order on every rank: ppcr_create_ex -> ppcr_shard_export -> (exchange the tokens out of band,
+ * e.g. torch.distributed.all_gather) -> ppcr_shard_connect -> ppcr_align.  The ranks may be processes (one per GPU: the
+ * mailboxes are mapped over CUDA IPC) or host threads of one process (one per GPU: plain peer access).  The mailbox of a device
+ * and the mappings of its peers are made once per process and re-used by every later sharded handle. */
+#define PPCR_SHARD_TOKEN_BYTES 128
 ppcr_status ppcr_shard_export(ppcr_handle* h, int32_t rank, int32_t world, uint8_t* token_out);
-ppcr_status ppcr_shard_connect(ppcr_handle* h, const uint8_t* tokens_world_x_64);
+ppcr_status ppcr_shard_connect(ppcr_handle* h, const uint8_t* tokens /* [world][PPCR_SHARD_TOKEN_BYTES], rank order */);
 
 #ifdef __cplusplus
 }

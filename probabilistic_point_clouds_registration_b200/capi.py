@@ -21,10 +21,10 @@ EXPORTED_SYMBOLS = [
     "ppcr_filtered_source", "ppcr_filtered_target", "ppcr_association", "ppcr_get_stage_times", "ppcr_time_kernel",
     "ppcr_voxel_filter", "ppcr_time_voxel_filter", "ppcr_radius_search", "ppcr_weights_normal_eq", "ppcr_iteration_solve", "ppcr_transform",
     "ppcr_replay_metrics", "ppcr_closest_point_metrics",
-    "ppcr_align_batch", "ppcr_shard_export", "ppcr_shard_connect",
+    "ppcr_align_batch", "ppcr_align_batch_devices", "ppcr_shard_export", "ppcr_shard_connect",
 ]
 
-SHARD_TOKEN_BYTES = 64
+SHARD_TOKEN_BYTES = 128
 
 
 class PpcrError(RuntimeError):
@@ -143,6 +143,7 @@ def lib():
         L.ppcr_replay_metrics.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
         L.ppcr_closest_point_metrics.argtypes = [vp, i64, vp, i64, f64, C.POINTER(Options), C.POINTER(ClosestMetrics), vp]
         L.ppcr_align_batch.argtypes = [C.POINTER(PairDesc), i32, C.POINTER(Params), C.POINTER(Options), i32, vp, vp, vp]
+        L.ppcr_align_batch_devices.argtypes = [C.POINTER(PairDesc), i32, C.POINTER(Params), C.POINTER(Options), vp, i32, i32, vp, vp, vp]
         L.ppcr_shard_export.argtypes = [vp, i32, i32, vp]
         L.ppcr_shard_connect.argtypes = [vp, vp]
         for name in EXPORTED_SYMBOLS:
@@ -407,9 +408,10 @@ def closest_point_metrics(cloud1, cloud2, factor=3.0, options: Options | None = 
     return {name: getattr(out, name) for name, _ in ClosestMetrics._fields_}, (d2[:len(a)] if d2 is not None else None)
 
 
-def align_batch(pairs, params: Params, options: Options | None = None, slots=0):
+def align_batch(pairs, params: Params, options: Options | None = None, slots=0, devices=None):
     """pairs: list of (source, target) numpy clouds (or (src_ptr, n_src, tgt_ptr, n_tgt) device tuples when
-    options.input_on_device).  Returns (T [n,4,4], n_outer [n], correspondences [n])."""
+    options.input_on_device).  devices: list of device ordinals (ppcr_align_batch_devices: `slots` lanes on each).
+    Returns (T [n,4,4], n_outer [n], correspondences [n])."""
     n = len(pairs)
     descs = (PairDesc * max(n, 1))()
     keep = []
@@ -423,6 +425,12 @@ def align_batch(pairs, params: Params, options: Options | None = None, slots=0):
     T = np.zeros((max(n, 1), 16))
     n_outer = np.zeros(max(n, 1), dtype=np.int32)
     corr = np.zeros(max(n, 1), dtype=np.int64)
-    _check(lib().ppcr_align_batch(descs, n, C.byref(params), C.byref(options) if options is not None else None,
-                                  int(slots), T.ctypes.data, n_outer.ctypes.data, corr.ctypes.data))
+    popt = C.byref(options) if options is not None else None
+    if devices is None:
+        _check(lib().ppcr_align_batch(descs, n, C.byref(params), popt, int(slots), T.ctypes.data, n_outer.ctypes.data,
+                                      corr.ctypes.data))
+    else:
+        ids = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        _check(lib().ppcr_align_batch_devices(descs, n, C.byref(params), popt, ids, len(devices), int(slots), T.ctypes.data,
+                                              n_outer.ctypes.data, corr.ctypes.data))
     return T[:n].reshape(n, 4, 4), n_outer[:n], corr[:n]

@@ -18,9 +18,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unistd.h>
 #include <vector>
 
 #include "ppcr_kernels.cuh"
@@ -179,7 +181,7 @@ struct Pair {
     DevBuf<unsigned> sort_vals[2];
     DevBuf<unsigned char> sort_tmp;
     DevBuf<float> nbr_d2, nbr_kth;
-    DevBuf<double> partials, history, mailbox;
+    DevBuf<double> partials, history;
     DevBuf<PairState> state;
     DevBuf<Config> cfg;
     DevBuf<IterStats> stats;
@@ -195,7 +197,7 @@ struct Pair {
         nodes.release(); tree_counters.release(); sort_keys[0].release(); sort_keys[1].release();
         sort_vals[0].release(); sort_vals[1].release(); sort_tmp.release(); nbr_pos.release(); inv_perm.release(); group_ticket.release(); nbr_cnt.release();
         scan_sums.release(); nbr_d2.release(); nbr_kth.release();
-        partials.release(); history.release(); mailbox.release(); state.release(); cfg.release(); stats.release();
+        partials.release(); history.release(); state.release(); cfg.release(); stats.release();
         scratch_u.release(); scratch_ull.release();
     }
 };
@@ -237,7 +239,6 @@ struct Engine {
     ppcr_stage_times times{};
     // sharded mode
     int rank = 0, world = 1;
-    std::vector<void*> peer_ptrs;
     // L2 flush buffer for ppcr_time_kernel
     DevBuf<float4> flush;
 
@@ -251,8 +252,6 @@ struct Engine {
         }
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (graph) cudaGraphDestroy(graph);
-        for (size_t r = 0; r < peer_ptrs.size(); ++r)
-            if (peer_ptrs[r] && static_cast<int>(r) != rank) cudaIpcCloseMemHandle(peer_ptrs[r]);
         for (auto& p : pairs) p.release();
         d_pairs.release();
         d_loop.release();
@@ -267,6 +266,31 @@ struct Engine {
 struct ppcr_handle {
     Engine eng;
 };
+
+// ---- sharded pairs: the mailboxes of the moment exchange live as long as the process ----
+// One small cudaMalloc block per device, exported over CUDA IPC once; the mappings of the peers' blocks are kept too.  A
+// sharded handle therefore costs no allocation, no IPC open and no implicit device synchronisation (allocating, exporting and
+// mapping per handle was where one repetition in eight of the 10M-point pair lost 100-300 ms).
+struct ShardToken {  // what ppcr_shard_export hands out (PPCR_SHARD_TOKEN_BYTES, zero padded)
+    cudaIpcMemHandle_t ipc;
+    uint64_t pid;     // a peer in the same process uses `ptr` directly (cudaIpcOpenMemHandle refuses the exporting process)
+    uint64_t ptr;
+    int32_t device;
+    uint32_t epoch;   // proposed stamp epoch
+};
+static_assert(sizeof(ShardToken) <= PPCR_SHARD_TOKEN_BYTES, "token size");
+constexpr size_t kMailboxDoubles = 2ull * 8 * kMailDoubles;  // two alternating slots x up to 8 ranks
+struct DeviceMailbox {
+    double* p = nullptr;
+    cudaIpcMemHandle_t ipc{};
+};
+struct ShardGlobals {
+    std::mutex mu;
+    DeviceMailbox box[64];
+    std::map<std::string, void*> opened;  // peer mailboxes of other processes, by IPC handle bytes
+    uint32_t epoch = 0;
+};
+static ShardGlobals g_shard;
 
 // ------------------------------------------------------------------------------------------------------------
 // device selection
@@ -661,6 +685,7 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     CK(cudaMemcpyAsync(P.state.p, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
     D.dump_w = nullptr;
     D.mailbox = nullptr;
+    D.mail_base = 0.0;
     D.rank = 0;
     D.world = 1;
     D.spin_limit = 4000000000ll;  // ~2 s of SM clocks
@@ -713,6 +738,7 @@ static void engine_commit(Engine& E)
         E.pairs[p].dev.search_queued = queued ? 1 : 0;
         E.pairs[p].dev.q_cand = getenv("PPCR_Q_CAND") ? atoi(getenv("PPCR_Q_CAND")) : search_q_cand(E.params.max_neighbours);
         E.pairs[p].dev.q_heavy = getenv("PPCR_Q_HEAVY") ? static_cast<float>(atof(getenv("PPCR_Q_HEAVY"))) : 0.75f;  // (tuning)
+        E.pairs[p].dev.q_leaves = getenv("PPCR_Q_LEAVES") ? atoi(getenv("PPCR_Q_LEAVES")) : kQTaskPerQuery;
         host[p] = E.pairs[p].dev;
         max_m = std::max(max_m, host[p].m);
         max_src = std::max<long long>(max_src, host[p].n_src);
@@ -958,7 +984,7 @@ static void run_to_completion(Engine& E)
     CK(cudaGetLastError());
     E.times.total_launches += 1;
     const bool rec = E.opts.record_stage_times != 0;
-    bool use_graph = (E.opts.driver == 2) || (E.opts.driver == 0 && !rec && E.world == 1);
+    bool use_graph = (E.opts.driver == 2) || (E.opts.driver == 0 && !rec);
     Trace tr(E.stream);
     if (use_graph) use_graph = build_graph(E);
     tr.mark("graph build");
@@ -1799,20 +1825,25 @@ ppcr_status ppcr_closest_point_metrics(const float* cloud1, int64_t n1, const fl
 
 // ---- batch ---------------------------------------------------------------------------------------------------
 
-ppcr_status ppcr_align_batch(const ppcr_pair* pairs, int32_t n_pairs, const ppcr_params* params,
-                             const ppcr_options* options, int32_t slots, double* out_T, int32_t* out_n_outer,
-                             int64_t* out_corr)
+ppcr_status ppcr_align_batch_devices(const ppcr_pair* pairs, int32_t n_pairs, const ppcr_params* params,
+                                     const ppcr_options* options, const int32_t* device_ids, int32_t n_dev, int32_t slots,
+                                     double* out_T, int32_t* out_n_outer, int64_t* out_corr)
 {
-    if (!pairs || n_pairs < 0 || !params || !out_T) return fail(PPCR_ERR_INVALID, "bad argument");
+    if (!pairs || n_pairs < 0 || !params || !out_T || !device_ids || n_dev < 1) return fail(PPCR_ERR_INVALID, "bad argument");
+    if (n_dev > 1 && options && options->input_on_device)
+        return fail(PPCR_ERR_INVALID, "device-resident pair buffers belong to one device: pass host buffers to a multi-device batch");
     return guarded([&] {
         if (n_pairs == 0) return;
         // `slots` lanes, each a host thread with its own engine and stream, pull pairs from a shared counter: the set-up
         // of one pair (upload, sorts, tree build) overlaps the iterations of the others, a 120k-point pair does not fill
         // 148 SMs on its own, and a lane that draws a pair needing few outer iterations moves on at once.
+        // With several devices every device gets `slots` lanes and all lanes draw from the same counter: the pairs are dealt
+        // dynamically, no device waits for another's block of the batch, and there is no exchange between them.
         if (slots <= 0) slots = 6;
-        const int lanes = std::min(slots, n_pairs);
+        const int lanes = static_cast<int>(std::min<long long>(static_cast<long long>(slots) * n_dev, n_pairs));
         ppcr_options lane_opt;
         if (options) lane_opt = *options; else ppcr_default_options(&lane_opt);
+        if (n_dev > 1) lane_opt.stream = nullptr;  // a stream belongs to one device
         if (lane_opt.stream && lanes > 1) {
             // device-resident inputs were produced on the caller's stream: wait for them, then use one stream per lane
             CK(cudaSetDevice(lane_opt.device));
@@ -1822,10 +1853,12 @@ ppcr_status ppcr_align_batch(const ppcr_pair* pairs, int32_t n_pairs, const ppcr
         std::atomic<int> next{0};
         std::mutex err_mutex;
         StatusError first_error{PPCR_OK, ""};
-        auto lane = [&]() {
+        auto lane = [&](int lane_index) {
             try {
                 Engine E;
-                engine_init(E, *params, &lane_opt);
+                ppcr_options my_opt = lane_opt;
+                my_opt.device = device_ids[lane_index % n_dev];  // lanes interleave over the devices
+                engine_init(E, *params, &my_opt);
                 E.pairs.resize(1);
                 const bool on_dev = E.opts.input_on_device != 0;
                 for (;;) {
@@ -1861,14 +1894,22 @@ ppcr_status ppcr_align_batch(const ppcr_pair* pairs, int32_t n_pairs, const ppcr
             }
         };
         if (lanes == 1) {
-            lane();
+            lane(0);
         } else {
             std::vector<std::thread> threads;
-            for (int t = 0; t < lanes; ++t) threads.emplace_back(lane);
+            for (int t = 0; t < lanes; ++t) threads.emplace_back(lane, t);
             for (auto& t : threads) t.join();
         }
         if (first_error.code != PPCR_OK) throw first_error;
     });
+}
+
+ppcr_status ppcr_align_batch(const ppcr_pair* pairs, int32_t n_pairs, const ppcr_params* params,
+                             const ppcr_options* options, int32_t slots, double* out_T, int32_t* out_n_outer,
+                             int64_t* out_corr)
+{
+    const int32_t device = options ? options->device : 0;
+    return ppcr_align_batch_devices(pairs, n_pairs, params, options, &device, 1, slots, out_T, out_n_outer, out_corr);
 }
 
 // ---- sharded pair -------------------------------------------------------------------------------------------
@@ -1877,20 +1918,30 @@ ppcr_status ppcr_shard_export(ppcr_handle* h, int32_t rank, int32_t world, uint8
 {
     if (!h || !token_out || world < 1 || world > 8 || rank < 0 || rank >= world) return fail(PPCR_ERR_INVALID, "bad argument");
     return guarded([&] {
-        static_assert(sizeof(cudaIpcMemHandle_t) <= PPCR_SHARD_TOKEN_BYTES, "token size");
         Engine& E = h->eng;
         use_engine(E);
-        Pair& P = E.pairs[0];
         E.rank = rank;
         E.world = world;
-        // a dedicated allocation: IPC handles cover whole cudaMalloc blocks
-        P.mailbox.plain = true;
-        P.mailbox.reserve(2ull * 8 * kMailDoubles);
-        CK(cudaMemset(P.mailbox.p, 0, P.mailbox.cap * sizeof(double)));
-        cudaIpcMemHandle_t mh;
-        CK(cudaIpcGetMemHandle(&mh, P.mailbox.p));
+        ShardToken tok{};
+        {
+            std::lock_guard<std::mutex> lock(g_shard.mu);
+            DeviceMailbox& M = g_shard.box[E.device];
+            if (!M.p) {
+                // a dedicated allocation (IPC handles cover whole cudaMalloc blocks), made once per device and process:
+                // every later sharded handle on this device re-uses it, and the peers keep their mapping of it
+                CK(cudaMalloc(&M.p, kMailboxDoubles * sizeof(double)));
+                CK(cudaMemset(M.p, 0, kMailboxDoubles * sizeof(double)));
+                CK(cudaDeviceSynchronize());
+                CK(cudaIpcGetMemHandle(&M.ipc, M.p));
+            }
+            tok.ipc = M.ipc;
+            tok.pid = static_cast<uint64_t>(getpid());
+            tok.ptr = reinterpret_cast<uint64_t>(M.p);
+            tok.device = E.device;
+            tok.epoch = g_shard.epoch + 1;  // proposal; the group takes the largest
+        }
         memset(token_out, 0, PPCR_SHARD_TOKEN_BYTES);
-        memcpy(token_out, &mh, sizeof(mh));
+        memcpy(token_out, &tok, sizeof(tok));
     });
 }
 
@@ -1901,21 +1952,45 @@ ppcr_status ppcr_shard_connect(ppcr_handle* h, const uint8_t* tokens)
         Engine& E = h->eng;
         use_engine(E);
         Pair& P = E.pairs[0];
-        if (!P.mailbox.p) throw StatusError{PPCR_ERR_INVALID, "call ppcr_shard_export first"};
-        E.peer_ptrs.assign(E.world, nullptr);
+        std::lock_guard<std::mutex> lock(g_shard.mu);
+        DeviceMailbox& M = g_shard.box[E.device];
+        if (!M.p) throw StatusError{PPCR_ERR_INVALID, "call ppcr_shard_export first"};
+        uint32_t epoch = 0;
+        for (int r = 0; r < 8; ++r) P.dev.peer_mailbox[r] = nullptr;
         for (int r = 0; r < E.world; ++r) {
+            ShardToken tok;
+            memcpy(&tok, tokens + static_cast<size_t>(r) * PPCR_SHARD_TOKEN_BYTES, sizeof(tok));
+            epoch = std::max(epoch, tok.epoch);
             if (r == E.rank) {
-                E.peer_ptrs[r] = P.mailbox.p;
+                P.dev.peer_mailbox[r] = M.p;
+            } else if (tok.pid == static_cast<uint64_t>(getpid())) {
+                // a rank of this very process (one host thread per device): plain peer access, no IPC
+                if (tok.device != E.device) {
+                    int can = 0;
+                    CK(cudaDeviceCanAccessPeer(&can, E.device, tok.device));
+                    if (!can) throw StatusError{PPCR_ERR_UNSUPPORTED, "the devices of a sharded pair need peer access to each other"};
+                    const cudaError_t e = cudaDeviceEnablePeerAccess(tok.device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+                    cudaGetLastError();
+                }
+                P.dev.peer_mailbox[r] = reinterpret_cast<double*>(tok.ptr);
             } else {
-                cudaIpcMemHandle_t mh;
-                memcpy(&mh, tokens + static_cast<size_t>(r) * PPCR_SHARD_TOKEN_BYTES, sizeof(mh));
-                void* ptr = nullptr;
-                CK(cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess));
-                E.peer_ptrs[r] = ptr;
+                // another process: map its mailbox once, keep the mapping for the life of this process
+                const std::string key(reinterpret_cast<const char*>(&tok.ipc), sizeof(tok.ipc));
+                auto it = g_shard.opened.find(key);
+                if (it == g_shard.opened.end()) {
+                    void* ptr = nullptr;
+                    CK(cudaIpcOpenMemHandle(&ptr, tok.ipc, cudaIpcMemLazyEnablePeerAccess));
+                    it = g_shard.opened.emplace(key, ptr).first;
+                }
+                P.dev.peer_mailbox[r] = static_cast<double*>(it->second);
             }
         }
-        P.dev.mailbox = P.mailbox.p;
-        for (int r = 0; r < 8; ++r) P.dev.peer_mailbox[r] = r < E.world ? static_cast<double*>(E.peer_ptrs[r]) : nullptr;
+        // Stamps must be new to every mailbox of the group although the mailboxes outlive the handles: the group adopts the
+        // largest proposal (every rank sees the same tokens, so the same value) and every rank's counter moves up to it.
+        g_shard.epoch = std::max(g_shard.epoch, epoch);
+        P.dev.mailbox = M.p;
+        P.dev.mail_base = static_cast<double>(epoch) * kMailEpochStride;
         P.dev.rank = E.rank;
         P.dev.world = E.world;
         engine_commit(E);

@@ -57,6 +57,7 @@ constexpr int kEvalStages = PPCR_EVAL_STAGES;  // staged tiles per block
 constexpr int kFoldGroup = 16;    // blocks per first-level group of the moment reduction
 constexpr int kFoldChains = 4;    // interleaved chains of the second level
 constexpr int kMailDoubles = 32;  // 24 moments + K + sequence stamp, padded
+constexpr double kMailEpochStride = 67108864.0;  // 2^26 ticks per stamp epoch (mailboxes outlive handles; a handle's ticks stay far below)
 constexpr unsigned kFull = 0xffffffffu;
 
 struct PairDev {
@@ -73,6 +74,7 @@ struct PairDev {
     int search_queued;  // 1: searches that follow a cloud move are k_search_q's, k_search only does the first of an align()
     int q_cand;                // k_search_q: candidate positions per query (search_q_cand(max_neighbours))
     float q_heavy;             // k_search_q: a query expecting more than q_heavy * q_cand candidates counts as heavy
+    int q_leaves;              // k_search_q: leaves one query may queue before it falls back to tree_search (kQTaskPerQuery)
     unsigned char* q_scratch;  // k_search_q's task / candidate queues: one slab per block of its grid (all pairs share the pointer)
     float r2f;      // float(radius * radius): strict membership bound (FLANN)
     int* nbr_pos;   // [m][n_pad] slot-major association: positions in tgt_sorted
@@ -95,6 +97,7 @@ struct PairDev {
     // sharded mode: mailbox exchange of the moment vector between ranks
     double* mailbox;          // [world][kMailDoubles] on THIS device, written by the peers
     double* peer_mailbox[8];  // the same buffer on every rank (peer-mapped), indexed by rank
+    double mail_base;         // this handle's stamp epoch * kMailEpochStride: stamps are mail_base + tick number
     int rank, world;
     long long spin_limit;
 };
@@ -547,19 +550,26 @@ PPCR_HD constexpr size_t search_q_smem(int m)
 }
 PPCR_HD constexpr size_t search_q_scratch_per_block(int q_cand) { return 4u * kQTaskCap + 4u * kSearchThreads * static_cast<size_t>(q_cand); }
 
+constexpr uint32_t kQNoTask = 0xffffffffu;       // a queue entry nobody filled (phase B skips it)
 struct QEmit {  // phase A -> task queue
     uint32_t* tasks;
     int* n_tasks;
     uint32_t slot;
     int mine;
+    int per_query;
     // the leaf children `first + c`, c a set bit of mask, of one opened node: one reservation for all of them
     __device__ __forceinline__ bool operator()(int first, int mask)
     {
         const int n = __popc(mask);
         mine += n;
-        if (mine > kQTaskPerQuery) return false;
+        if (mine > per_query) return false;
         int t = atomicAdd(n_tasks, n);
-        if (t + n > kQTaskCap) return false;
+        if (t + n > kQTaskCap) {
+            // the reservation that crosses the end of the queue owns [t, cap): phase B reads every entry below
+            // min(n_tasks, cap), so the part nobody will write must not keep a task of an earlier chunk
+            for (; t < kQTaskCap; ++t) __stcg(tasks + t, kQNoTask);
+            return false;
+        }
         for (; mask; mask &= mask - 1) __stcg(tasks + t++, (slot << kQNodeBits) | static_cast<uint32_t>(first + lowest_bit(mask)));
         return true;
     }
@@ -703,7 +713,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
         }
         if (valid && !dead) {
             s_q[threadIdx.x] = make_float4(q.x, q.y, q.z, candidate_limit(bound0, r2f));
-            QEmit emit{s_tasks, &s_ntasks, threadIdx.x, 0};
+            QEmit emit{s_tasks, &s_ntasks, threadIdx.x, 0, P.q_leaves};
             fallback = !tree_collect_leaves(geom, nodes, q.x, q.y, q.z, bound0, emit, stack);
         }
         __syncthreads();
@@ -712,6 +722,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
         const int n_tasks = min(s_ntasks, kQTaskCap);
         for (int t = threadIdx.x; t < n_tasks; t += kSearchThreads) {
             const uint32_t task = __ldcg(s_tasks + t);
+            if (task == kQNoTask) continue;
             const uint32_t ql = task >> kQNodeBits;
             const float4 qq = s_q[ql];
             QPush push{s_cand + ql, s_cnt + ql, q_cand};
@@ -1344,7 +1355,7 @@ __global__ void __launch_bounds__(eval_threads(kFast), kFast ? kEvalFastBlocks :
             const int parity = seq & 1;
             for (int r = 0; r < P.world; ++r) {
                 double* dst = P.peer_mailbox[r] + (static_cast<size_t>(parity) * P.world + P.rank) * kMailDoubles;
-                *reinterpret_cast<volatile double*>(dst + kMailDoubles - 1) = static_cast<double>(seq);
+                *reinterpret_cast<volatile double*>(dst + kMailDoubles - 1) = P.mail_base + static_cast<double>(seq);
             }
             __threadfence_system();
         }
@@ -1355,7 +1366,7 @@ __global__ void __launch_bounds__(eval_threads(kFast), kFast ? kEvalFastBlocks :
             const int parity = seq & 1;
             const double* src = P.mailbox + (static_cast<size_t>(parity) * P.world + threadIdx.x) * kMailDoubles;
             const long long t0 = clock64();
-            while (ld_volatile_f64(src + kMailDoubles - 1) != static_cast<double>(seq)) {
+            while (ld_volatile_f64(src + kMailDoubles - 1) != P.mail_base + static_cast<double>(seq)) {
                 if (clock64() - t0 > P.spin_limit) {
                     s_timeout = 1;
                     break;

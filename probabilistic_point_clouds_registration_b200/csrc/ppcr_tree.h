@@ -783,6 +783,28 @@ PPCR_HD void leaf_candidates(const TreeNode* __restrict__ nodes, const float4* _
 #endif
     PPCR_STAT(leaves, 1);
     PPCR_STAT(points, n.end - n.begin);
+#if defined(PPCR_TREE_STATS) && !defined(__CUDA_ARCH__)
+    {   // experiment: how many of the queued leaves would a tight bounding box of their points have pruned
+        float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+        for (int j = n.begin; j < n.end; ++j) {
+            const float c[3] = {pts[j].x, pts[j].y, pts[j].z};
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = c[a] < lo[a] ? c[a] : lo[a];
+                hi[a] = c[a] > hi[a] ? c[a] : hi[a];
+            }
+        }
+        const float q[3] = {qx, qy, qz};
+        float d2 = 0.f;
+        for (int a = 0; a < 3; ++a) {
+            const float d = q[a] < lo[a] ? lo[a] - q[a] : (q[a] > hi[a] ? q[a] - hi[a] : 0.f);
+            d2 += d * d;
+        }
+        if (d2 > limit_d2) {
+            PPCR_STAT(leaves_skipped, 1);
+            PPCR_STAT(stack_skipped, n.end - n.begin);
+        }
+    }
+#endif
     const int last = n.end - 1;
     for (int j0 = n.begin; j0 < n.end; j0 += 32) {
         const int stop = n.end - j0 < 32 ? n.end - j0 : 32;

@@ -5,7 +5,7 @@
                                         exchange is the 24-moment vector (+ association size) per LM iteration, which the
                                         eval kernel's controller block writes straight into the peers' mailboxes over
                                         NVLink (ppcr_shard_export / ppcr_shard_connect); torch.distributed only carries
-                                        the 64-byte IPC tokens once, at set-up.
+                                        the 128-byte mailbox tokens once, at set-up.
 
 torch.distributed is plumbing here (rendezvous, token exchange, result gather); none of it is on the per-iteration path.
 """
@@ -32,7 +32,7 @@ def deal_pairs(n_pairs: int, rank: int, world: int) -> list[int]:
 
 
 def gather_tokens(token: bytes, dist=None) -> bytes:
-    """All-gathers the 64-byte mailbox tokens of every rank (rank order).  Works on any backend (gloo / nccl)."""
+    """All-gathers the mailbox tokens of every rank (rank order).  Works on any backend (gloo / nccl)."""
     import torch
     if dist is None:
         import torch.distributed as dist

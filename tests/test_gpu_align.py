@@ -115,6 +115,35 @@ def test_config2_gaussian_outliers_default_path(capi, oracle):
     _assert_tolerance_parity(hist, stats, ref)
 
 
+def test_config2_full_size_pose_parity(capi, oracle):
+    """BASELINE config 2 at its stated size: ~100k rays (64 rings x 1563 azimuths), 20% uniform outliers, the flags
+    `-u -s 0.05 -t 0.05` with everything else at the CLI defaults (m 20, r 3).  The scene is bounded (60 x 60 x 20 m box)
+    so that the 0.05 m voxel grid does not overflow int32 and both filters really run."""
+    src, tgt, _ = synth.config2_lidar_outliers()
+    hist, stats, moved, done, ref = _run_both(capi, oracle, src, tgt, exact=False, max_neighbours=20, dof=np.inf,
+                                              radius=3.0, source_filter_size=0.05, target_filter_size=0.05)
+    assert done
+    assert len(moved) == ref.n_filtered_src < len(src)
+    _assert_tolerance_parity(hist, stats, ref)
+
+
+def test_config5_pairs_through_the_batch_entry(capi, oracle):
+    """BASELINE config 5 at its stated size (120k-point pairs, seeds 1000.., CLI defaults m 20 / r 3 / dof 5) through
+    ppcr_align_batch with several lanes: every pair against the oracle run on its own."""
+    idx = [0, 1, 2, 3]
+    pairs = [synth.config5_pair(i)[:2] for i in idx]
+    kw = dict(max_neighbours=20, dof=5.0, radius=3.0)
+    T, n_outer, corr = capi.align_batch(pairs, capi.make_params(**kw), slots=3)
+    for k, (s, t) in enumerate(pairs):
+        ref = oracle.align(s, t, oracle.make_params(**kw), oracle.make_options(inner_kind=1), use_grid=True)
+        assert abs(int(n_outer[k]) - ref.n_outer) <= 1, (k, n_outer[k], ref.n_outer)
+        if int(n_outer[k]) == ref.n_outer:
+            want = sum(x["n_correspondences"] for x in ref.stats)
+            assert abs(int(corr[k]) - want) <= 1e-4 * want, (k, corr[k], want)
+        rot, tr = pose_delta(T[k], ref.transformation)
+        assert rot < POSE_TOL_RAD and tr < POSE_TOL_M, (k, rot, tr)
+
+
 def test_config3_full_size_pose_parity(capi, oracle):
     """BASELINE config 3 at full size (1M-point pair, -m 10 -r 0.5 -d 5), library defaults, against the oracle run
     to its own stopping rule: final pose within 1e-4 rad / 1e-4 m."""
@@ -184,3 +213,21 @@ def test_batch_matches_single(capi):
         assert n_outer[i] == len(h)
         assert corr[i] == sum(x["n_correspondences"] for x in st)
         np.testing.assert_allclose(T[i], h[-1], rtol=0, atol=1e-12)
+
+
+def test_batch_over_a_device_list(capi):
+    """ppcr_align_batch_devices (device_ids[], n_dev): lanes on every listed device draw from one counter; the
+    result of a pair does not depend on the device or lane that ran it.  On a one-GPU box the list names device 0 twice."""
+    import torch
+    n_dev = torch.cuda.device_count()
+    devices = list(range(min(n_dev, 4))) if n_dev > 1 else [0, 0]
+    pairs = [synth.lidar_pair(200 + i, 16, 400, random_motion=(2.0, 0.5))[:2] for i in range(7)]
+    params = capi.make_params(max_neighbours=12, radius=2.0, n_iter=30)
+    T1, n1, c1 = capi.align_batch(pairs, params, slots=2)
+    T2, n2, c2 = capi.align_batch(pairs, params, slots=2, devices=devices)
+    assert np.array_equal(n1, n2) and np.array_equal(c1, c2)
+    np.testing.assert_array_equal(T1, T2)
+    dev_opt = capi.make_options(input_on_device=True)
+    with pytest.raises(capi.PpcrError) as e:
+        capi.align_batch([(0, 0, 0, 0)], params, dev_opt, devices=[0, 0])
+    assert e.value.code == 1

@@ -60,6 +60,22 @@ def test_lattice_with_exact_ties(capi, oracle, m):
     assert np.all(gc == 1) and np.array_equal(gi[:, 0], np.arange(400))
 
 
+def test_large_lattice_ties_on_the_oracle_grid_path(capi, oracle):
+    """The same kind of lattice above 4000 points, where the oracle answers from its CPU grid instead of brute force:
+    both sides keep the pure (d2, index) order, so a tie at the m-th boundary resolves to the lower index whatever the
+    traversal order (a 3-D lattice: 6 neighbours at d2 = 0.25, 12 at 0.5, 8 at 0.75)."""
+    g = np.arange(18, dtype=np.float32) * 0.5
+    xx, yy, zz = np.meshgrid(g, g, g, indexing="ij")
+    pts = np.ones((18 ** 3, 4), dtype=np.float32)
+    pts[:, 0], pts[:, 1], pts[:, 2] = xx.ravel(), yy.ravel(), zz.ravel()
+    assert len(pts) > 4000
+    for radius, m in ((0.75, 4), (0.75, 10), (0.9, 20), (0.9, 32)):
+        _compare(capi, oracle, pts, pts, radius, m)
+    # and shuffled, so that index order and Morton order disagree
+    perm = np.random.default_rng(5).permutation(len(pts))
+    _compare(capi, oracle, pts[::3], pts[perm], 0.75, 10)
+
+
 def test_edge_cases(capi, oracle):
     rng = np.random.default_rng(3)
     tgt = np.ones((50, 4), dtype=np.float32)
@@ -116,6 +132,30 @@ def test_full_size_properties(capi, oracle):
     oi, od, oc, _ = oracle.radius_search(src[sel], tgt, radius, m, use_grid=True)
     assert np.array_equal(oc, gc[sel])
     assert rows_as_sets(oi, oc) == rows_as_sets(gi[sel], gc[sel])
+
+
+def test_ten_million_point_pair_sampled_rows(capi, oracle):
+    """BASELINE config 4's clouds (10M points each, -m 10 -r 0.5): size-independent properties of every row and an
+    exact comparison of 4000 sampled rows with the oracle's grid search over the whole 10M-point target."""
+    src, tgt, _ = synth.config4_lidar_10m()
+    radius, m = 0.5, 10
+    gi, gd, gc = capi.radius_search(src, tgt, radius, m)
+    r2 = np.float32(radius * radius)
+    valid = np.arange(m)[None, :] < gc[:, None]
+    assert gc.min() >= 0 and gc.max() <= m
+    assert np.all(gd[valid] < r2)
+    d = np.where(valid, gd, np.inf)
+    assert np.all(np.diff(d, axis=1)[valid[:, 1:]] >= 0)
+    assert np.all(gi[valid] >= 0) and np.all(gi[valid] < len(tgt))
+    assert np.all(gi[~valid] == -1)
+    rng = np.random.default_rng(1)
+    sel = np.sort(rng.choice(len(src), 4000, replace=False))
+    oi, od, oc, _ = oracle.radius_search(src[sel], tgt, radius, m, use_grid=True)
+    assert np.array_equal(oc, gc[sel])
+    for k, i in enumerate(sel):
+        c = oc[k]
+        assert np.array_equal(gi[i, :c], oi[k, :c]), i
+        assert np.array_equal(gd[i, :c].view(np.uint32), od[k, :c].view(np.uint32)), i
 
 
 def _moved_search_rows(capi, src, tgt, n_iter, **kw):

@@ -2,7 +2,7 @@
 
 What is exercised is what the multi-GPU path adds on top of the single-GPU one:
   * the partitioning rules (source slices of a sharded pair, pairs of a batch),
-  * the set-up exchange of the 64-byte mailbox tokens,
+  * the set-up exchange of the mailbox tokens,
   * the algebra the sharded mode rests on: the 24 moments of the weights + normal-equation pass are additive over
     source slices, so rank-ordered sums of per-slice moments reproduce the single-process 7x7 system (the product's
     own eval code, compiled for the CPU, on each rank).
