@@ -239,6 +239,7 @@ struct Engine {
     ppcr_stage_times times{};
     // sharded mode
     int rank = 0, world = 1;
+    int requested_max_neighbours = 0;  // what the caller asked for (params.max_neighbours holds the row capacity)
     // L2 flush buffer for ppcr_time_kernel
     DevBuf<float4> flush;
 
@@ -547,10 +548,18 @@ static int64_t voxel_filter_device(const float4* in, int64_t n, double leaf_d, D
 // pair / engine setup
 // ------------------------------------------------------------------------------------------------------------
 
-static void validate_params(const ppcr_params& p)
+// Rows of the association hold at most kMaxRow neighbours.  A request for more -- max_neighbours <= 0 is pcl's "every target
+// within the radius" (registration.cc:74-75 passes it straight to radiusSearch), and so is anything above the target size -- is
+// served with rows of kMaxRow as long as no query has that many targets within the radius: every row then holds ALL of its
+// in-radius targets, which is what the reference would have returned.  A row that fills up stops the registration with
+// PPCR_ERR_UNSUPPORTED instead of silently truncating it.
+constexpr int kMaxRow = 128;
+static bool wide_rows(int max_neighbours) { return max_neighbours <= 0 || max_neighbours > kMaxRow; }
+
+static void validate_params(const ppcr_params& p, bool allow_wide)
 {
-    if (p.max_neighbours < 1 || p.max_neighbours > 128)
-        throw StatusError{PPCR_ERR_UNSUPPORTED, "max_neighbours must be in [1,128] (0/negative = unlimited is not implemented)"};
+    if (wide_rows(p.max_neighbours) && !allow_wide)
+        throw StatusError{PPCR_ERR_UNSUPPORTED, "max_neighbours must be in [1,128] at this entry point"};
     if (!(p.radius > 0.0) || !std::isfinite(p.radius)) throw StatusError{PPCR_ERR_INVALID, "radius must be finite and > 0"};
     if (!(p.dof > 0.0)) throw StatusError{PPCR_ERR_INVALID, "dof must be > 0 (+inf selects the Gaussian model)"};
     if (p.n_iter < 0) throw StatusError{PPCR_ERR_INVALID, "n_iter must be >= 0"};
@@ -600,6 +609,9 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     D.n_pad = (D.n_src + kEvalFastThreads - 1) / kEvalFastThreads * kEvalFastThreads;
     if (D.n_pad == 0) D.n_pad = kEvalFastThreads;
     D.m = static_cast<int>(std::min<int64_t>(prm.max_neighbours, std::max<int64_t>(P.n_tgt, 1)));
+    // wide rows: a row that reaches the capacity may have lost neighbours -- unless the capacity is the whole target
+    const int64_t wanted = E.requested_max_neighbours <= 0 ? P.n_tgt : std::min<int64_t>(E.requested_max_neighbours, P.n_tgt);
+    D.overflow_at = wanted > D.m ? D.m : INT_MAX;
     D.search_cap = search_cap(prm.max_neighbours);
     D.r2f = static_cast<float>(prm.radius * prm.radius);
     D.src = P.src.p;
@@ -693,12 +705,14 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     tr.mark("buffers + state");
 }
 
-static void engine_init(Engine& E, const ppcr_params& params, const ppcr_options* options)
+static void engine_init(Engine& E, const ppcr_params& params, const ppcr_options* options, bool allow_wide = false)
 {
     E.params = params;
     g_launch_sink = &E.times.total_launches;
     if (options) E.opts = *options; else memset(&E.opts, 0, sizeof(E.opts));
-    validate_params(params);
+    validate_params(params, allow_wide);
+    E.requested_max_neighbours = params.max_neighbours;
+    if (wide_rows(params.max_neighbours)) E.params.max_neighbours = kMaxRow;  // every size below derives from this
     E.device = E.opts.device;
     select_device(E.device);
     if (E.opts.stream) {
@@ -1028,6 +1042,9 @@ static PairState download_state(Engine& E, int p)
 
 static void check_state_error(const PairState& s)
 {
+    if (s.error == kErrRowOverflow)
+        throw StatusError{PPCR_ERR_UNSUPPORTED, "a source point has 128 or more targets within the radius: neighbour sets beyond 128 "
+                                                "(max_neighbours <= 0 or > 128) are not supported -- reduce the radius or filter the target"};
     if (s.error >= 100) throw StatusError{PPCR_ERR_TIMEOUT, "a peer rank did not arrive at the moment exchange"};
     if (s.error != 0) throw StatusError{PPCR_ERR_CUDA, "device tick cap reached before convergence"};
 }
@@ -1217,7 +1234,7 @@ ppcr_status ppcr_create_ex(const float* src, int64_t n_src, const float* tgt, in
     ppcr_status s = guarded([&] {
         h = new ppcr_handle();
         Engine& E = h->eng;
-        engine_init(E, *params, options);
+        engine_init(E, *params, options, true);
         E.pairs.resize(1);
         pair_setup(E, E.pairs[0], src, n_src, tgt, n_tgt, E.opts.input_on_device != 0);
         engine_commit(E);
@@ -1858,7 +1875,7 @@ ppcr_status ppcr_align_batch_devices(const ppcr_pair* pairs, int32_t n_pairs, co
                 Engine E;
                 ppcr_options my_opt = lane_opt;
                 my_opt.device = device_ids[lane_index % n_dev];  // lanes interleave over the devices
-                engine_init(E, *params, &my_opt);
+                engine_init(E, *params, &my_opt, true);
                 E.pairs.resize(1);
                 const bool on_dev = E.opts.input_on_device != 0;
                 for (;;) {

@@ -56,6 +56,7 @@ constexpr int kEvalStages = PPCR_EVAL_STAGES;  // staged tiles per block
 #endif
 constexpr int kFoldGroup = 16;    // blocks per first-level group of the moment reduction
 constexpr int kFoldChains = 4;    // interleaved chains of the second level
+constexpr int kErrRowOverflow = 200;  // PairState::error: a row of a wide association filled up
 constexpr int kMailDoubles = 32;  // 24 moments + K + sequence stamp, padded
 constexpr double kMailEpochStride = 67108864.0;  // 2^26 ticks per stamp epoch (mailboxes outlive handles; a handle's ticks stay far below)
 constexpr unsigned kFull = 0xffffffffu;
@@ -74,6 +75,7 @@ struct PairDev {
     int search_queued;  // 1: searches that follow a cloud move are k_search_q's, k_search only does the first of an align()
     int q_cand;                // k_search_q: candidate positions per query (search_q_cand(max_neighbours))
     float q_heavy;             // k_search_q: a query expecting more than q_heavy * q_cand candidates counts as heavy
+    int overflow_at;           // a row that reaches this count may have lost neighbours (wide rows; INT_MAX otherwise)
     int q_leaves;              // k_search_q: leaves one query may queue before it falls back to tree_search (kQTaskPerQuery)
     unsigned char* q_scratch;  // k_search_q's task / candidate queues: one slab per block of its grid (all pairs share the pointer)
     float r2f;      // float(radius * radius): strict membership bound (FLANN)
@@ -500,6 +502,7 @@ __global__ void PPCR_SEARCH_BOUNDS k_search(const PairDev* __restrict__ pairs)
         nbr_cnt[i] = cnt;
         nbr_kth[i] = kth;
         cnt_total += cnt;
+        if (cnt >= P.overflow_at) st->row_overflow = 1;
     }
     // association size: warp sum, one atomic per warp
     for (int o = 16; o > 0; o >>= 1) cnt_total += __shfl_xor_sync(kFull, cnt_total, o);
@@ -708,6 +711,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
                 nbr_cnt[i] = cnt;
                 nbr_kth[i] = L.kth_key() != kKeyInf ? key_d2(L.kth_key()) : kInf;
                 cnt_total += cnt;
+                if (cnt >= P.overflow_at) st->row_overflow = 1;
             }
             continue;
         }
@@ -783,6 +787,7 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
             nbr_cnt[i] = cnt;
             nbr_kth[i] = kth;
             cnt_total += cnt;
+            if (cnt >= P.overflow_at) st->row_overflow = 1;
 #if defined(PPCR_Q_PROFILE)
             n_fall += fallback ? 1 : 0;
 #endif
@@ -1404,6 +1409,14 @@ __global__ void __launch_bounds__(eval_threads(kFast), kFast ? kEvalFastBlocks :
             reinterpret_cast<unsigned long long*>(&s_cfg)[k] = reinterpret_cast<const unsigned long long*>(P.cfg)[k];
         __shared__ CtrlShared s_ctrl;
         __syncthreads();
+        if (s_state.row_overflow && s_state.phase != PH_DONE) {  // block-uniform: a row of a wide association filled up
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_state.error = kErrRowOverflow;
+                s_state.phase = PH_DONE;
+            }
+            __syncthreads();
+        }
         if (s_state.phase != PH_DONE) {  // block-uniform
             // moment expansion around the pose the residuals were taken at: 36 entries of N, then 27 output tasks
             if (threadIdx.x == 0) quat_frame(evaluated_at(&s_state), &s_ctrl.frame);

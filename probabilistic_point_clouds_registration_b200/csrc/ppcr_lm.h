@@ -97,7 +97,7 @@ struct PairState {
     int32_t error;
     int32_t search_cursor;  // next chunk of queries to hand out (persistent search kernel)
     int32_t eval_ticket;    // blocks of the eval kernel that have published their partial sums
-    int32_t pad;
+    int32_t row_overflow;   // set by a search kernel: a row reached PairDev::overflow_at
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -582,7 +582,7 @@ PPCR_HD void state_init(PairState* s, const Config* cfg)
     s->ticks = 0;
     s->evals = 0;
     s->error = 0;
-    s->pad = 0;
+    s->row_overflow = 0;
     s->search_cursor = 0;
     s->eval_ticket = 0;
     for (int k = 0; k < 16; ++k) {

@@ -1,6 +1,11 @@
 // Command-line front end with the reference's flags, defaults, messages, output files and exit codes
 // (reference: src/prob_point_cloud_registration_ex.cc:26-190).
 //
+// Attribution: the option names, help strings, defaults, printed messages, output file names and exit codes below are the
+// command-line contract of iralabdisco/probabilistic_point_clouds_registration (GPLv3, see NOTICE.md at the repository root)
+// and are reproduced so that scripts written against the reference binary keep working; main() follows the order of the
+// reference's main() for the same reason.  This file is therefore distributed under the GNU GPL v3 like the reference.
+//
 //   prob_point_cloud_registration <source.pcd> <target.pcd> [-s leaf] [-t leaf] [-m 20] [-i 1000] [-d 5] [-r 3]
 //                                 [-c 0.01] [-n 5] [-u] [-v] [-g ground_truth.pcd] [--dump]
 #include <cstdlib>

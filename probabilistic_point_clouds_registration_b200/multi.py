@@ -25,6 +25,19 @@ def slice_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def block_cyclic_indices(n: int, rank: int, world: int, block: int = 4096) -> np.ndarray:
+    """Source points of `rank` when the cloud is dealt in blocks of `block` consecutive points, round robin.  A scan is stored
+    ring by ring, near rings first, and the cost of a search row follows the local density: contiguous slices give the rank
+    that draws the near rings 25 % more search time than the last one (10M-point pair, two GPUs), while a block-cyclic deal
+    gives every rank arcs of every ring.  Every rank sorts its own points along the target's Morton curve afterwards, so
+    which points a rank holds does not matter for locality as long as they come in runs."""
+    n, block = int(n), int(block)
+    n_blocks = (n + block - 1) // block
+    mine = np.arange(rank, n_blocks, world, dtype=np.int64)
+    idx = (mine[:, None] * block + np.arange(block, dtype=np.int64)[None, :]).ravel()
+    return idx[idx < n]
+
+
 def deal_pairs(n_pairs: int, rank: int, world: int) -> list[int]:
     """Pairs of a batch owned by `rank` (contiguous blocks, same rule as slice_bounds)."""
     lo, hi = slice_bounds(n_pairs, rank, world)

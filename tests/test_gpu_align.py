@@ -231,3 +231,28 @@ def test_batch_over_a_device_list(capi):
     with pytest.raises(capi.PpcrError) as e:
         capi.align_batch([(0, 0, 0, 0)], params, dev_opt, devices=[0, 0])
     assert e.value.code == 1
+
+
+@pytest.mark.parametrize("max_neighbours", [0, -3, 500])
+def test_unlimited_neighbour_sets(capi, oracle, max_neighbours):
+    """max_neighbours <= 0 (pcl: every target within the radius; reachable with `-m 0`, registration.cc:74-75) and values above
+    the row capacity of 128: rows hold ALL in-radius targets as long as no row reaches 128 of them."""
+    src, tgt, _ = synth.config1_plane_sphere(seed=5, n_plane=1500, n_sphere=1000)
+    hist, stats, moved, done, ref = _run_both(capi, oracle, src, tgt, max_neighbours=max_neighbours, dof=5.0, radius=0.45)
+    assert done and 20 < stats[0]["n_correspondences"] / len(src) < 128  # well beyond the default of 20 per row
+    _assert_parity(hist, stats, moved, ref)
+
+
+def test_unlimited_neighbour_sets_small_target_and_overflow(capi, oracle):
+    src, tgt, _ = synth.config1_plane_sphere(seed=6, n_plane=400, n_sphere=300)
+    # a target of fewer points than the row capacity: "all of them" fits whatever the radius
+    small = tgt[::7]
+    assert len(small) <= 128
+    hist, stats, moved, done, ref = _run_both(capi, oracle, src, small, max_neighbours=0, dof=5.0, radius=50.0, n_iter=4)
+    assert stats[0]["n_correspondences"] == len(src) * len(small)
+    _assert_parity(hist, stats, moved, ref)
+    # a row that would need more than 128 neighbours stops the registration instead of being truncated silently
+    with capi.Registration(src, tgt, capi.make_params(max_neighbours=0, radius=3.0)) as reg:
+        with pytest.raises(capi.PpcrError) as e:
+            reg.align()
+        assert e.value.code == 4 and "128" in str(e.value)

@@ -29,6 +29,18 @@ def test_slice_bounds_cover_everything_once():
     assert sum(len(multi.deal_pairs(1024, r, 8)) for r in range(8)) == 1024
 
 
+def test_block_cyclic_deal_covers_everything_once():
+    for n in (0, 1, 100, 10007, 1000064):
+        for world in (1, 2, 3, 8):
+            for block in (1, 64, 8192):
+                parts = [multi.block_cyclic_indices(n, r, world, block) for r in range(world)]
+                assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(n))
+                assert all(np.all(np.diff(p) > 0) for p in parts if len(p) > 1)
+                if n >= world * block * 4:
+                    sizes = [len(p) for p in parts]
+                    assert max(sizes) - min(sizes) <= block
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -48,9 +60,10 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         # 1. token exchange
-        token = bytes([rank + 1]) * 64
+        from probabilistic_point_clouds_registration_b200 import capi
+        token = bytes([rank + 1]) * capi.SHARD_TOKEN_BYTES
         tokens = multi.gather_tokens(token, dist)
-        assert tokens == b"".join(bytes([r + 1]) * 64 for r in range(world))
+        assert tokens == b"".join(bytes([r + 1]) * capi.SHARD_TOKEN_BYTES for r in range(world))
         # 2. additivity of the moments over source slices
         lib = C.CDLL(os.path.join(here, "emu", "libppcr_emu.so"))
         src, tgt, _ = synth.config1_plane_sphere(seed=31, n_plane=900, n_sphere=700)

@@ -30,47 +30,47 @@ src, tgt, _ = synth.lidar_pair(4, rings, az)
 src, tgt = np.ascontiguousarray(src), np.ascontiguousarray(tgt)
 gen_s = time.perf_counter() - t0
 params = capi.make_params(max_neighbours=10, radius=0.5, dof=5.0)
-lo, hi = multi.slice_bounds(len(src), rank, world)
-# clouds resident in HBM, like bench.py's `value`
-if os.environ.get("SHARD_STRIDED"):
-    mine = np.ascontiguousarray(src[rank::world])
-    lo, hi = 0, len(mine)
-    d_src = torch.from_numpy(mine).cuda()
-else:
-    d_src = torch.from_numpy(src[lo:hi]).cuda()
 d_tgt = torch.from_numpy(tgt).cuda()
 stages = bool(os.environ.get("SHARD_STAGES"))
 opt = capi.make_options(device=local, input_on_device=True, driver=1 if stages else 0, record_stage_times=stages)
-times = []
-for rep in range(reps + 1):
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    with multi.ShardedRegistration(d_src.data_ptr(), d_tgt.data_ptr(), params, rank, world, opt, n_source=hi - lo,
-                                   n_target=len(tgt)) as reg:
-        reg.align()
-        stats = reg.iteration_stats()
-        hist = reg.transformation_history()
-        if stages:
-            lt = reg.stage_times()
-            print(f"[rank {rank}] rep {rep}: search {lt.search_ms:.1f} ms in {lt.search_launches} launches, eval {lt.eval_ms:.1f} ms in "
-                  f"{lt.eval_launches} launches, K local {sum(s['n_correspondences'] for s in stats)}", flush=True)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    print(f"[rank {rank}] rep {rep}: {1e3 * dt:.1f} ms", flush=True)
-    if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    if rep > 0:
-        times.append(dt)
-if rank == 0:
-    corr = sum(s["n_correspondences"] for s in stats)
-    evals = sum(s["lm_iterations"] + 1 for s in stats)
-    ms = 1e3 * float(np.mean(times))
-    print("SHARD_BENCH reps (ms):", " ".join(f"{1e3 * t:.1f}" for t in times))
-    print(f"SHARD_BENCH n_gpus={world} n_src={len(src)} n_tgt={len(tgt)} outer={len(stats)} evals={evals} "
-          f"correspondences={corr} ms={ms:.1f} (min {1e3 * min(times):.1f}) corr_per_s={corr / (ms * 1e-3):.3e} gen_s={gen_s:.0f}")
+# how the source is dealt to the ranks: contig (slice_bounds), strided (rank::world), block:<points> (block-cyclic)
+for mode in os.environ.get("SHARD_MODES", "contig").split(","):
+    if mode == "contig":
+        lo, hi = multi.slice_bounds(len(src), rank, world)
+        mine = src[lo:hi]
+    elif mode == "strided":
+        mine = np.ascontiguousarray(src[rank::world])
+    else:
+        mine = np.ascontiguousarray(src[multi.block_cyclic_indices(len(src), rank, world, int(mode.split(":")[1]))])
+    d_src = torch.from_numpy(mine).cuda()
+    times = []
+    for rep in range(reps + 1):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with multi.ShardedRegistration(d_src.data_ptr(), d_tgt.data_ptr(), params, rank, world, opt, n_source=len(mine),
+                                       n_target=len(tgt)) as reg:
+            reg.align()
+            stats = reg.iteration_stats()
+            hist = reg.transformation_history()
+            if stages:
+                lt = reg.stage_times()
+                print(f"[rank {rank}] {mode} rep {rep}: search {lt.search_ms:.1f} ms in {lt.search_launches} launches, eval {lt.eval_ms:.1f} ms in "
+                      f"{lt.eval_launches} launches, K {sum(s['n_correspondences'] for s in stats)}", flush=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        if rep > 0:
+            times.append(dt)
+    if rank == 0:
+        corr = sum(s["n_correspondences"] for s in stats)
+        evals = sum(s["lm_iterations"] + 1 for s in stats)
+        ms = 1e3 * float(np.median(times))
+        print(f"SHARD_BENCH {mode} n_gpus={world} n_src={len(src)} outer={len(stats)} evals={evals} correspondences={corr} "
+              f"median ms={ms:.1f} reps: " + " ".join(f"{1e3 * t:.1f}" for t in times), flush=True)
 if world > 1:
     dist.destroy_process_group()
