@@ -44,6 +44,7 @@ import os
 import subprocess
 import sys
 import threading
+import traceback
 import time
 
 import numpy as np
@@ -294,10 +295,11 @@ def run_reference(args):
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------
 
-def _pin(arr, chunk_bytes=256 << 20):
+def _pin(arr, chunk_bytes):
     """cudaHostRegister of a numpy array's memory (the shared mappings the inputs were generated into), in chunks: one
     registration of the whole 3.9 GB batch is refused on some boxes (cudaErrorOperatingSystem), and a refused call must not
-    leave its error behind for the next CUDA call of this thread.  Returns the fraction of the bytes that got pinned."""
+    leave its error behind for the next CUDA call of this thread.  A copy must not straddle two registrations (CUDA refuses
+    it), so chunk_bytes has to be a multiple of whatever is copied in one call.  Returns the fraction of the bytes pinned."""
     import ctypes
     try:
         rt = ctypes.CDLL("libcudart.so.12")
@@ -325,10 +327,11 @@ def bench_batch_c5(args, ctx):
     if buf is None or args.batch_pairs <= 0:
         return None
     params = capi.make_params(**WORKLOADS["c5"]["params"])
-    pinned = _pin(buf)
-    torch.cuda.synchronize()
-    d_buf = torch.from_numpy(buf).cuda()  # resident copy of every slot this rank may run
     el = C5_POINTS * 4 * 4  # bytes per cloud
+    d_buf = torch.from_numpy(buf).cuda()  # resident copy of every slot this rank may run (before pinning: one copy of it all)
+    torch.cuda.synchronize()
+    pinned = _pin(buf, 64 * el)  # 32 pairs per registration; ppcr copies cloud by cloud
+    torch.cuda.synchronize()
 
     def host_pairs(slots):
         return [(buf[s, 0], buf[s, 1]) for s in slots]
@@ -676,10 +679,12 @@ def run_ours(args):
         try:
             batch_rec = bench_batch_c5(args, ctx)
         except Exception as e:  # the headline line must still print
+            traceback.print_exc()
             batch_rec = {"error": f"{type(e).__name__}: {e}"} if rank == 0 else None
         try:
             sharded_rec = bench_sharded_c4(args, ctx)
         except Exception as e:
+            traceback.print_exc()
             sharded_rec = {"error": f"{type(e).__name__}: {e}"} if rank == 0 else None
 
     if rank == 0:

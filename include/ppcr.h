@@ -17,6 +17,7 @@
 #ifndef PPCR_H
 #define PPCR_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -227,6 +228,16 @@ ppcr_status ppcr_align_batch(const ppcr_pair* pairs, int32_t n_pairs, const ppcr
 ppcr_status ppcr_align_batch_devices(const ppcr_pair* pairs, int32_t n_pairs, const ppcr_params* params,
                                      const ppcr_options* options, const int32_t* device_ids, int32_t n_dev, int32_t slots,
                                      double* out_T, int32_t* out_n_outer, int64_t* out_corr);
+
+/* ---- page-locked host memory for clouds (new surface) ------------------------------------------------------ */
+
+/* A cloud that is read from a file straight into page-locked memory goes to the device at the full speed of the link and
+ * asynchronously (ppcr_create's copy of a pageable buffer is staged by the driver).  ppcr_host_alloc returns NULL when no
+ * CUDA device is usable or the allocation is refused -- fall back to malloc; ppcr_host_free returns 1 if `p` was one of
+ * its blocks (and frees it), 0 otherwise (the caller frees it its own way).  The PCL stand-in's PointCloud uses them
+ * (include/ppcr_compat/pcl/point_cloud.h); with the real PCL, cudaHostRegister the cloud's vector instead. */
+void* ppcr_host_alloc(size_t bytes);
+int32_t ppcr_host_free(void* p);
 
 /* ---- one pair sharded over several GPUs (new surface) --------------------------------------------------- */
 

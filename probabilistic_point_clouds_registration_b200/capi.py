@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "ppcr_filtered_source", "ppcr_filtered_target", "ppcr_association", "ppcr_get_stage_times", "ppcr_time_kernel",
     "ppcr_voxel_filter", "ppcr_time_voxel_filter", "ppcr_radius_search", "ppcr_weights_normal_eq", "ppcr_iteration_solve", "ppcr_transform",
     "ppcr_replay_metrics", "ppcr_closest_point_metrics",
-    "ppcr_align_batch", "ppcr_align_batch_devices", "ppcr_shard_export", "ppcr_shard_connect",
+    "ppcr_align_batch", "ppcr_align_batch_devices", "ppcr_host_alloc", "ppcr_host_free", "ppcr_shard_export", "ppcr_shard_connect",
 ]
 
 SHARD_TOKEN_BYTES = 128
@@ -144,11 +144,15 @@ def lib():
         L.ppcr_closest_point_metrics.argtypes = [vp, i64, vp, i64, f64, C.POINTER(Options), C.POINTER(ClosestMetrics), vp]
         L.ppcr_align_batch.argtypes = [C.POINTER(PairDesc), i32, C.POINTER(Params), C.POINTER(Options), i32, vp, vp, vp]
         L.ppcr_align_batch_devices.argtypes = [C.POINTER(PairDesc), i32, C.POINTER(Params), C.POINTER(Options), vp, i32, i32, vp, vp, vp]
+        L.ppcr_host_alloc.argtypes = [C.c_size_t]
+        L.ppcr_host_alloc.restype = vp
+        L.ppcr_host_free.argtypes = [vp]
         L.ppcr_shard_export.argtypes = [vp, i32, i32, vp]
         L.ppcr_shard_connect.argtypes = [vp, vp]
         for name in EXPORTED_SYMBOLS:
             fn = getattr(L, name)
-            if name not in ("ppcr_last_error", "ppcr_version", "ppcr_destroy", "ppcr_default_params", "ppcr_default_options"):
+            if name not in ("ppcr_last_error", "ppcr_version", "ppcr_destroy", "ppcr_default_params", "ppcr_default_options",
+                            "ppcr_host_alloc"):
                 fn.restype = i32
         _lib = L
     return _lib

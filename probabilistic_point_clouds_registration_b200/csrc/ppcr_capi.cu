@@ -20,6 +20,7 @@
 #include <atomic>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <thread>
 #include <unistd.h>
@@ -1927,6 +1928,43 @@ ppcr_status ppcr_align_batch(const ppcr_pair* pairs, int32_t n_pairs, const ppcr
 {
     const int32_t device = options ? options->device : 0;
     return ppcr_align_batch_devices(pairs, n_pairs, params, options, &device, 1, slots, out_T, out_n_outer, out_corr);
+}
+
+// ---- page-locked host memory ----------------------------------------------------------------------------------
+
+static std::mutex g_host_mutex;
+static std::set<void*> g_host_blocks;
+
+void* ppcr_host_alloc(size_t bytes)
+{
+    if (bytes == 0) return nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lock(g_host_mutex);
+    g_host_blocks.insert(p);
+    return p;
+}
+
+int32_t ppcr_host_free(void* p)
+{
+    if (!p) return 0;
+    {
+        std::lock_guard<std::mutex> lock(g_host_mutex);
+        auto it = g_host_blocks.find(p);
+        if (it == g_host_blocks.end()) return 0;
+        g_host_blocks.erase(it);
+    }
+    cudaFreeHost(p);
+    cudaGetLastError();
+    return 1;
 }
 
 // ---- sharded pair -------------------------------------------------------------------------------------------

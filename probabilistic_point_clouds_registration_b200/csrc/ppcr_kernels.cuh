@@ -493,12 +493,13 @@ __global__ void PPCR_SEARCH_BOUNDS k_search(const PairDev* __restrict__ pairs)
         L.k = s_heap + threadIdx.x;
         L.init(m, cap);
         tree_search(geom, nodes, tgt_sorted, q.x, q.y, q.z, r2f, bound0, L, stack);
-        L.finish();
+        if (VAR == 16) L.finish();  // (the collect + select variant knows its m-th key only afterwards)
+        if (L.kth_key() != kKeyInf) kth = key_d2(L.kth_key());
+        if (VAR != 16) L.finish();  // the heap: sorted in place, the root is gone after this
         for (int s = L.begin(); s < L.end(); ++s) {
             const unsigned long long key = L.k[s * kSearchThreads];
             if (key != kKeyInf) search_store(out, i, cnt++, key);
         }
-        if (L.kth_key() != kKeyInf) kth = key_d2(L.kth_key());
         nbr_cnt[i] = cnt;
         nbr_kth[i] = kth;
         cnt_total += cnt;
@@ -703,13 +704,15 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
                 L.k = s_heap + threadIdx.x;
                 L.init(m);
                 tree_search(geom, nodes, tgt_sorted, q.x, q.y, q.z, r2f, bound0, L, stack);
+                const unsigned long long kk = L.kth_key();
+                L.finish();
                 int cnt = 0;
                 for (int s = 0; s < m; ++s) {
                     const unsigned long long key = L.k[s * kSearchThreads];
                     if (key != kKeyInf) search_store(out, i, cnt++, key);
                 }
                 nbr_cnt[i] = cnt;
-                nbr_kth[i] = L.kth_key() != kKeyInf ? key_d2(L.kth_key()) : kInf;
+                nbr_kth[i] = kk != kKeyInf ? key_d2(kk) : kInf;
                 cnt_total += cnt;
                 if (cnt >= P.overflow_at) st->row_overflow = 1;
             }
@@ -778,11 +781,12 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
                 L.k = s_heap + threadIdx.x;
                 L.init(m);
                 tree_search(geom, nodes, tgt_sorted, q.x, q.y, q.z, r2f, bound1, L, stack);
+                if (L.kth_key() != kKeyInf) kth = key_d2(L.kth_key());
+                L.finish();  // (bound1 came from whichever candidates were pushed first: without the sort the row's order would differ from run to run)
                 for (int s = 0; s < m; ++s) {
                     const unsigned long long key = L.k[s * kSearchThreads];
                     if (key != kKeyInf) search_store(out, i, cnt++, key);
                 }
-                if (L.kth_key() != kKeyInf) kth = key_d2(L.kth_key());
             }
             nbr_cnt[i] = cnt;
             nbr_kth[i] = kth;

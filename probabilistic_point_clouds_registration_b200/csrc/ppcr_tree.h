@@ -370,10 +370,25 @@ struct HeapList {
             sift_down(0, x);
         }
     }
-    PPCR_HD void finish() {}
+    // The product's list (FILL == 0) leaves the column in ascending (distance, index) order, unused slots (kKeyInf) last:
+    // the layout of a heap depends on the order its keys arrived in, and the order of a row's neighbours decides the last
+    // bits of the float32 row sums -- a row must be the same whichever kernel, bound or traversal produced it.  Heap sort
+    // in place; call kth_key() BEFORE finish().
+    PPCR_HD void finish()
+    {
+        if (FILL != 0) return;
+        const int full = m;
+        for (int e = full - 1; e > 0; --e) {
+            const unsigned long long top = k[0], x = k[e * STRIDE];
+            m = e;
+            sift_down(0, x);
+            k[e * STRIDE] = top;
+        }
+        m = full;
+    }
     PPCR_HD int begin() const { return FILL == 2 ? m - n : 0; }
     PPCR_HD int end() const { return FILL == 2 ? m : n; }
-    // key of the m-th best, kKeyInf when fewer than m real keys are held
+    // key of the m-th best, kKeyInf when fewer than m real keys are held (before finish())
     PPCR_HD unsigned long long kth_key() const { return n == m ? k[0] : kKeyInf; }
 };
 

@@ -49,7 +49,7 @@ ppcr_params to_c(const ProbPointCloudRegistrationParams& p)
 // The finite points of a cloud that is flagged !is_dense, in order.  PCL's own stages drop the others: VoxelGrid skips
 // non-finite points when the input is not dense, and KdTreeFLANN leaves them out of the tree it builds
 // (registration.cc:27-30,37-40,66-67).  The C ABI takes finite clouds only.
-bool finite_points(const pcl::PointCloud<pcl::PointXYZ>& cloud, std::vector<pcl::PointXYZ>* out)
+bool finite_points(const pcl::PointCloud<pcl::PointXYZ>& cloud, pcl::PointCloud<pcl::PointXYZ>::VectorType* out)
 {
     if (cloud.is_dense) return false;
     out->clear();
@@ -116,7 +116,7 @@ void ProbPointCloudRegistration::init()
     // Clouds flagged !is_dense (e.g. organised depth-sensor PCDs): the target's non-finite points never reach the search
     // structure, and a voxel-filtered source loses them in the filter.  An unfiltered source keeps them, as in the reference;
     // such a point finds no neighbour (every comparison with NaN fails) and contributes nothing.
-    std::vector<pcl::PointXYZ> finite_src, finite_tgt;
+    pcl::PointCloud<pcl::PointXYZ>::VectorType finite_src, finite_tgt;
     if (finite_points(*target_cloud_, &finite_tgt)) {
         tgt = finite_tgt.empty() ? nullptr : reinterpret_cast<const float*>(finite_tgt.data());
         n_tgt = static_cast<int64_t>(finite_tgt.size());
@@ -130,7 +130,7 @@ void ProbPointCloudRegistration::init()
         // the reference runs pcl::VoxelGrid on the caller's target cloud in place (registration.cc:34-41)
         int64_t n = 0;
         check(ppcr_filtered_target(handle_, nullptr, &n), "ppcr_filtered_target");
-        std::vector<pcl::PointXYZ> filtered(static_cast<std::size_t>(n));
+        pcl::PointCloud<pcl::PointXYZ>::VectorType filtered(static_cast<std::size_t>(n));
         if (n > 0) check(ppcr_filtered_target(handle_, reinterpret_cast<float*>(filtered.data()), &n), "ppcr_filtered_target");
         for (auto& p : filtered) p.data[3] = 1.0f;
         target_cloud_->points.swap(filtered);
