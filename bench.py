@@ -451,7 +451,7 @@ def bench_sharded_c4(args, ctx):
     d_mine = d_src.index_select(0, mine_idx).contiguous()
     torch.cuda.synchronize()
     src_ptr, n_mine = d_mine.data_ptr(), int(d_mine.shape[0])
-    times, parity = [], "ok"
+    times, exchange, parity = [], [], "ok"
     for rep in range(args.sharded_reps + 1):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx["barrier"]()
@@ -459,12 +459,14 @@ def bench_sharded_c4(args, ctx):
         with multi.ShardedRegistration(src_ptr, d_tgt.data_ptr(), params, rank, world, opt, n_source=n_mine, n_target=n) as reg:
             reg.align()
             hist, stats = reg.transformation_history(), reg.iteration_stats()
+            lt = reg.stage_times()
         ev1.record()
         torch.cuda.synchronize()
-        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ev0.elapsed_time(ev1), lt.exchange_wait_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rep > 0:
-            times.append(float(t.item()))
+            times.append(float(t[0].item()))
+            exchange.append((float(t[1].item()), int(lt.exchanges)))
         # parity, asserted on the box: bit-identical histories on every rank, and the single-GPU pose
         mine = torch.from_numpy(np.ascontiguousarray(hist)).cuda()
         shapes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
@@ -492,6 +494,12 @@ def bench_sharded_c4(args, ctx):
     rec["ms_all"] = [round(v, 2) for v in times]
     rec["speedup_vs_single_gpu"] = rec["single_gpu_ms"] / rec["ms_per_registration"]
     rec["sharded_parity"] = parity
+    if exchange:
+        worst = max(e[0] for e in exchange)
+        rec["exchange"] = {"per_registration_ms_max_over_ranks": worst, "exchanges": exchange[-1][1],
+                           "us_per_exchange": 1e3 * worst / max(exchange[-1][1], 1),
+                           "note": "SM clocks between the controller block starting to send its 25 doubles and having every peer's "
+                                   "(includes waiting for the slowest rank's evaluation to finish: load imbalance shows up here)"}
     rec["timing"] = "CUDA events around constructor (incl. the token exchange) + align() + read-back, clouds resident, max over ranks"
     return rec if rank == 0 else None
 

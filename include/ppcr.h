@@ -82,6 +82,8 @@ typedef struct ppcr_stage_times {   /* accumulated milliseconds + launch counts 
     float grid_build_ms, search_ms, eval_ms, controller_ms, transform_ms, voxel_ms;
     int32_t search_launches, eval_launches, controller_launches, transform_launches, total_launches;
     int32_t ticks;
+    int32_t exchanges;        /* sharded pairs: moment exchanges (= evaluations) so far */
+    float exchange_wait_ms;   /* sharded pairs: time the controller block spent sending its moments and waiting for the peers' */
 } ppcr_stage_times;
 
 typedef struct ppcr_handle ppcr_handle;

@@ -84,6 +84,7 @@ class StageTimes(C.Structure):
         ("transform_ms", C.c_float), ("voxel_ms", C.c_float),
         ("search_launches", C.c_int32), ("eval_launches", C.c_int32), ("controller_launches", C.c_int32),
         ("transform_launches", C.c_int32), ("total_launches", C.c_int32), ("ticks", C.c_int32),
+        ("exchanges", C.c_int32), ("exchange_wait_ms", C.c_float),
     ]
 
 
@@ -115,6 +116,17 @@ def lib():
                 "(there is no CPU fallback)")
         # PPCR_CUDA_LIB: a differently tuned build of the same library (tools/tune_build.sh), tuning runs only
         L = C.CDLL(os.environ.get("PPCR_CUDA_LIB", LIB_PATH))
+        if "PPCR_CUDA_LIB" in os.environ:  # an older build may lack the newest entry points: tolerate that in tuning runs
+            class _Missing:
+                pass
+
+            class _Tolerant:
+                def __getattr__(self, name):
+                    try:
+                        return getattr(L_real, name)
+                    except AttributeError:
+                        return _Missing()
+            L_real, L = L, _Tolerant()
         vp, i32, i64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
         L.ppcr_last_error.restype = C.c_char_p
         L.ppcr_version.restype = C.c_char_p

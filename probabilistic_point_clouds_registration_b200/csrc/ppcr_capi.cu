@@ -753,6 +753,7 @@ static void engine_commit(Engine& E)
         E.pairs[p].dev.search_queued = queued ? 1 : 0;
         E.pairs[p].dev.q_cand = getenv("PPCR_Q_CAND") ? atoi(getenv("PPCR_Q_CAND")) : search_q_cand(E.params.max_neighbours);
         E.pairs[p].dev.q_heavy = getenv("PPCR_Q_HEAVY") ? static_cast<float>(atof(getenv("PPCR_Q_HEAVY"))) : 0.75f;  // (tuning)
+        E.pairs[p].dev.q_flags = getenv("PPCR_Q_FLAGS") ? atoi(getenv("PPCR_Q_FLAGS")) : 0;
         E.pairs[p].dev.q_leaves = getenv("PPCR_Q_LEAVES") ? atoi(getenv("PPCR_Q_LEAVES")) : kQTaskPerQuery;
         host[p] = E.pairs[p].dev;
         max_m = std::max(max_m, host[p].m);
@@ -1399,6 +1400,13 @@ ppcr_status ppcr_get_stage_times(ppcr_handle* h, ppcr_stage_times* out)
         Engine& E = h->eng;
         use_engine(E);
         *out = E.times;
+        if (E.world > 1) {
+            const PairState s = download_state(E, 0);
+            int khz = 0;
+            CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, E.device));
+            out->exchanges = s.evals;
+            out->exchange_wait_ms = khz > 0 ? static_cast<float>(static_cast<double>(s.exchange_cycles) / khz) : 0.f;
+        }
         if (E.graph_ready) {  // the WHILE graph loops on the device: k_evalctl every tick, k_search once per outer iteration
             const PairState s = download_state(E, 0);
             out->ticks = s.ticks;

@@ -76,6 +76,7 @@ struct PairDev {
     int q_cand;                // k_search_q: candidate positions per query (search_q_cand(max_neighbours))
     float q_heavy;             // k_search_q: a query expecting more than q_heavy * q_cand candidates counts as heavy
     int overflow_at;           // a row that reaches this count may have lost neighbours (wide rows; INT_MAX otherwise)
+    int q_flags;               // k_search_q tuning switches (PPCR_Q_FLAGS): 1 = fallback rows are not sorted, 2 = the fallback starts from the incoming bound
     int q_leaves;              // k_search_q: leaves one query may queue before it falls back to tree_search (kQTaskPerQuery)
     unsigned char* q_scratch;  // k_search_q's task / candidate queues: one slab per block of its grid (all pairs share the pointer)
     float r2f;      // float(radius * radius): strict membership bound (FLANN)
@@ -493,9 +494,8 @@ __global__ void PPCR_SEARCH_BOUNDS k_search(const PairDev* __restrict__ pairs)
         L.k = s_heap + threadIdx.x;
         L.init(m, cap);
         tree_search(geom, nodes, tgt_sorted, q.x, q.y, q.z, r2f, bound0, L, stack);
-        if (VAR == 16) L.finish();  // (the collect + select variant knows its m-th key only afterwards)
+        L.finish();
         if (L.kth_key() != kKeyInf) kth = key_d2(L.kth_key());
-        if (VAR != 16) L.finish();  // the heap: sorted in place, the root is gone after this
         for (int s = L.begin(); s < L.end(); ++s) {
             const unsigned long long key = L.k[s * kSearchThreads];
             if (key != kKeyInf) search_store(out, i, cnt++, key);
@@ -555,6 +555,11 @@ PPCR_HD constexpr size_t search_q_smem(int m)
 PPCR_HD constexpr size_t search_q_scratch_per_block(int q_cand) { return 4u * kQTaskCap + 4u * kSearchThreads * static_cast<size_t>(q_cand); }
 
 constexpr uint32_t kQNoTask = 0xffffffffu;       // a queue entry nobody filled (phase B skips it)
+#if defined(PPCR_Q_FALLBACK_NOINLINE)  // measured: 137 against 130 ms over the first 12 searches of the 10M-point pair
+#define PPCR_Q_FALLBACK_INLINE __device__ __noinline__
+#else
+#define PPCR_Q_FALLBACK_INLINE __device__ __forceinline__
+#endif
 struct QEmit {  // phase A -> task queue
     uint32_t* tasks;
     int* n_tasks;
@@ -595,6 +600,43 @@ struct QCand {  // phase C: candidate c of one query -> position in the sorted t
     const uint32_t* cand;
     __device__ __forceinline__ int operator()(int c) const { return static_cast<int>(__ldcg(cand + c * kSearchThreads)); }
 };
+
+// The one-by-one fallback of k_search_q: a query whose candidate list (or the block's task queue) overflowed is searched by its
+// thread alone, 127 others waiting.  What the list does hold are DISTINCT targets within the radius, so when there are m of them
+// their m-th smallest distance bounds the true one -- and it is tight (a sample of a far larger candidate set), where the bound
+// the query came in with was loose enough to overflow the list: the walk then opens a handful of leaves instead of the hundreds
+// the loose bound touches (it was 130 us of a 350 us block on the 1M-point pair; -DPPCR_Q_PROFILE).  The register allocation of
+// the whole kernel is sensitive to this code (48 registers, 16 bytes spilled): holding the m-th key in a register across the
+// store loop -- here or in the heavy path -- cost the 10M-point pair, whose chunks mostly take the heap walk, 10-35 % of its
+// search time; the keys are therefore read back from the column after the stores.
+PPCR_Q_FALLBACK_INLINE int search_q_fallback(const TreeGeom& geom, const TreeNode* __restrict__ nodes, const float4* __restrict__ tgt_sorted,
+                                             const SearchOut& out, float4 q, float r2f, float bound0, int have, int m, int flags,
+                                             const uint32_t* cand, unsigned long long* heap, int* stack, int i, float* kth)
+{
+    float bound1 = bound0;
+    if (have >= m && !(flags & 2)) {
+        unsigned long long kk;
+        const QCand at{cand};
+        select_candidates<kSearchThreads>(tgt_sorted, at, have, m, q.x, q.y, q.z, heap, &kk);
+        if (kk != kKeyInf) bound1 = fminf(bound1, key_d2(kk));
+    }
+    HeapList<kSearchThreads, 0> L;
+    L.k = heap;
+    L.init(m);
+    tree_search(geom, nodes, tgt_sorted, q.x, q.y, q.z, r2f, bound1, L, stack);
+    // bound1 came from whichever candidates were pushed first, so the heap's layout differs from run to run: sorted, the row is
+    // the same bits every time (the m-th key then sits in the last slot)
+    const bool sorted = !(flags & 1);
+    if (sorted) L.sort();
+    int cnt = 0;
+    for (int s = 0; s < m; ++s) {
+        const unsigned long long key = L.k[s * kSearchThreads];
+        if (key != kKeyInf) search_store(out, i, cnt++, key);
+    }
+    const unsigned long long kk = sorted ? L.k[(m - 1) * kSearchThreads] : L.kth_key();
+    if (kk != kKeyInf) *kth = key_d2(kk);
+    return cnt;
+}
 
 __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __restrict__ pairs)
 {
@@ -704,15 +746,13 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
                 L.k = s_heap + threadIdx.x;
                 L.init(m);
                 tree_search(geom, nodes, tgt_sorted, q.x, q.y, q.z, r2f, bound0, L, stack);
-                const unsigned long long kk = L.kth_key();
-                L.finish();
                 int cnt = 0;
                 for (int s = 0; s < m; ++s) {
                     const unsigned long long key = L.k[s * kSearchThreads];
                     if (key != kKeyInf) search_store(out, i, cnt++, key);
                 }
                 nbr_cnt[i] = cnt;
-                nbr_kth[i] = kk != kKeyInf ? key_d2(kk) : kInf;
+                nbr_kth[i] = L.kth_key() != kKeyInf ? key_d2(L.kth_key()) : kInf;
                 cnt_total += cnt;
                 if (cnt >= P.overflow_at) st->row_overflow = 1;
             }
@@ -764,29 +804,8 @@ __global__ void __launch_bounds__(kSearchThreads) k_search_q(const PairDev* __re
                 for (int s = 0; s < n; ++s) search_store(out, i, cnt++, s_heap[threadIdx.x + s * kSearchThreads]);
                 if (kk != kKeyInf) kth = key_d2(kk);
             } else {
-                // The list overflowed (or a queue did): this thread searches its query alone, 127 others waiting.  What the list does
-                // hold are DISTINCT targets within the radius, so when there are m of them their m-th smallest distance bounds the
-                // true one -- and it is tight (a sample of a far larger candidate set), where the bound the query came in with was
-                // loose enough to overflow the list.  The walk then opens a handful of leaves instead of the hundreds the loose
-                // bound touches (it was 130 us of a 350 us block; -DPPCR_Q_PROFILE).
-                float bound1 = bound0;
-                const int have = min(n_c, q_cand);
-                if (have >= m) {
-                    unsigned long long kk;
-                    const QCand at{s_cand + threadIdx.x};
-                    select_candidates<kSearchThreads>(tgt_sorted, at, have, m, q.x, q.y, q.z, s_heap + threadIdx.x, &kk);
-                    if (kk != kKeyInf) bound1 = fminf(bound1, key_d2(kk));
-                }
-                HeapList<kSearchThreads, 0> L;
-                L.k = s_heap + threadIdx.x;
-                L.init(m);
-                tree_search(geom, nodes, tgt_sorted, q.x, q.y, q.z, r2f, bound1, L, stack);
-                if (L.kth_key() != kKeyInf) kth = key_d2(L.kth_key());
-                L.finish();  // (bound1 came from whichever candidates were pushed first: without the sort the row's order would differ from run to run)
-                for (int s = 0; s < m; ++s) {
-                    const unsigned long long key = L.k[s * kSearchThreads];
-                    if (key != kKeyInf) search_store(out, i, cnt++, key);
-                }
+                cnt = search_q_fallback(geom, nodes, tgt_sorted, out, q, r2f, bound0, min(n_c, q_cand), m, P.q_flags, s_cand + threadIdx.x,
+                                        s_heap + threadIdx.x, stack, i, &kth);
             }
             nbr_cnt[i] = cnt;
             nbr_kth[i] = kth;
@@ -1347,6 +1366,7 @@ __global__ void __launch_bounds__(eval_threads(kFast), kFast ? kEvalFastBlocks :
         // ranks hold bit-identical sums and take identical decisions.  The exchange is a one-shot all-gather
         // written straight into the peers' mailboxes over NVLink; a sequence stamp doubles as the ready flag.
         const int seq = st->ticks + 1;
+        const long long t_exchange = clock64();
         if (threadIdx.x < kMailDoubles) {
             double payload = 0.0;
             if (threadIdx.x < kNSum) payload = s_sum[threadIdx.x];
@@ -1400,6 +1420,7 @@ __global__ void __launch_bounds__(eval_threads(kFast), kFast ? kEvalFastBlocks :
             __syncthreads();
             if (threadIdx.x == 0 && st->phase == PH_SEARCH) st->K = static_cast<int64_t>(s_sum[kNSum]);
         }
+        if (threadIdx.x == 0) st->exchange_cycles += clock64() - t_exchange;
         __syncthreads();
     }
 

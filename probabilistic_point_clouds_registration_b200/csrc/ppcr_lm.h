@@ -93,6 +93,7 @@ struct PairState {
     int32_t current_iteration, num_unuseful, phase, apply_dT;
     int64_t K;        // correspondences of the current association (search kernel)
     int64_t K_total;  // summed over outer iterations
+    int64_t exchange_cycles;  // sharded pairs: SM clocks the controller block spent in the moment exchange (send + wait), summed
     int32_t ticks, evals;
     int32_t error;
     int32_t search_cursor;  // next chunk of queries to hand out (persistent search kernel)
@@ -579,6 +580,7 @@ PPCR_HD void state_init(PairState* s, const Config* cfg)
     s->apply_dT = 0;
     s->K = 0;
     s->K_total = 0;
+    s->exchange_cycles = 0;
     s->ticks = 0;
     s->evals = 0;
     s->error = 0;

@@ -370,11 +370,14 @@ struct HeapList {
             sift_down(0, x);
         }
     }
-    // The product's list (FILL == 0) leaves the column in ascending (distance, index) order, unused slots (kKeyInf) last:
-    // the layout of a heap depends on the order its keys arrived in, and the order of a row's neighbours decides the last
-    // bits of the float32 row sums -- a row must be the same whichever kernel, bound or traversal produced it.  Heap sort
-    // in place; call kth_key() BEFORE finish().
-    PPCR_HD void finish()
+    PPCR_HD void finish() {}
+    // Leaves the column (FILL == 0) in ascending (distance, index) order, unused slots (kKeyInf) last.  The layout of a heap
+    // depends on the order its keys arrived in -- fixed for a given query, tree and starting bound, which is all k_search and
+    // the heavy chunks of k_search_q need for a reproducible row (the order of a row's neighbours decides the last bits of its
+    // float32 sums) -- but the one-by-one fallback of k_search_q starts from a bound that depends on which candidates other
+    // threads pushed first, so it sorts.  (Sorting everywhere was measured: the 10M-point pair 375 -> 467 ms, the sift paths of
+    // the 32 lanes of a warp all differ.)  Heap sort in place; call kth_key() BEFORE sort().
+    PPCR_HD void sort()
     {
         if (FILL != 0) return;
         const int full = m;
@@ -388,7 +391,7 @@ struct HeapList {
     }
     PPCR_HD int begin() const { return FILL == 2 ? m - n : 0; }
     PPCR_HD int end() const { return FILL == 2 ? m : n; }
-    // key of the m-th best, kKeyInf when fewer than m real keys are held (before finish())
+    // key of the m-th best, kKeyInf when fewer than m real keys are held (before sort())
     PPCR_HD unsigned long long kth_key() const { return n == m ? k[0] : kKeyInf; }
 };
 

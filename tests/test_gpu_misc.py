@@ -40,7 +40,9 @@ def test_invalid_arguments(capi):
         capi.Registration(c, c, capi.make_params(radius=-1.0))
     assert e.value.code == 1 and "radius" in str(e.value)
     with pytest.raises(capi.PpcrError):
-        capi.Registration(c, c, capi.make_params(max_neighbours=0))
+        capi.Registration(c, c, capi.make_params(dof=0.0))
+    with capi.Registration(c, c, capi.make_params(max_neighbours=0)):  # pcl's "all in-radius targets": accepted (rows of 128)
+        pass
     bad = c.copy()
     bad[3, 1] = np.nan
     with pytest.raises(capi.PpcrError):

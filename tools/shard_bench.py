@@ -54,6 +54,10 @@ for mode in os.environ.get("SHARD_MODES", "contig").split(","):
             reg.align()
             stats = reg.iteration_stats()
             hist = reg.transformation_history()
+            ex = reg.stage_times()
+            if rep == reps:
+                print(f"[rank {rank}] {mode}: {ex.exchanges} exchanges, {ex.exchange_wait_ms:.2f} ms in them "
+                      f"({1e3 * ex.exchange_wait_ms / max(ex.exchanges, 1):.1f} us each, waiting for the slowest rank included)", flush=True)
             if stages:
                 lt = reg.stage_times()
                 print(f"[rank {rank}] {mode} rep {rep}: search {lt.search_ms:.1f} ms in {lt.search_launches} launches, eval {lt.eval_ms:.1f} ms in "
