@@ -451,22 +451,29 @@ def bench_sharded_c4(args, ctx):
     d_mine = d_src.index_select(0, mine_idx).contiguous()
     torch.cuda.synchronize()
     src_ptr, n_mine = d_mine.data_ptr(), int(d_mine.shape[0])
-    times, exchange, parity = [], [], "ok"
+    times, exchange, phases, parity = [], [], [], "ok"
     for rep in range(args.sharded_reps + 1):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx["barrier"]()
         ev0.record()
+        w0 = time.perf_counter()
         with multi.ShardedRegistration(src_ptr, d_tgt.data_ptr(), params, rank, world, opt, n_source=n_mine, n_target=n) as reg:
+            w1 = time.perf_counter()
             reg.align()
+            w2 = time.perf_counter()
             hist, stats = reg.transformation_history(), reg.iteration_stats()
             lt = reg.stage_times()
+            w2b = time.perf_counter()
+        w3 = time.perf_counter()
         ev1.record()
         torch.cuda.synchronize()
-        t = torch.tensor([ev0.elapsed_time(ev1), lt.exchange_wait_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ev0.elapsed_time(ev1), lt.exchange_wait_ms, 1e3 * (w1 - w0), 1e3 * (w2 - w1), 1e3 * (w2b - w2), 1e3 * (w3 - w2b)],
+                         dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rep > 0:
             times.append(float(t[0].item()))
             exchange.append((float(t[1].item()), int(lt.exchanges)))
+            phases.append([round(float(v), 2) for v in t[2:].tolist()])
         # parity, asserted on the box: bit-identical histories on every rank, and the single-GPU pose
         mine = torch.from_numpy(np.ascontiguousarray(hist)).cuda()
         shapes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
@@ -492,6 +499,7 @@ def bench_sharded_c4(args, ctx):
                     parity = f"FAILED: pose differs from the single-GPU run by {ang:.2e} rad / {dt:.2e} m"
     rec["ms_per_registration"] = float(np.median(times))
     rec["ms_all"] = [round(v, 2) for v in times]
+    rec["phases_ms_all"] = {"constructor_incl_token_exchange, align, read_back, destroy (host clock, max over ranks)": phases}
     rec["speedup_vs_single_gpu"] = rec["single_gpu_ms"] / rec["ms_per_registration"]
     rec["sharded_parity"] = parity
     if exchange:
@@ -765,7 +773,7 @@ def main():
     ap.add_argument("--batch-single", type=int, default=192, help="N > 1: pairs of rank 0's single-GPU reference leg")
     ap.add_argument("--sharded-rings", type=int, default=320, help="rings of the sharded pair (320 x 31250 = 10M points); 0 = skip")
     ap.add_argument("--sharded-az", type=int, default=31250)
-    ap.add_argument("--sharded-reps", type=int, default=3)
+    ap.add_argument("--sharded-reps", type=int, default=5)
     ap.add_argument("--sharded-block", type=int, default=8192, help="points per run of the block-cyclic deal of the sharded pair")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

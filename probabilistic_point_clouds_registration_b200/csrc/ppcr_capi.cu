@@ -248,19 +248,31 @@ struct Engine {
     {
         if (g_launch_sink == &times.total_launches) g_launch_sink = &g_launch_sink_dummy;
         cudaSetDevice(device);
+        const bool trace = getenv("PPCR_TRACE") != nullptr;
+        auto t0 = std::chrono::steady_clock::now();
+        auto mark = [&](const char* what) {
+            if (!trace) return;
+            const auto t1 = std::chrono::steady_clock::now();
+            fprintf(stderr, "[ppcr trace] destroy: %-19s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+            t0 = t1;
+        };
         for (auto& e : events) {
             cudaEventDestroy(e.a);
             cudaEventDestroy(e.b);
         }
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (graph) cudaGraphDestroy(graph);
+        mark("events + graph");
         for (auto& p : pairs) p.release();
         d_pairs.release();
         d_loop.release();
         flush.release();
         q_scratch.release();
+        mark("stream-ordered frees");
         if (stream) cudaStreamSynchronize(stream);  // the frees above are stream-ordered
+        mark("stream synchronize");
         if (own_stream && stream) cudaStreamDestroy(stream);
+        mark("stream destroy");
         if (g_alloc_stream == stream) g_alloc_stream = nullptr;
     }
 };

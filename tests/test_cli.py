@@ -132,3 +132,21 @@ def test_cli_gaussian_with_filters(cli, oracle, tmp_path):
     assert abs(len(hist) - ref.n_outer) <= 1
     t = np.array([float(v) for v in hist[-1][0].split(",")])
     assert np.linalg.norm(t - ref.transformation[:3, 3]) < 2e-4
+
+
+@pytest.mark.gpu
+def test_cli_unlimited_neighbours_and_its_failure_exit(cli, oracle, tmp_path):
+    """`-m 0` reaches pcl's "every target within the radius" (CLI:43-44 -> registration.cc:74-75): served while no row needs
+    128 neighbours or more; a row that would stops the program with the failure exit code instead of a truncated answer."""
+    src, tgt, _ = synth.config1_plane_sphere(seed=5, n_plane=1500, n_sphere=1000)
+    write_pcd(tmp_path / "s.pcd", src, "binary")
+    write_pcd(tmp_path / "t.pcd", tgt, "binary")
+    r = _run([cli, "s.pcd", "t.pcd", "-m", "0", "-r", "0.7", "-v"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    hist = re.findall(r"^T: (.*?) \|\|\| R: (.*)$", r.stdout, flags=re.M)
+    ref = oracle.align(src, tgt, oracle.make_params(max_neighbours=0, dof=5.0, radius=0.7), oracle.make_options(inner_kind=1))
+    assert abs(len(hist) - ref.n_outer) <= 1
+    t = np.array([float(v) for v in hist[-1][0].split(",")])
+    assert np.linalg.norm(t - ref.transformation[:3, 3]) < 2e-4
+    r = _run([cli, "s.pcd", "t.pcd", "-m", "0", "-r", "3"], tmp_path)
+    assert r.returncode == 1 and "128" in (r.stderr + r.stdout)

@@ -91,3 +91,27 @@ def test_replay_metrics_match_a_host_replay(capi):
     assert np.array_equal(np.concatenate([g1, g2]), np.concatenate([mse_gt[:half], np.zeros(len(inc) - half)]))
     assert np.array_equal(np.concatenate([p1, p2]), mse_prev)
     assert mse_gt[-1] < mse_gt[0]
+
+
+def test_page_locked_host_memory(capi):
+    """ppcr_host_alloc / ppcr_host_free (the storage of the PCL stand-in's clouds): blocks it handed out are recognised and freed,
+    foreign pointers are refused, and a cloud living in such a block registers like any other."""
+    import ctypes as C
+    L = capi.lib()
+    n = 5000
+    p = L.ppcr_host_alloc(n * 16)
+    assert p
+    buf = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n, 4))
+    src, tgt, _ = synth.config1_plane_sphere(seed=9, n_plane=n // 2, n_sphere=n - n // 2)
+    buf[:] = tgt
+    with capi.Registration(src, buf, capi.make_params(max_neighbours=8, radius=0.6)) as a, \
+            capi.Registration(src, tgt, capi.make_params(max_neighbours=8, radius=0.6)) as b:
+        a.align()
+        b.align()
+        assert np.array_equal(a.transformation_history(), b.transformation_history())
+    del buf
+    assert L.ppcr_host_free(p) == 1
+    assert L.ppcr_host_free(p) == 0                       # already gone
+    other = np.zeros(4, dtype=np.float32)
+    assert L.ppcr_host_free(other.ctypes.data) == 0       # not ours: the caller frees it its own way
+    assert not L.ppcr_host_alloc(0)

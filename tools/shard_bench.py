@@ -55,8 +55,8 @@ for mode in os.environ.get("SHARD_MODES", "contig").split(","):
             stats = reg.iteration_stats()
             hist = reg.transformation_history()
             ex = reg.stage_times()
-            if rep == reps:
-                print(f"[rank {rank}] {mode}: {ex.exchanges} exchanges, {ex.exchange_wait_ms:.2f} ms in them "
+            if rep >= 1:
+                print(f"[rank {rank}] {mode} rep {rep}: {1e3 * (time.perf_counter() - t0):.1f} ms so far; {ex.exchanges} exchanges, {ex.exchange_wait_ms:.2f} ms in them "
                       f"({1e3 * ex.exchange_wait_ms / max(ex.exchanges, 1):.1f} us each, waiting for the slowest rank included)", flush=True)
             if stages:
                 lt = reg.stage_times()
