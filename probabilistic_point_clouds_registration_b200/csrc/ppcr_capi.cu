@@ -161,6 +161,7 @@ static int search_cap(int max_nn)
 constexpr int kSearchQueuedMaxM = 32;  // k_search_q's shared-memory heap columns: m KiB per block on top of 35 KiB of queues
 constexpr size_t kEvalSmem = static_cast<size_t>(kNSum) * kEvalThreads * sizeof(double);  // per-thread moment columns
 constexpr int kDefaultLeafCap = 32;
+constexpr int kEvalBatchBlocks = 4;  // evaluation blocks per SM of a batch lane (see pair_setup)
 
 // kernel-launch bookkeeping for ppcr_get_stage_times: every launch site outside the tick adds to the engine the
 // calling thread is currently working for
@@ -240,6 +241,7 @@ struct Engine {
     ppcr_stage_times times{};
     // sharded mode
     int rank = 0, world = 1;
+    bool batch_lane = false;  // one of several lanes of ppcr_align_batch working on the same device
     int requested_max_neighbours = 0;  // what the caller asked for (params.max_neighbours holds the row capacity)
     // L2 flush buffer for ppcr_time_kernel
     DevBuf<float4> flush;
@@ -671,7 +673,15 @@ static void pair_setup(Engine& E, Pair& P, const float* src, int64_t n_src, cons
     {
         const bool fast = !E.opts.exact_weights;
         // (the asynchronous-gather variant stages the target points too: 64 KB of shared memory per block at m = 10, three blocks per SM)
-        const int per_sm = fast ? (eval_async(E.params.max_neighbours) ? std::min(kEvalFastBlocks, kEvalAsyncBlocks) : kEvalFastBlocks) : E.eval_blocks_per_sm;
+        int per_sm = fast ? (eval_async(E.params.max_neighbours) ? std::min(kEvalFastBlocks, kEvalAsyncBlocks) : kEvalFastBlocks) : E.eval_blocks_per_sm;
+        // A lane of a batch shares the device with the other lanes' kernels: a smaller evaluation grid leaves them registers and
+        // shared memory to run beside it (PPCR_EVAL_PER_SM / PPCR_EVAL_PER_SM_BATCH: tuning)
+        static const int env_single = getenv("PPCR_EVAL_PER_SM") ? atoi(getenv("PPCR_EVAL_PER_SM")) : 0;
+        static const int env_batch = getenv("PPCR_EVAL_PER_SM_BATCH") ? atoi(getenv("PPCR_EVAL_PER_SM_BATCH")) : 0;
+        if (fast) {
+            const int want = E.batch_lane ? (env_batch > 0 ? env_batch : kEvalBatchBlocks) : (env_single > 0 ? env_single : per_sm);
+            per_sm = std::max(1, std::min(per_sm, want));
+        }
         D.n_eval_blocks = std::max(1, std::min(ceil_div(std::max(D.n_src, 1), eval_threads(fast)), per_sm * std::max(g_sm_count, 1)));
     }
     D.n_eval_groups = ceil_div(D.n_eval_blocks, kFoldGroup);
@@ -1897,6 +1907,7 @@ ppcr_status ppcr_align_batch_devices(const ppcr_pair* pairs, int32_t n_pairs, co
                 ppcr_options my_opt = lane_opt;
                 my_opt.device = device_ids[lane_index % n_dev];  // lanes interleave over the devices
                 engine_init(E, *params, &my_opt, true);
+                E.batch_lane = lanes > 1;
                 E.pairs.resize(1);
                 const bool on_dev = E.opts.input_on_device != 0;
                 for (;;) {

@@ -380,6 +380,42 @@ PPCR_HD void rowf_end_s(const RowAccF* a, double sx, double sy, double sz, doubl
 }
 PPCR_HD void rowf_end(const RowAccF* a, double sx, double sy, double sz, double* acc) { rowf_end_s<1>(a, sx, sy, sz, acc); }
 
+// The same 24 contributions of a finished row as float32 values (v[m], moment index m as above): the source coordinates are
+// float32 to begin with and the row quotients are, so every product carries one more float32 rounding (6e-8 relative) on top of
+// the row sums' own.  Used by the evaluation kernel, which adds the rows of a warp in float32 (a fixed tree over 32 rows) before
+// anything goes into a float64 accumulator.
+PPCR_HD void rowf_end_f(const RowAccF* a, float sx, float sy, float sz, float* v)
+{
+    const float inv = a->a0 > 0.f ? 1.0f / a->a0 : 0.f;
+    const float W = a->a1 * inv;
+    const float r0 = a->ar[0] * inv, r1 = a->ar[1] * inv, r2 = a->ar[2] * inv;
+    const float Wx = W * sx, Wy = W * sy, Wz = W * sz;
+    v[M_S0] = W;
+    v[M_S1 + 0] = Wx;
+    v[M_S1 + 1] = Wy;
+    v[M_S1 + 2] = Wz;
+    v[M_S2 + 0] = Wx * sx;
+    v[M_S2 + 1] = Wx * sy;
+    v[M_S2 + 2] = Wx * sz;
+    v[M_S2 + 3] = Wy * sy;
+    v[M_S2 + 4] = Wy * sz;
+    v[M_S2 + 5] = Wz * sz;
+    v[M_SR + 0] = r0;
+    v[M_SR + 1] = r1;
+    v[M_SR + 2] = r2;
+    v[M_C + 0] = sx * r0;
+    v[M_C + 1] = sx * r1;
+    v[M_C + 2] = sx * r2;
+    v[M_C + 3] = sy * r0;
+    v[M_C + 4] = sy * r1;
+    v[M_C + 5] = sy * r2;
+    v[M_C + 6] = sz * r0;
+    v[M_C + 7] = sz * r1;
+    v[M_C + 8] = sz * r2;
+    v[M_COST] = 0.5f * a->ac * inv;
+    v[M_ROWS] = 1.0f;
+}
+
 // weight of one correspondence once the row statistics are known (parity dumps only); pw = p_w as a float pair
 PPCR_HD float rowf_finished_weight(const RowAccF* a, const WeightCfg& wc, float yx, float yy, float yz, const PointHL& pw)
 {

@@ -40,10 +40,13 @@ namespace ppcr {
 constexpr int kSearchThreads = 128;  // one query per thread
 constexpr int kEvalThreads = 256;      // float64 ("exact") evaluation: one row per thread, grid-stride, moments in shared memory
 constexpr int kEvalFastThreads = 128;  // float32-row evaluation: tiles of 128 rows staged by bulk copies, moments in registers
-#ifndef PPCR_EVAL_FAST_BLOCKS
-#define PPCR_EVAL_FAST_BLOCKS 4
+#ifndef PPCR_EVAL_LANEACC
+#define PPCR_EVAL_LANEACC 1  // 1: the rows of a warp are added by a float32 transpose-reduction, one float64 accumulator per lane
 #endif
-constexpr int kEvalFastBlocks = PPCR_EVAL_FAST_BLOCKS;  // resident blocks per SM the fast evaluation is held to (4: 128 registers per thread)
+#ifndef PPCR_EVAL_FAST_BLOCKS
+#define PPCR_EVAL_FAST_BLOCKS (PPCR_EVAL_LANEACC ? 5 : 4)
+#endif
+constexpr int kEvalFastBlocks = PPCR_EVAL_FAST_BLOCKS;  // resident blocks per SM the fast evaluation is held to (5: 96 registers per thread, no spills; 6: 80 with spills, no faster)
 #ifndef PPCR_EVAL_STAGES
 #define PPCR_EVAL_STAGES 3
 #endif
@@ -1047,10 +1050,30 @@ __device__ __forceinline__ void eval_issue_tile(const PairDev& P, const EvalStag
     if (lane == ((S.m + 1) & 31)) bulk_g2s(dst + seg * S.m + seg, P.src + row0, kEvalFastThreads * 16u, bar);
 }
 
+// Sum over the 32 lanes of a warp of 32 values per lane, transposed: lane L returns sum_over_lanes v[L].  Recursive halving --
+// a lane keeps one half of its values and trades the other half with its partner, 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of
+// 32 x 5 -- in a fixed tree, so the float32 result is the same on every run.  All 32 lanes must call it.
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32])
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float keep = upper ? v[i + half] : v[i];
+            const float send = upper ? v[i] : v[i + half];
+            v[i] = keep + __shfl_xor_sync(kFull, send, half);
+        }
+    }
+    return v[0];
+}
+
 template <int WM, bool SAME, bool ASYNC>
 __device__ __forceinline__ void eval_rows_fast(const PairDev& P, const EvalStage& S, const Pose& pe, const Pose& pw,
                                                const WeightCfg& wc, double* __restrict__ racc)
 {
+    // PPCR_EVAL_LANEACC: racc is ONE double, the lane's accumulator of moment `lane` (lanes 24..31 add zeros); else the thread's 24
     constexpr int kU = PPCR_EVAL_BATCH;
     const int n_tiles = (P.n_src + kEvalFastThreads - 1) / kEvalFastThreads;
     const int tile_step = P.n_eval_blocks;
@@ -1090,6 +1113,11 @@ __device__ __forceinline__ void eval_rows_fast(const PairDev& P, const EvalStage
         const int* s_pos = reinterpret_cast<const int*>(sb) + threadIdx.x;
         int cnt = reinterpret_cast<const int*>(sb + static_cast<size_t>(kEvalFastThreads) * 4u * S.m)[threadIdx.x];
         if (tile * kEvalFastThreads + static_cast<int>(threadIdx.x) >= n_src) cnt = 0;
+#if PPCR_EVAL_LANEACC
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = 0.f;
+#endif
         if (cnt > 0) {
             const float4 sp = reinterpret_cast<const float4*>(sb + static_cast<size_t>(kEvalFastThreads) * 4u * (S.m + 1))[threadIdx.x];
             const double sx = sp.x, sy = sp.y, sz = sp.z;
@@ -1124,7 +1152,11 @@ __device__ __forceinline__ void eval_rows_fast(const PairDev& P, const EvalStage
                 for (int u = 0; u < kU - 1; ++u)
                     if (k0 + u < cnt) rowf_add_t<WM, SAME>(&row, wc, y[u].x, y[u].y, y[u].z, he, dw);
             }
+#if PPCR_EVAL_LANEACC
+            rowf_end_f(&row, sp.x, sp.y, sp.z, v);
+#else
             rowf_end_s<1>(&row, sx, sy, sz, racc);
+#endif
             if (!ASYNC && P.dump_w) {
                 // Parity dump (ppcr_weights_normal_eq): the weight of every correspondence of this row, from the row statistics
                 // just folded into the moments and the same staged positions, residual arithmetic and weight terms.
@@ -1151,6 +1183,10 @@ __device__ __forceinline__ void eval_rows_fast(const PairDev& P, const EvalStage
                 }
             }
         }
+#if PPCR_EVAL_LANEACC
+        // the 32 rows of the warp, added in float32 by a fixed tree; only the sums of whole warps meet the float64 accumulator
+        racc[0] += static_cast<double>(warp_transpose_sum(v));
+#endif
         __syncthreads();  // every thread is done with this stage: refill it with the tile kEvalStages ahead
         if (threadIdx.x < 32) {
             const int next = tile + kEvalStages * tile_step;
@@ -1216,9 +1252,10 @@ __global__ void __launch_bounds__(eval_threads(kFast), kFast ? kEvalFastBlocks :
     const Pose& pe = s_pe;
     const Pose& pw = s_pw;
     const WeightCfg wc = P.wcfg;
-    double racc[kNSum];  // fast path: the thread's 24 moments, in registers
+    // fast path: the lane's accumulator (PPCR_EVAL_LANEACC) or the thread's 24 moments, in registers
+    double racc[(kFast && PPCR_EVAL_LANEACC) ? 1 : kNSum];
 #pragma unroll
-    for (int k = 0; k < kNSum; ++k) racc[k] = 0.0;
+    for (int k = 0; k < ((kFast && PPCR_EVAL_LANEACC) ? 1 : kNSum); ++k) racc[k] = 0.0;
     if constexpr (kFast) {
         // pose_w == pose_e on the first evaluation of every outer iteration: one residual serves both uses
         bool same = true;
@@ -1284,11 +1321,15 @@ __global__ void __launch_bounds__(eval_threads(kFast), kFast ? kEvalFastBlocks :
     }
     // fixed-shape reduction: xor-shuffle tree inside the warp, then warps in index order
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if constexpr (kFast && PPCR_EVAL_LANEACC) {
+        if (lane < kNSum) s_red[warp][lane] = racc[0];  // lane L already holds the warp's sum of moment L
+    } else {
 #pragma unroll
-    for (int k = 0; k < kNSum; ++k) {
-        double v = racc[k];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-        if (lane == 0) s_red[warp][k] = v;
+        for (int k = 0; k < kNSum; ++k) {
+            double v = racc[k];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+            if (lane == 0) s_red[warp][k] = v;
+        }
     }
     __syncthreads();
     if (threadIdx.x < kNSum) {

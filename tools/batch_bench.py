@@ -23,7 +23,11 @@ for i in range(n_pairs):
     pairs.append((np.ascontiguousarray(s), np.ascontiguousarray(t)))
 print(f"generated {n_pairs} pairs of {len(pairs[0][0])} points in {time.perf_counter() - t0:.1f} s")
 params = capi.make_params(**bench.WORKLOADS["c5"]["params"])
-capi.align_batch(pairs[:2], params, slots=2)  # warm-up
+# warm-up: every lane's share of the memory pool exists, and the clocks are up (the GPU idled while the pairs were generated:
+# a timed run right after a short warm-up came out anywhere between 150 and 450 pairs/s)
+t0 = time.perf_counter()
+while time.perf_counter() - t0 < 2.0:
+    capi.align_batch(pairs[:min(n_pairs, 8 * max(slot_list))], params, slots=max(slot_list))
 for slots in slot_list:
     t0 = time.perf_counter()
     T, n_outer, corr = capi.align_batch(pairs, params, slots=slots)

@@ -1,7 +1,5 @@
-# usage: tools/run_variants.sh name1 name2 ...   (csrc/tune_<name>.so; "default" = the product library)
-for v in "$@"; do
-  if [ "$v" = default ]; then unset PPCR_CUDA_LIB; else export PPCR_CUDA_LIB=probabilistic_point_clouds_registration_b200/csrc/tune_$v.so; fi
-  echo "=== $v"
-  C4_ITERS=12 python tools/c4_probe.py "" 2>&1 | grep "rep 1"
-  python tools/run_once.py c3 1000 1 2>&1 | grep "rep 1" | sed 's/; launches.*//'
-done
+run() { export PPCR_CUDA_LIB=probabilistic_point_clouds_registration_b200/csrc/tune_$1.so; shift; for b in "$@"; do echo -n "$PPCR_CUDA_LIB batch per_sm $b: "; PPCR_EVAL_PER_SM_BATCH=$b python tools/batch_bench.py 192 6 6 | tail -2 | tr '\n' ' '; echo; done; }
+run old4 4 3
+run la4 4 3 2
+run la5 5 4 3
+run la6 6 4
