@@ -1,4 +1,4 @@
-python -m pytest tests/test_gpu_search.py tests/test_gpu_align.py -m gpu -x -q 2>&1 | tail -4
-for f in 0 4; do echo "== PPCR_Q_FLAGS=$f"; PPCR_Q_FLAGS=$f python tools/run_once.py c3 1000 1 2>&1 | grep "rep 1" | sed 's/; launches.*//'; PPCR_Q_FLAGS=$f C4_ITERS=12 python tools/c4_probe.py "" 2>&1 | grep "rep 1"; done
-PPCR_Q_FLAGS=0 python tools/batch_bench.py 96 6 | tail -1
-PPCR_Q_FLAGS=4 python tools/batch_bench.py 96 6 | tail -1
+bash tools/ncu_capture.sh r02 "4 1 0" c3 > /dev/null 2>&1
+python tools/time_kernels.py c3 > gpurun_out/r02_time_kernels.txt 2>&1
+PPCR_DRIVER=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r02_launches_c3.csv python bench.py --steps 2 --warmup 1 --no-cpu --headline-only > gpurun_out/r02_launches_bench.log 2>&1
+ls -la gpurun_out | grep r02; cat gpurun_out/r02_time_kernels.txt
