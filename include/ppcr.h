@@ -95,7 +95,8 @@ void ppcr_default_options(ppcr_options* o);
 
 /* Replaces the ProbPointCloudRegistration constructor (src/prob_point_cloud_registration.cc:15-49): copies the
  * source, voxel-filters source and target when the leaf sizes are > 0, builds the target octree.
- * max_neighbours must be in [1, 128] (the reference also allows 0 / negative = unlimited: PPCR_ERR_UNSUPPORTED). */
+ * max_neighbours <= 0 (pcl: every target within the radius) and > 128 run with rows of 128; ppcr_align then returns
+ * PPCR_ERR_UNSUPPORTED if a source point has 128 or more targets within the radius (never a truncated row). */
 ppcr_status ppcr_create(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, int64_t n_tgt,
                         const ppcr_params* params, ppcr_handle** out);
 ppcr_status ppcr_create_ex(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, int64_t n_tgt,
