@@ -187,6 +187,8 @@ ppcr_status ppcr_replay_metrics(ppcr_handle* h, float* cloud_xyzw, const float* 
 
 /* pcl::transformPointCloud(cloud, cloud, Affine3d) at :110-112: double math, float store, in place. */
 ppcr_status ppcr_transform(float* xyzw, int64_t n, const double* T4x4_rowmajor);
+/* the same on options->device / options->stream, in place on a device-resident cloud when options->input_on_device */
+ppcr_status ppcr_transform_ex(float* xyzw, int64_t n, const double* T4x4_rowmajor, const ppcr_options* options);
 
 /* The closest-point metric helpers of include/prob_point_cloud_registration/utilities.hpp:28-234 in one call.  Each of them
  * builds a kd-tree on cloud2, takes nearestKSearch(k = 1) of every cloud1 point -- a SQUARED distance, float -- and reduces

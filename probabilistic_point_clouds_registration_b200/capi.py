@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "ppcr_create_ex", "ppcr_destroy", "ppcr_align", "ppcr_has_converged", "ppcr_history", "ppcr_increment_history",
     "ppcr_iteration_stats",
     "ppcr_filtered_source", "ppcr_filtered_target", "ppcr_association", "ppcr_get_stage_times", "ppcr_time_kernel",
-    "ppcr_voxel_filter", "ppcr_time_voxel_filter", "ppcr_radius_search", "ppcr_weights_normal_eq", "ppcr_iteration_solve", "ppcr_transform",
+    "ppcr_voxel_filter", "ppcr_time_voxel_filter", "ppcr_radius_search", "ppcr_weights_normal_eq", "ppcr_iteration_solve", "ppcr_transform", "ppcr_transform_ex",
     "ppcr_replay_metrics", "ppcr_closest_point_metrics",
     "ppcr_align_batch", "ppcr_align_batch_devices", "ppcr_host_alloc", "ppcr_host_free", "ppcr_shard_export", "ppcr_shard_connect",
 ]
@@ -152,6 +152,7 @@ def lib():
         L.ppcr_weights_normal_eq.argtypes = [vp, i64, vp, i64, vp, vp, i32, f64, i32, vp, vp, i32, vp, vp]
         L.ppcr_iteration_solve.argtypes = [vp, i64, vp, i64, vp, vp, i32, C.POINTER(Params), C.POINTER(Options), f64, vp, vp, vp]
         L.ppcr_transform.argtypes = [vp, i64, vp]
+        L.ppcr_transform_ex.argtypes = [vp, i64, vp, C.POINTER(Options)]
         L.ppcr_replay_metrics.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
         L.ppcr_closest_point_metrics.argtypes = [vp, i64, vp, i64, f64, C.POINTER(Options), C.POINTER(ClosestMetrics), vp]
         L.ppcr_align_batch.argtypes = [C.POINTER(PairDesc), i32, C.POINTER(Params), C.POINTER(Options), i32, vp, vp, vp]
@@ -405,10 +406,17 @@ def iteration_solve(src, tgt, idx, count, params: Params, function_tolerance=1e-
                                        n_correspondences=st.n_correspondences)
 
 
-def transform(cloud, T):
-    out = _cloud(cloud).copy()
+def transform(cloud, T, options: Options | None = None, n_points=None):
+    """pcl::transformPointCloud.  With options.input_on_device `cloud` is a device pointer (moved in place, n_points given)."""
     T = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
-    _check(lib().ppcr_transform(out.ctypes.data, len(out), T.ctypes.data))
+    if options is not None and options.input_on_device:
+        _check(lib().ppcr_transform_ex(int(cloud), int(n_points), T.ctypes.data, C.byref(options)))
+        return None
+    out = _cloud(cloud).copy()
+    if options is None:
+        _check(lib().ppcr_transform(out.ctypes.data, len(out), T.ctypes.data))
+    else:
+        _check(lib().ppcr_transform_ex(out.ctypes.data, len(out), T.ctypes.data, C.byref(options)))
     return out
 
 

@@ -1720,26 +1720,44 @@ ppcr_status ppcr_iteration_solve(const float* src, int64_t n_src, const float* t
     });
 }
 
-ppcr_status ppcr_transform(float* xyzw, int64_t n, const double* T)
+ppcr_status ppcr_transform_ex(float* xyzw, int64_t n, const double* T, const ppcr_options* options)
 {
     if ((n > 0 && !xyzw) || !T || n < 0) return fail(PPCR_ERR_INVALID, "bad argument");
     return guarded([&] {
-        select_device(0);
-        g_alloc_stream = nullptr;  // the legacy default stream, like the copies and the launch below
+        const int device = options ? options->device : 0;
+        const bool on_device = options && options->input_on_device;
+        select_device(device);
+        CK(cudaSetDevice(device));
         if (n == 0) return;
+        cudaStream_t st = options && options->stream ? static_cast<cudaStream_t>(options->stream) : nullptr;
+        bool own = false;
+        if (!st) {
+            CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            own = true;
+        }
+        g_alloc_stream = st;
         DevBuf<float4> d;
         DevBuf<double> dT;
-        d.reserve(n);
         dT.reserve(16);
-        CK(cudaMemcpy(d.p, xyzw, static_cast<size_t>(n) * 16, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(dT.p, T, 16 * sizeof(double), cudaMemcpyHostToDevice));
-        k_transform_plain<<<std::min(ceil_div(n, 256), 8 * std::max(g_sm_count, 1)), 256>>>(d.p, static_cast<int>(n), dT.p);
+        CK(cudaMemcpyAsync(dT.p, T, 16 * sizeof(double), cudaMemcpyHostToDevice, st));
+        float4* pts = reinterpret_cast<float4*>(xyzw);
+        if (!on_device) {
+            d.reserve(n);
+            CK(cudaMemcpyAsync(d.p, xyzw, static_cast<size_t>(n) * 16, cudaMemcpyHostToDevice, st));
+            pts = d.p;
+        }
+        k_transform_plain<<<std::min(ceil_div(n, 256), 8 * std::max(g_sm_count, 1)), 256, 0, st>>>(pts, static_cast<int>(n), dT.p);
         CK(cudaGetLastError());
-        CK(cudaMemcpy(xyzw, d.p, static_cast<size_t>(n) * 16, cudaMemcpyDeviceToHost));
+        if (!on_device) CK(cudaMemcpyAsync(xyzw, d.p, static_cast<size_t>(n) * 16, cudaMemcpyDeviceToHost, st));
         d.release();
         dT.release();
+        CK(cudaStreamSynchronize(st));  // T (and a host cloud) belong to the caller again when this returns
+        if (own) cudaStreamDestroy(st);
+        g_alloc_stream = nullptr;
     });
 }
+
+ppcr_status ppcr_transform(float* xyzw, int64_t n, const double* T) { return ppcr_transform_ex(xyzw, n, T, nullptr); }
 
 ppcr_status ppcr_replay_metrics(ppcr_handle* h, float* cloud_xyzw, const float* gt_xyzw, int64_t n, int32_t first, int32_t count,
                                 double* mse_gt, double* mse_prev)

@@ -38,6 +38,32 @@ def block_cyclic_indices(n: int, rank: int, world: int, block: int = 4096) -> np
     return idx[idx < n]
 
 
+def morton_order(cloud: np.ndarray, bits: int = 10) -> np.ndarray:
+    """Indices of `cloud` ([N,>=3] float) along a Z-order curve over its bounding cube (`bits` per axis)."""
+    xyz = np.asarray(cloud)[:, :3].astype(np.float64)
+    lo = xyz.min(axis=0)
+    span = float((xyz.max(axis=0) - lo).max()) or 1.0
+    q = np.minimum(((xyz - lo) * ((1 << bits) / span)).astype(np.int64), (1 << bits) - 1)
+    key = np.zeros(len(xyz), dtype=np.int64)
+    for b in range(bits):
+        for a in range(3):
+            key |= ((q[:, a] >> b) & 1) << (3 * b + a)
+    return np.argsort(key, kind="stable")
+
+
+def morton_chunk_indices(cloud: np.ndarray, rank: int, world: int, chunk: int = 4096) -> np.ndarray:
+    """Source points of `rank` when the cloud is cut into runs of `chunk` points ALONG A Z-ORDER CURVE and the runs are dealt
+    round robin: every rank gets compact patches at the cloud's full local density (the 32 queries of a warp stay neighbours
+    in space, which is what the octree walk's speed depends on) and, there being thousands of patches, an even share of the
+    dense and the sparse regions.  Dealing runs of the scan's own storage order (block_cyclic_indices) thins every region by
+    the number of ranks instead: 1.85 ms per search and rank on eight GPUs where 1/8 of the single-GPU search is 1.05."""
+    order = morton_order(cloud)
+    n_chunks = (len(order) + chunk - 1) // chunk
+    mine = np.arange(rank, n_chunks, world, dtype=np.int64)
+    pos = (mine[:, None] * chunk + np.arange(chunk, dtype=np.int64)[None, :]).ravel()
+    return order[pos[pos < len(order)]]
+
+
 def deal_pairs(n_pairs: int, rank: int, world: int) -> list[int]:
     """Pairs of a batch owned by `rank` (contiguous blocks, same rule as slice_bounds)."""
     lo, hi = slice_bounds(n_pairs, rank, world)

@@ -32,6 +32,15 @@ def test_transform_bit_exact(capi, oracle):
     got = capi.transform(src, T)
     ref = oracle.transform(src, T)
     assert np.array_equal(got[:, :3].view(np.uint32), ref[:, :3].view(np.uint32))
+    # ppcr_transform_ex: on a given device and stream, in place on a device-resident cloud
+    import torch
+    stream = torch.cuda.Stream()
+    d = torch.from_numpy(src).cuda()
+    stream.wait_stream(torch.cuda.current_stream())
+    capi.transform(d.data_ptr(), T, capi.make_options(input_on_device=True, stream=stream.cuda_stream), n_points=len(src))
+    assert np.array_equal(d.cpu().numpy()[:, :3].view(np.uint32), ref[:, :3].view(np.uint32))
+    got = capi.transform(src, T, capi.make_options(device=torch.cuda.device_count() - 1))
+    assert np.array_equal(got[:, :3].view(np.uint32), ref[:, :3].view(np.uint32))
 
 
 def test_invalid_arguments(capi):

@@ -1,4 +1,4 @@
-bash tools/ncu_capture.sh r02 "4 1 0" c3 > /dev/null 2>&1
-python tools/time_kernels.py c3 > gpurun_out/r02_time_kernels.txt 2>&1
-PPCR_DRIVER=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r02_launches_c3.csv python bench.py --steps 2 --warmup 1 --no-cpu --headline-only > gpurun_out/r02_launches_bench.log 2>&1
-ls -la gpurun_out | grep r02; cat gpurun_out/r02_time_kernels.txt
+for f in 0/8 3/8 7/8; do
+echo "== fake $f"
+SHARD_FAKE=$f SHARD_STAGES=1 SHARD_MODES=block:8192,morton:4096,morton:1250000 python tools/shard_bench.py 320 31250 1 2>&1 | grep "rep 1: search"
+done

@@ -34,14 +34,19 @@ d_tgt = torch.from_numpy(tgt).cuda()
 stages = bool(os.environ.get("SHARD_STAGES"))
 opt = capi.make_options(device=local, input_on_device=True, driver=1 if stages else 0, record_stage_times=stages)
 # how the source is dealt to the ranks: contig (slice_bounds), strided (rank::world), block:<points> (block-cyclic)
+# SHARD_FAKE="rank/world": pick that rank's share of the source but run it alone (world 1): what a share costs without any exchange
+fake = os.environ.get("SHARD_FAKE")
+d_rank, d_world = (int(v) for v in fake.split("/")) if fake else (rank, world)
 for mode in os.environ.get("SHARD_MODES", "contig").split(","):
     if mode == "contig":
-        lo, hi = multi.slice_bounds(len(src), rank, world)
+        lo, hi = multi.slice_bounds(len(src), d_rank, d_world)
         mine = src[lo:hi]
     elif mode == "strided":
-        mine = np.ascontiguousarray(src[rank::world])
+        mine = np.ascontiguousarray(src[d_rank::d_world])
+    elif mode.startswith("morton:"):
+        mine = np.ascontiguousarray(src[multi.morton_chunk_indices(src, d_rank, d_world, int(mode.split(":")[1]))])
     else:
-        mine = np.ascontiguousarray(src[multi.block_cyclic_indices(len(src), rank, world, int(mode.split(":")[1]))])
+        mine = np.ascontiguousarray(src[multi.block_cyclic_indices(len(src), d_rank, d_world, int(mode.split(":")[1]))])
     d_src = torch.from_numpy(mine).cuda()
     times = []
     for rep in range(reps + 1):
