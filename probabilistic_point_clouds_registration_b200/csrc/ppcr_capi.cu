@@ -479,8 +479,9 @@ static void build_target_tree(Engine& E, Pair& P, int leaf_cap)
         level_nodes = std::min<long long>(level_nodes * 8, g.n_nodes_cap);
     }
     k_tree_finalize<<<4 * std::max(g_sm_count, 1), 256, 0, st>>>(P.nodes.p, P.tree_counters.p, g.n_nodes_cap);
+    k_tree_leaf_boxes<<<8 * std::max(g_sm_count, 1), 256, 0, st>>>(P.nodes.p, P.tgt_sorted.p, P.tree_counters.p, g.n_nodes_cap);
     CK(cudaGetLastError());
-    note_launches(3 + kTreeBits);
+    note_launches(4 + kTreeBits);
     P.dev.tree = g;
     P.dev.nodes = P.nodes.p;
     P.dev.tgt_sorted = P.tgt_sorted.p;

@@ -336,6 +336,13 @@ __global__ void k_tree_finalize(TreeNode* __restrict__ nodes, const TreeCounters
     for (int ni = blockIdx.x * blockDim.x + threadIdx.x; ni < n; ni += gridDim.x * blockDim.x) tree_mark_leaf_children(nodes, ni);
 }
 
+// every non-empty leaf but a root leaf gets the bounding box of its points (ppcr_tree.h, "tight leaf boxes"); after k_tree_finalize
+__global__ void k_tree_leaf_boxes(TreeNode* __restrict__ nodes, const float4* __restrict__ pts, const TreeCounters* __restrict__ tc, int cap)
+{
+    const int n = min(tc->n_nodes, cap);
+    for (int ni = blockIdx.x * blockDim.x + threadIdx.x; ni < n; ni += gridDim.x * blockDim.x) tree_box_leaf(nodes, pts, ni);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // radius search: one thread per query walks the octree with a register-resident sorted top-m list
 // ------------------------------------------------------------------------------------------------------------

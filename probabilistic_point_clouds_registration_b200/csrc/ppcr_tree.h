@@ -306,6 +306,60 @@ PPCR_HD void tree_mark_leaf_children(TreeNode* nodes, int ni)
     nodes[ni].mask = (nodes[ni].mask & 0xffff) | bits;
 }
 
+// ---- tight leaf boxes ------------------------------------------------------------------------------------------
+//
+// The octree's cells are cubes; the points of a scan lie on surfaces.  A search ball that cuts a leaf's cube usually misses
+// the few points inside it: of the leaves a query of the 1M-point pair reaches, a third hold no point within its bound, and of
+// the leaves reached by a query that still has fewer than m neighbours (bound = the full radius: 8 % of the rows while the
+// pose is off) seven in eight (tools/tree_stats_real.py).  Once the tree is built nobody reads the cube of a LEAF any more --
+// its parent computes the children's lower bounds from its own centre -- so every leaf but a root leaf stores the bounding
+// box of its points in those fields: (cx, cy, cz) = min corner, (half, child, mask) = max corner (the last two as float bits).
+// One 32-byte node load then answers "can this leaf hold a point within the bound" exactly: the box distance is computed with
+// the operations of dist2_exact in the same order, and rounding is monotone, so it never exceeds the distance of a point inside.
+// Must run after tree_mark_leaf_children has looked at every node (it recognises a leaf by child < 0, which the box overwrites).
+// A thread only touches its own node.
+PPCR_HD void tree_box_leaf(TreeNode* nodes, const float4* __restrict__ pts, int ni)
+{
+    TreeNode leaf = nodes[ni];
+    if (ni == 0 || leaf.child >= 0 || leaf.end <= leaf.begin) return;  // the root, inner nodes, empty and unused slots stay as they are
+    float lo[3] = {pts[leaf.begin].x, pts[leaf.begin].y, pts[leaf.begin].z};
+    float hi[3] = {lo[0], lo[1], lo[2]};
+    for (int j = leaf.begin + 1; j < leaf.end; ++j) {
+        const float4 p = pts[j];
+        lo[0] = p.x < lo[0] ? p.x : lo[0];
+        lo[1] = p.y < lo[1] ? p.y : lo[1];
+        lo[2] = p.z < lo[2] ? p.z : lo[2];
+        hi[0] = p.x > hi[0] ? p.x : hi[0];
+        hi[1] = p.y > hi[1] ? p.y : hi[1];
+        hi[2] = p.z > hi[2] ? p.z : hi[2];
+    }
+    leaf.cx = lo[0];
+    leaf.cy = lo[1];
+    leaf.cz = lo[2];
+    leaf.half = hi[0];
+    leaf.child = static_cast<int>(float_bits(hi[1]));
+    leaf.mask = static_cast<int>(float_bits(hi[2]));
+    nodes[ni] = leaf;
+}
+
+// lower bound of dist2_exact(q, p) over the points p of a boxed leaf (never above any of them)
+PPCR_HD float leaf_box_lower_bound(const TreeNode& leaf, float qx, float qy, float qz)
+{
+    const float hy = bits_float(static_cast<uint32_t>(leaf.child)), hz = bits_float(static_cast<uint32_t>(leaf.mask));
+    float gx = f_sub(leaf.cx, qx), gy = f_sub(leaf.cy, qy), gz = f_sub(leaf.cz, qz);
+    const float ux = f_sub(qx, leaf.half), uy = f_sub(qy, hy), uz = f_sub(qz, hz);
+    gx = gx > ux ? gx : ux;
+    gy = gy > uy ? gy : uy;
+    gz = gz > uz ? gz : uz;
+    gx = gx > 0.f ? gx : 0.f;
+    gy = gy > 0.f ? gy : 0.f;
+    gz = gz > 0.f ? gz : 0.f;
+    float acc = f_mul(gx, gx);
+    acc = f_add(acc, f_mul(gy, gy));
+    acc = f_add(acc, f_mul(gz, gz));
+    return acc;
+}
+
 // binary max-heap of the m best keys in addressable memory, element i at k[i * STRIDE] (the search kernel keeps one
 // column per thread in shared memory, STRIDE = block size).  Once m candidates are known a better one replaces the
 // root and sifts down.  How the first m get in is what FILL selects; measured on the 1M-point pair (profiles/):
@@ -549,6 +603,19 @@ PPCR_HD float axis_gap2(float q, float c, float hi)
 // rounding in the lower bound can only keep a subtree that exact arithmetic would prune, never the reverse.
 PPCR_HD float prune_threshold(float bound_d2) { return bound_d2 * 1.00002f; }
 
+// the leaf children `first + c` (c a set bit of mask) that can hold a point within bound_d2 of q
+PPCR_HD int tree_prune_leaf_mask(const TreeNode* __restrict__ nodes, int first, int mask, float qx, float qy, float qz, float bound_d2)
+{
+    int keep = 0;
+    for (int mk = mask; mk; mk &= mk - 1) {
+        const int c = lowest_bit(static_cast<uint32_t>(mk));
+        const TreeNode leaf = load_node(nodes + first + c);
+        if (!(leaf_box_lower_bound(leaf, qx, qy, qz) > bound_d2)) keep |= 1 << c;
+        else PPCR_STAT(leaves_skipped, 1);
+    }
+    return keep;
+}
+
 // Leaves the (at most m) nearest targets with d2 < r2f in L.  pts = Morton-sorted target, .w = original index.
 // bound0 <= r2f is a caller-supplied squared distance within which at least m targets are KNOWN to lie (r2f when
 // nothing is known): points farther than it cannot be among the m nearest, so subtrees beyond it are never opened.
@@ -653,6 +720,11 @@ PPCR_HD void tree_search(const TreeGeom& g, const TreeNode* __restrict__ nodes, 
                 continue;
             }
             const TreeNode n = load_node(nodes + pend[2 * np]);
+            // (a leaf other than a root leaf carries the box of its points, tree_box_leaf)
+            if (pend[2 * np] != 0 && leaf_box_lower_bound(n, qx, qy, qz) > bound_d2) {
+                PPCR_STAT(leaves_skipped, 1);
+                continue;
+            }
             PPCR_STAT(leaves, 1);
             PPCR_STAT(points, n.end - n.begin);
             // 32 points at a time, in two passes so that the threads of a warp stay together: first a plain distance
@@ -768,7 +840,10 @@ PPCR_HD bool tree_collect_leaves(const TreeGeom& g, const TreeNode* __restrict__
     int sp = 0;
     stack[sp++] = at;
     bool ok = true;
-    auto leaves = [&](int first, int mask) { ok = emit(first, mask) && ok; };
+    auto leaves = [&](int first, int mask) {
+        mask = tree_prune_leaf_mask(nodes, first, mask, qx, qy, qz, bound_d2);
+        if (mask) ok = emit(first, mask) && ok;
+    };
     auto inner = [&](int child) { stack[sp++] = child; };
     while (sp > 0) tree_open_node(g, nodes, stack[--sp], qx, qy, qz, thr, leaves, inner);
     return ok;
@@ -801,28 +876,6 @@ PPCR_HD void leaf_candidates(const TreeNode* __restrict__ nodes, const float4* _
 #endif
     PPCR_STAT(leaves, 1);
     PPCR_STAT(points, n.end - n.begin);
-#if defined(PPCR_TREE_STATS) && !defined(__CUDA_ARCH__)
-    {   // experiment: how many of the queued leaves would a tight bounding box of their points have pruned
-        float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
-        for (int j = n.begin; j < n.end; ++j) {
-            const float c[3] = {pts[j].x, pts[j].y, pts[j].z};
-            for (int a = 0; a < 3; ++a) {
-                lo[a] = c[a] < lo[a] ? c[a] : lo[a];
-                hi[a] = c[a] > hi[a] ? c[a] : hi[a];
-            }
-        }
-        const float q[3] = {qx, qy, qz};
-        float d2 = 0.f;
-        for (int a = 0; a < 3; ++a) {
-            const float d = q[a] < lo[a] ? lo[a] - q[a] : (q[a] > hi[a] ? q[a] - hi[a] : 0.f);
-            d2 += d * d;
-        }
-        if (d2 > limit_d2) {
-            PPCR_STAT(leaves_skipped, 1);
-            PPCR_STAT(stack_skipped, n.end - n.begin);
-        }
-    }
-#endif
     const int last = n.end - 1;
     for (int j0 = n.begin; j0 < n.end; j0 += 32) {
         const int stop = n.end - j0 < 32 ? n.end - j0 : 32;

@@ -257,6 +257,7 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
         le = std::min(n_nodes, g.n_nodes_cap);
     }
     for (int ni = 0; ni < std::min(n_nodes, g.n_nodes_cap); ++ni) tree_mark_leaf_children(nodes.data(), ni);
+    for (int ni = 0; ni < std::min(n_nodes, g.n_nodes_cap); ++ni) tree_box_leaf(nodes.data(), pts.data(), ni);
     if (out_n_nodes) *out_n_nodes = n_nodes;
     int64_t total = 0;
     int stack[2 * kTreeStack];

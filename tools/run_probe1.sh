@@ -1,4 +1,6 @@
-for f in 0/8 3/8 7/8; do
-echo "== fake $f"
-SHARD_FAKE=$f SHARD_STAGES=1 SHARD_MODES=block:8192,morton:4096,morton:1250000 python tools/shard_bench.py 320 31250 1 2>&1 | grep "rep 1: search"
-done
+python -m pytest tests/test_gpu_search.py tests/test_gpu_metrics.py -m gpu -x -q 2>&1 | tail -3
+python tools/run_once.py c3 1000 1 2>&1 | grep "rep 1" | sed 's/; launches.*//'
+python tools/run_once.py c3 1000 0 2>&1 | grep "rep 1" | sed 's/; 34 outer.*//'
+C4_ITERS=12 python tools/c4_probe.py "" 2>&1 | grep "rep 1"
+python tools/batch_bench.py 192 6 6 | tail -2
+python tools/time_kernels.py c3 | head -4
