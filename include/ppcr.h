@@ -256,6 +256,15 @@ int32_t ppcr_host_free(void* p);
 ppcr_status ppcr_shard_export(ppcr_handle* h, int32_t rank, int32_t world, uint8_t* token_out);
 ppcr_status ppcr_shard_connect(ppcr_handle* h, const uint8_t* tokens /* [world][PPCR_SHARD_TOKEN_BYTES], rank order */);
 
+/* The same for the GPUs of ONE process: the host source is dealt to the listed devices in runs of 8192 consecutive points (round
+ * robin), every device gets the whole target, one host thread per device builds a handle, the mailboxes are connected by peer
+ * access and the ranks run align() together.  out_T: [*n_inout][16] accumulated poses per outer iteration (ppcr_history),
+ * *n_inout <- outer iterations run; out_corr (may be NULL) <- association size summed over them.  params->source_filter_size
+ * must be 0 (a voxel filter would act on every share separately): PPCR_ERR_UNSUPPORTED. */
+ppcr_status ppcr_align_sharded(const float* src_xyzw, int64_t n_src, const float* tgt_xyzw, int64_t n_tgt, const ppcr_params* params,
+                               const ppcr_options* options, const int32_t* device_ids, int32_t n_dev, double* out_T,
+                               int32_t* n_inout, int64_t* out_corr);
+
 #ifdef __cplusplus
 }
 #endif

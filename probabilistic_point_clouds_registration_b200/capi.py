@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "ppcr_filtered_source", "ppcr_filtered_target", "ppcr_association", "ppcr_get_stage_times", "ppcr_time_kernel",
     "ppcr_voxel_filter", "ppcr_time_voxel_filter", "ppcr_radius_search", "ppcr_weights_normal_eq", "ppcr_iteration_solve", "ppcr_transform", "ppcr_transform_ex",
     "ppcr_replay_metrics", "ppcr_closest_point_metrics",
-    "ppcr_align_batch", "ppcr_align_batch_devices", "ppcr_host_alloc", "ppcr_host_free", "ppcr_shard_export", "ppcr_shard_connect",
+    "ppcr_align_batch", "ppcr_align_batch_devices", "ppcr_host_alloc", "ppcr_host_free", "ppcr_shard_export", "ppcr_shard_connect", "ppcr_align_sharded",
 ]
 
 SHARD_TOKEN_BYTES = 128
@@ -162,6 +162,7 @@ def lib():
         L.ppcr_host_free.argtypes = [vp]
         L.ppcr_shard_export.argtypes = [vp, i32, i32, vp]
         L.ppcr_shard_connect.argtypes = [vp, vp]
+        L.ppcr_align_sharded.argtypes = [vp, i64, vp, i64, C.POINTER(Params), C.POINTER(Options), vp, i32, vp, vp, vp]
         for name in EXPORTED_SYMBOLS:
             fn = getattr(L, name)
             if name not in ("ppcr_last_error", "ppcr_version", "ppcr_destroy", "ppcr_default_params", "ppcr_default_options",
@@ -458,3 +459,17 @@ def align_batch(pairs, params: Params, options: Options | None = None, slots=0, 
         _check(lib().ppcr_align_batch_devices(descs, n, C.byref(params), popt, ids, len(devices), int(slots), T.ctypes.data,
                                               n_outer.ctypes.data, corr.ctypes.data))
     return T[:n].reshape(n, 4, 4), n_outer[:n], corr[:n]
+
+
+def align_sharded(source, target, params: Params, devices, options: Options | None = None, max_history=4096):
+    """ppcr_align_sharded: one pair over the GPUs `devices` of this process.  Returns (history [n,4,4], correspondences)."""
+    s, t = _cloud(source), _cloud(target)
+    ids = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+    hist = np.zeros((max_history, 16))
+    n = C.c_int32(max_history)
+    corr = C.c_int64(0)
+    _check(lib().ppcr_align_sharded(s.ctypes.data, len(s), t.ctypes.data, len(t), C.byref(params),
+                                    C.byref(options) if options is not None else None, ids, len(devices), hist.ctypes.data,
+                                    C.byref(n), C.byref(corr)))
+    k = min(n.value, max_history)
+    return hist[:k].reshape(k, 4, 4), int(corr.value)

@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cfloat>
 #include <climits>
+#include <condition_variable>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1978,6 +1979,97 @@ ppcr_status ppcr_align_batch(const ppcr_pair* pairs, int32_t n_pairs, const ppcr
 {
     const int32_t device = options ? options->device : 0;
     return ppcr_align_batch_devices(pairs, n_pairs, params, options, &device, 1, slots, out_T, out_n_outer, out_corr);
+}
+
+// ---- one pair over several GPUs of one process ------------------------------------------------------------------
+
+namespace {
+struct HostBarrier {  // reusable barrier for the rank threads of ppcr_align_sharded
+    std::mutex mu;
+    std::condition_variable cv;
+    int count = 0, generation = 0, parties;
+    explicit HostBarrier(int n) : parties(n) {}
+    void wait()
+    {
+        std::unique_lock<std::mutex> lock(mu);
+        const int gen = generation;
+        if (++count == parties) {
+            count = 0;
+            ++generation;
+            cv.notify_all();
+        } else {
+            cv.wait(lock, [&] { return gen != generation; });
+        }
+    }
+};
+}  // namespace
+
+ppcr_status ppcr_align_sharded(const float* src, int64_t n_src, const float* tgt, int64_t n_tgt, const ppcr_params* params,
+                               const ppcr_options* options, const int32_t* device_ids, int32_t n_dev, double* out_T,
+                               int32_t* n_inout, int64_t* out_corr)
+{
+    if (!params || !device_ids || n_dev < 1 || n_dev > 8 || !n_inout || n_src < 0 || n_tgt < 0 || (n_src > 0 && !src) || (n_tgt > 0 && !tgt))
+        return fail(PPCR_ERR_INVALID, "bad argument");
+    if (options && options->input_on_device) return fail(PPCR_ERR_INVALID, "ppcr_align_sharded takes host buffers");
+    if (params->source_filter_size > 0)
+        return fail(PPCR_ERR_UNSUPPORTED, "a source voxel filter would act on every share separately: filter the source first (ppcr_voxel_filter)");
+    return guarded([&] {
+        constexpr int64_t kRun = 8192;  // points per run of the block-cyclic deal
+        std::vector<uint8_t> tokens(static_cast<size_t>(n_dev) * PPCR_SHARD_TOKEN_BYTES);
+        HostBarrier barrier(n_dev);
+        std::mutex err_mutex;
+        StatusError first_error{PPCR_OK, ""};
+        std::atomic<int> failed{0};
+        const int cap = *n_inout;
+        auto rank_main = [&](int r) {
+            ppcr_handle* h = nullptr;
+            auto note = [&](ppcr_status st) {
+                if (st == PPCR_OK) return true;
+                std::lock_guard<std::mutex> lock(err_mutex);
+                if (first_error.code == PPCR_OK) first_error = StatusError{st, g_last_error};
+                failed.store(1);
+                return false;
+            };
+            // this rank's share of the source: runs r, r + n_dev, r + 2 n_dev, ... of kRun consecutive points
+            std::vector<float> share;
+            const int64_t n_runs = (n_src + kRun - 1) / kRun;
+            for (int64_t b = r; b < n_runs; b += n_dev) {
+                const int64_t lo = b * kRun, hi = std::min(n_src, lo + kRun);
+                share.insert(share.end(), src + 4 * lo, src + 4 * hi);
+            }
+            ppcr_options opt;
+            if (options) opt = *options; else ppcr_default_options(&opt);
+            opt.device = device_ids[r];
+            opt.stream = nullptr;
+            bool ok = note(ppcr_create_ex(share.empty() ? nullptr : share.data(), static_cast<int64_t>(share.size() / 4), tgt, n_tgt, params, &opt, &h));
+            if (ok && n_dev > 1) ok = note(ppcr_shard_export(h, r, n_dev, tokens.data() + static_cast<size_t>(r) * PPCR_SHARD_TOKEN_BYTES));
+            barrier.wait();  // every token is written (or a rank has failed)
+            if (!failed.load() && n_dev > 1) ok = note(ppcr_shard_connect(h, tokens.data()));
+            barrier.wait();  // every rank is connected: nobody starts writing into a mailbox whose owner is not ready
+            if (!failed.load()) ok = note(ppcr_align(h));
+            if (ok && !failed.load() && r == 0) {
+                int32_t n = cap;
+                if (note(ppcr_history(h, out_T, &n))) *n_inout = n;
+                if (out_corr) {
+                    try {
+                        use_engine(h->eng);
+                        *out_corr = download_state(h->eng, 0).K_total;
+                    } catch (...) {
+                        note(PPCR_ERR_CUDA);
+                    }
+                }
+            }
+            ppcr_destroy(h);
+        };
+        if (n_dev == 1) {
+            rank_main(0);
+        } else {
+            std::vector<std::thread> threads;
+            for (int r = 0; r < n_dev; ++r) threads.emplace_back(rank_main, r);
+            for (auto& t : threads) t.join();
+        }
+        if (first_error.code != PPCR_OK) throw first_error;
+    });
 }
 
 // ---- page-locked host memory ----------------------------------------------------------------------------------
