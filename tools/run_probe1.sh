@@ -1,1 +1,4 @@
-for d in 1 2 4 6; do echo "== PPCR_SEARCH_Q_BATCH_DIV=$d"; PPCR_SEARCH_Q_BATCH_DIV=$d python tools/batch_bench.py 256 6 6 8 2>&1 | tail -3; done
+bash tools/ncu_capture.sh r02 "4 1 0" c3 > /dev/null 2>&1
+python tools/time_kernels.py c3 > gpurun_out/r02_time_kernels.txt 2>&1
+PPCR_DRIVER=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r02_launches_c3.csv python bench.py --steps 2 --warmup 1 --no-cpu --headline-only > gpurun_out/r02_launches_bench.log 2>&1
+cat gpurun_out/r02_time_kernels.txt
