@@ -318,6 +318,7 @@ static ShardGlobals g_shard;
 struct DeviceInfo {
     bool ready = false;
     int sm_count = 0;
+    int clock_khz = 0;  // (queried once: cudaDevAttrClockRate takes tens of milliseconds on a busy host)
 };
 static DeviceInfo g_devices[64];
 static std::mutex g_devices_mutex;
@@ -352,6 +353,7 @@ static void select_device(int device)
             unsigned long long keep = ~0ull;
             CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
             info.sm_count = sms;
+            CK(cudaDeviceGetAttribute(&info.clock_khz, cudaDevAttrClockRate, device));
             info.ready = true;
         }
         g_sm_count = info.sm_count;
@@ -1426,8 +1428,7 @@ ppcr_status ppcr_get_stage_times(ppcr_handle* h, ppcr_stage_times* out)
         *out = E.times;
         if (E.world > 1) {
             const PairState s = download_state(E, 0);
-            int khz = 0;
-            CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, E.device));
+            const int khz = g_devices[E.device].clock_khz;
             out->exchanges = s.evals;
             out->exchange_wait_ms = khz > 0 ? static_cast<float>(static_cast<double>(s.exchange_cycles) / khz) : 0.f;
         }
