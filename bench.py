@@ -526,8 +526,7 @@ def bench_sharded_c4(args, ctx):
                            "note": "SM clocks between the controller block starting to send its 25 doubles and having every peer's "
                                    "(includes waiting for the slowest rank's evaluation to finish: load imbalance shows up here)"}
     rec["timing"] = ("CUDA events around constructor (incl. the token exchange) + align() (which ends with its own read-back of the final "
-                     "state), clouds resident, max over ranks; the history / statistics reads that follow are outside (phases_ms_all lists "
-                     "them: seven 100-byte copies that take 1.5 ms or, on a busy host, 90)")
+                     "state), clouds resident, max over ranks; the history / statistics reads that follow are outside (phases_ms_all lists them)")
     return rec if rank == 0 else None
 
 
