@@ -549,8 +549,10 @@ __global__ void PPCR_SEARCH_BOUNDS k_search(const PairDev* __restrict__ pairs)
 constexpr int kQTaskPerQuery = 4096;
 constexpr int kQTaskCap = 8192;                  // leaf tasks per block of 128 queries (64 per query on average)
 // candidate positions per query.  128 for max_neighbours = 20 was tried: one 120k-point pair 6.2 -> 6.0 ms, but a batch of them
-// 403 -> 344 pairs/s (the slabs of six lanes crowd L2), so 64 for every m; PPCR_Q_CAND overrides it (tuning)
-PPCR_HD constexpr int search_q_cand(int /*max_nn*/) { return 64; }
+// 403 -> 344 pairs/s (the slabs of six lanes crowd L2).  Re-swept with the tight leaf boxes (round 2): 64 / 80 / 96 / 128 -> 15.5 /
+// 15.0 / 14.8 / 14.8 ms of search per registration on the 1M-point pair, a 120k-point pair alone 3.26 -> 3.01 ms at 96, batches and
+// the 10M-point pair unchanged: 96 for every m; PPCR_Q_CAND overrides it (tuning)
+PPCR_HD constexpr int search_q_cand(int /*max_nn*/) { return 96; }
 constexpr int kQNodeBits = 25;                   // task = query slot << 25 | node index
 constexpr uint32_t kQLowMask = (1u << kQNodeBits) - 1u;
 // The two queues of a block live in GLOBAL memory (a scratch slab per resident block, L2 resident, accessed with .cg
