@@ -2031,35 +2031,53 @@ ppcr_status ppcr_align_sharded(const float* src, int64_t n_src, const float* tgt
                 failed.store(1);
                 return false;
             };
-            // this rank's share of the source: runs r, r + n_dev, r + 2 n_dev, ... of kRun consecutive points
-            std::vector<float> share;
-            const int64_t n_runs = (n_src + kRun - 1) / kRun;
-            for (int64_t b = r; b < n_runs; b += n_dev) {
-                const int64_t lo = b * kRun, hi = std::min(n_src, lo + kRun);
-                share.insert(share.end(), src + 4 * lo, src + 4 * hi);
-            }
-            ppcr_options opt;
-            if (options) opt = *options; else ppcr_default_options(&opt);
-            opt.device = device_ids[r];
-            opt.stream = nullptr;
-            bool ok = note(ppcr_create_ex(share.empty() ? nullptr : share.data(), static_cast<int64_t>(share.size() / 4), tgt, n_tgt, params, &opt, &h));
-            if (ok && n_dev > 1) ok = note(ppcr_shard_export(h, r, n_dev, tokens.data() + static_cast<size_t>(r) * PPCR_SHARD_TOKEN_BYTES));
+            // Nothing may leave this thread as an exception (std::terminate), and both barriers must be reached whatever happens:
+            // every stage runs only while nobody has failed, inside its own try block.
+            auto stage = [&](auto&& body) {
+                if (failed.load()) return;
+                try {
+                    body();
+                } catch (const std::exception& e) {
+                    std::lock_guard<std::mutex> lock(err_mutex);
+                    if (first_error.code == PPCR_OK) first_error = StatusError{PPCR_ERR_INVALID, e.what()};
+                    failed.store(1);
+                } catch (...) {
+                    std::lock_guard<std::mutex> lock(err_mutex);
+                    if (first_error.code == PPCR_OK) first_error = StatusError{PPCR_ERR_CUDA, "unknown failure in a rank of ppcr_align_sharded"};
+                    failed.store(1);
+                }
+            };
+            stage([&] {
+                // this rank's share of the source: runs r, r + n_dev, r + 2 n_dev, ... of kRun consecutive points
+                std::vector<float> share;
+                const int64_t n_runs = (n_src + kRun - 1) / kRun;
+                for (int64_t b = r; b < n_runs; b += n_dev) {
+                    const int64_t lo = b * kRun, hi = std::min(n_src, lo + kRun);
+                    share.insert(share.end(), src + 4 * lo, src + 4 * hi);
+                }
+                ppcr_options opt;
+                if (options) opt = *options; else ppcr_default_options(&opt);
+                opt.device = device_ids[r];
+                opt.stream = nullptr;
+                if (note(ppcr_create_ex(share.empty() ? nullptr : share.data(), static_cast<int64_t>(share.size() / 4), tgt, n_tgt, params, &opt, &h)) &&
+                    n_dev > 1)
+                    note(ppcr_shard_export(h, r, n_dev, tokens.data() + static_cast<size_t>(r) * PPCR_SHARD_TOKEN_BYTES));
+            });
             barrier.wait();  // every token is written (or a rank has failed)
-            if (!failed.load() && n_dev > 1) ok = note(ppcr_shard_connect(h, tokens.data()));
+            stage([&] {
+                if (n_dev > 1) note(ppcr_shard_connect(h, tokens.data()));
+            });
             barrier.wait();  // every rank is connected: nobody starts writing into a mailbox whose owner is not ready
-            if (!failed.load()) ok = note(ppcr_align(h));
-            if (ok && !failed.load() && r == 0) {
+            stage([&] { note(ppcr_align(h)); });
+            stage([&] {
+                if (r != 0) return;
                 int32_t n = cap;
                 if (note(ppcr_history(h, out_T, &n))) *n_inout = n;
                 if (out_corr) {
-                    try {
-                        use_engine(h->eng);
-                        *out_corr = download_state(h->eng, 0).K_total;
-                    } catch (...) {
-                        note(PPCR_ERR_CUDA);
-                    }
+                    use_engine(h->eng);
+                    *out_corr = download_state(h->eng, 0).K_total;
                 }
-            }
+            });
             ppcr_destroy(h);
         };
         if (n_dev == 1) {
