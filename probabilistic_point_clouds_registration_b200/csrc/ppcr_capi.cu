@@ -162,6 +162,7 @@ static int search_cap(int max_nn)
 constexpr int kSearchQueuedMaxM = 32;  // k_search_q's shared-memory heap columns: m KiB per block on top of 35 KiB of queues
 constexpr size_t kEvalSmem = static_cast<size_t>(kNSum) * kEvalThreads * sizeof(double);  // per-thread moment columns
 constexpr int kDefaultLeafCap = 32;
+constexpr int kTreeSmallMax = 32768;  // targets up to this many points are built by one block in one launch
 constexpr int kEvalBatchBlocks = 4;  // evaluation blocks per SM of a batch lane (see pair_setup)
 
 // kernel-launch bookkeeping for ppcr_get_stage_times: every launch site outside the tick adds to the engine the
@@ -474,6 +475,18 @@ static void build_target_tree(Engine& E, Pair& P, int leaf_cap)
     P.nodes.reserve(static_cast<size_t>(g.n_nodes_cap) + 8);
     P.tree_counters.reserve(1);
     CK(cudaMemsetAsync(P.nodes.p, 0xff, (static_cast<size_t>(g.n_nodes_cap) + 8) * sizeof(TreeNode), st));
+    static const int small_max = getenv("PPCR_TREE_SMALL") ? atoi(getenv("PPCR_TREE_SMALL")) : kTreeSmallMax;  // (0: always level by level)
+    if (n <= small_max) {
+        k_tree_build_small<<<1, kTreeSmallThreads, 0, st>>>(P.nodes.p, n, g, P.sort_keys[1].p, P.tgt_sorted.p, P.tree_counters.p);
+        CK(cudaGetLastError());
+        note_launches(1);
+        P.dev.tree = g;
+        P.dev.nodes = P.nodes.p;
+        P.dev.tgt_sorted = P.tgt_sorted.p;
+        P.dev.tgt_raw = P.tgt_raw.p;
+        P.dev.inv_perm = P.inv_perm.p;
+        return;
+    }
     k_tree_root<<<1, 32, 0, st>>>(P.nodes.p, n, g, P.tree_counters.p);
     long long level_nodes = 1;
     for (int level = 0; level < kTreeBits; ++level) {
