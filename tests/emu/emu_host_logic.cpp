@@ -258,6 +258,33 @@ int64_t emu_tree_search(const float* src_xyzw, int64_t n_src, const float* tgt_x
     }
     for (int ni = 0; ni < std::min(n_nodes, g.n_nodes_cap); ++ni) tree_mark_leaf_children(nodes.data(), ni);
     for (int ni = 0; ni < std::min(n_nodes, g.n_nodes_cap); ++ni) tree_box_leaf(nodes.data(), pts.data(), ni);
+    if (getenv("EMU_CHECK_LEAF_BOXES")) {
+        // property behind the leaf boxes: for every boxed leaf and every query, the box bound never exceeds the float32
+        // distance (dist2_exact) of any point stored in the leaf -- so pruning on it cannot lose a neighbour
+        // walk the tree from the root so that leaves are identified by their parents' masks
+        std::vector<int> todo{0};
+        if (nodes[0].child >= 0)
+            while (!todo.empty()) {
+                const int ni = todo.back();
+                todo.pop_back();
+                const TreeNode n = nodes[static_cast<size_t>(ni)];
+                for (int c = 0; c < 8; ++c) {
+                    if (!((n.mask >> c) & 1)) continue;
+                    const int ch = n.child + c;
+                    if (!((n.mask >> (16 + c)) & 1)) {
+                        todo.push_back(ch);
+                        continue;
+                    }
+                    const TreeNode leaf = nodes[static_cast<size_t>(ch)];
+                    for (int64_t i = 0; i < n_src; ++i) {
+                        const float* q = src_xyzw + 4 * i;
+                        const float lb = leaf_box_lower_bound(leaf, q[0], q[1], q[2]);
+                        for (int j = leaf.begin; j < leaf.end; ++j)
+                            if (lb > dist2_exact(q[0], q[1], q[2], pts[static_cast<size_t>(j)].x, pts[static_cast<size_t>(j)].y, pts[static_cast<size_t>(j)].z)) return -2;
+                    }
+                }
+            }
+    }
     if (out_n_nodes) *out_n_nodes = n_nodes;
     int64_t total = 0;
     int stack[2 * kTreeStack];

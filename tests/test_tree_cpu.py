@@ -99,3 +99,42 @@ def test_warm_start_bound_does_not_change_the_result(emu, oracle):
             assert np.array_equal(gc, oc)
             valid = np.arange(m)[None, :] < oc[:, None]
             assert np.array_equal(gi[valid], oi[valid])
+
+
+def test_leaf_boxes_never_exceed_a_point_distance(emu, monkeypatch):
+    """Every leaf but a root leaf carries the bounding box of its points, and the searches prune a leaf whose box bound exceeds
+    the current bound.  That is exact only if the box bound never exceeds the float32 distance of any point inside, for queries
+    anywhere: inside the box, next to a face (differences of one ulp), far away, on clouds with coordinates of very different
+    magnitude.  emu_tree_search returns -2 when it finds a counter-example."""
+    import ctypes as C
+    monkeypatch.setenv("EMU_CHECK_LEAF_BOXES", "1")
+    rng = np.random.default_rng(7)
+    src, tgt, _ = synth.lidar_pair(17, 16, 400)
+    # queries displaced from target points along ONE axis: whenever such a point is the extreme of its leaf along that axis the
+    # box bound EQUALS its distance, so a bound that is one rounding too large shows up
+    base = tgt[rng.choice(len(tgt), 400, replace=False)]
+    axial = []
+    for axis in range(3):
+        for delta in (np.float32(3e-7), np.float32(1e-3), np.float32(0.3)):
+            for sign in (-1.0, 1.0):
+                q = base.copy()
+                q[:, axis] += np.float32(sign) * delta
+                axial.append(q)
+    far = src[:50].copy()
+    far[:, :3] *= 40.0
+    queries = np.concatenate([src[:150], far, tgt[:50]] + axial)
+    for scale, leaf in ((1.0, 32), (1.0, 4), (1000.0, 8), (1e-3, 8)):
+        t = tgt.copy()
+        t[:, :3] *= np.float32(scale)
+        q = queries.copy()
+        q[:, :3] *= np.float32(scale)
+        idx = np.full((len(q), 4), -1, dtype=np.int32)
+        d2 = np.zeros((len(q), 4), dtype=np.float32)
+        cnt = np.zeros(len(q), dtype=np.int32)
+        nn = C.c_int(0)
+        fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        emu.emu_tree_search.restype = C.c_int64
+        rc = emu.emu_tree_search(q.ctypes.data_as(fp), C.c_int64(len(q)), t.ctypes.data_as(fp), C.c_int64(len(t)), C.c_double(0.5 * scale),
+                                 C.c_int(4), C.c_int(leaf), C.c_int(2), None, idx.ctypes.data_as(ip), d2.ctypes.data_as(fp),
+                                 cnt.ctypes.data_as(ip), C.byref(nn))
+        assert rc >= 0, (scale, leaf, rc)
